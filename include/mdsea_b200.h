@@ -1,0 +1,192 @@
+/*
+ * mdsea_b200.h -- C ABI of the B200 (sm_100a) implementation of mdsea's
+ * ContinuousPotentialSolver step loop.
+ *
+ * The upstream reference (tpvasconcelos/mdsea) is pure Python/NumPy and has no FFI of
+ * its own; the entry points below are what a Python maintainer would bind with ctypes
+ * to replace the bodies of the methods cited next to each declaration (paths relative
+ * to the reference tree).  INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types cross this boundary.
+ *   - every array of particle data is float64, SoA, shape (ndim, N) row-major -- the
+ *     layout of the reference's r_vec / v_vec / acc (mdsea/simulator.py:54-70) and of one
+ *     HDF5 row of r_coords / v_coords (mdsea/core.py:236-238).
+ *   - host pointers unless stated otherwise; the caller owns every host buffer, the
+ *     library owns all device memory, streams and events (freed by mdsea_b200_destroy).
+ *   - every call returns MDSEA_OK (0) or a negative mdsea_status; the message for the
+ *     most recent failure on a context is available from mdsea_b200_last_error.
+ *   - a context is NOT thread-safe: one host thread drives one context (the reference
+ *     is single-threaded and synchronous).  Multi-GPU = one context per rank/process.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with MDSEA_ERR_CUDA.
+ */
+#ifndef MDSEA_B200_H
+#define MDSEA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDSEA_B200_ABI_VERSION 1
+
+typedef enum {
+    MDSEA_OK = 0,
+    MDSEA_ERR_BAD_ARG = -1,  /* invalid parameter / NULL pointer / unsupported combination */
+    MDSEA_ERR_CUDA = -2,     /* CUDA runtime error (no device, launch failure, OOM)       */
+    MDSEA_ERR_NCCL = -3,     /* NCCL error in the halo exchange / energy allreduce        */
+    MDSEA_ERR_STATE = -4,    /* call out of order (e.g. run before set_state)             */
+    MDSEA_ERR_NONFINITE = -5,/* reserved: NaN/Inf in the energy reduction (see first_nonfinite_step)   */
+    MDSEA_ERR_CAPACITY = -6, /* neighbour / ghost / migration buffer capacity exceeded   */
+    MDSEA_ERR_UNSUPPORTED = -7
+} mdsea_status;
+
+/* pair potential: the reference's bounded-Mie family, mdsea/potentials.py:15-64 */
+typedef enum {
+    MDSEA_POT_IDEAL = 0,      /* pf_ideal / ff_ideal  (potentials.py:33-35,62-64)            */
+    MDSEA_POT_BOUNDED_MIE = 1 /* pf_/ff_boundedmie; mie = a 0; lennardjones = m 12, n 6, a 0 */
+} mdsea_pot_kind;
+
+typedef enum { MDSEA_ALGO_VERLET = 0, MDSEA_ALGO_SIMPLE = 1 } mdsea_algorithm; /* simulator.py:530-544 */
+typedef enum { MDSEA_FP64 = 0, MDSEA_FP32 = 1 } mdsea_precision;
+
+typedef struct mdsea_ctx mdsea_ctx;
+
+typedef struct {
+    int32_t abi_version;       /* MDSEA_B200_ABI_VERSION */
+    int32_t ndim;              /* 1, 2 or 3 (SysManager.NDIM, core.py:68)                      */
+    int64_t num_particles;     /* global N (SysManager.NUM_PARTICLES)                           */
+    double  boxlen;            /* SysManager.LEN_BOX (core.py:113-115)                          */
+    double  mass;              /* SysManager.MASS                                               */
+    double  radius;            /* SysManager.RADIUS_PARTICLE (hard-wall clamp, simulator.py:168-179) */
+    double  dt;                /* integration step (simulator.py:86-87)                         */
+    int32_t pbc;               /* 1: apply_pbc (simulator.py:156-166); 0: apply_hbc (:168-179)  */
+    int32_t algorithm;         /* mdsea_algorithm                                               */
+    double  restitution;       /* restitution_coeff; only used by the hard-wall reflection      */
+    int32_t pot_kind;          /* mdsea_pot_kind                                                */
+    int32_t precision;         /* mdsea_precision: arithmetic of the PAIR math; state stays f64 */
+    double  epsilon, sigma;    /* Potential.kwargs (potentials.py:109-122)                      */
+    double  mie_m, mie_n, mie_a;
+    double  r_cutoff;          /* <= 0: all pairs, no cutoff (the reference's only working mode).
+                                  > 0 : EXTENSION -- plain truncation, pair counted iff dist < r_cutoff
+                                  (strict, as simulator.py:283), cell list + Verlet list, 3-D pbc only */
+    double  skin;              /* Verlet skin; list radius = r_cutoff + skin                    */
+    int32_t force_evals_per_step; /* 2: evaluate a(r) twice per verlet step like simulator.py:540,544;
+                                     1: reuse a(t+dt) as the next step's a(t) (pbc only; identical
+                                        positions modulo the wrap, differences ~1e-15)            */
+    int32_t ring_rows;         /* rows (steps) buffered on the device between flushes (k); >= 1 */
+    int32_t device;            /* CUDA device ordinal                                           */
+    int32_t max_neighbors;     /* per-particle neighbour capacity for the cutoff path; 0 = auto */
+    /* spatial domain decomposition (cutoff path only).  world == 1: single GPU.              */
+    int32_t rank, world;
+    int32_t proc_grid[3];      /* ranks along x,y,z; product == world                           */
+    int32_t reserved[8];
+} mdsea_params;
+
+/* per-call inputs of mdsea_b200_run */
+typedef struct {
+    int32_t nsteps;               /* 1..ring_rows                                                   */
+    int32_t record_coords;        /* 1: buffer r/v rows of every step on the device (update_files, simulator.py:143-150) */
+    double  k_boltzmann;          /* Config.k_boltzmann at call time (simulator.py:238)            */
+    double  gravity_acceleration; /* Config.gravity_acceleration if gravity else 0 (simulator.py:201-205) */
+    const double *quench_targets; /* NULL or [nsteps][2]: target temperatures of the (up to two) _quench
+                                     calls of each step in call order (isothermal first, then the
+                                     QUENCH_STEP entry; simulator.py:185-195); NaN = no quench     */
+} mdsea_run_args;
+
+/* caller-owned host buffers receiving the rows of one run() call, in HDF5 row layout
+ * (core.py:236-242).  r/v may be NULL (energies only).  Pinned memory makes the copies
+ * asynchronous with respect to the host. */
+typedef struct {
+    double *r;    /* [nsteps][ndim][N]  -> r_coords rows */
+    double *v;    /* [nsteps][ndim][N]  -> v_coords rows */
+    double *pe;   /* [nsteps]           -> pot_energy    */
+    double *ke;   /* [nsteps]           -> kin_energy    */
+    double *temp; /* [nsteps]           -> temp          */
+} mdsea_rows;
+
+typedef struct {
+    int64_t steps;               /* steps advanced since create                                  */
+    int64_t force_evals;         /* force evaluations launched                                   */
+    int64_t pair_evals_unique;   /* unique (i<j) pair interactions inside the cutoff, summed over evals */
+    int64_t pair_evals_executed; /* directed pair evaluations the kernels executed (list entries / N*N) */
+    int64_t kernel_launches;     /* kernels of this library launched since create                */
+    int64_t list_rebuilds;       /* cell binning + neighbour list rebuilds                        */
+    int64_t n_local, n_ghost;    /* owned / ghost particles on this rank (cutoff path)            */
+    int64_t nbr_entries;         /* directed entries in the current neighbour list                */
+    double  ms_force, ms_integrate, ms_rebuild, ms_comm; /* CUDA-event time sums when profiling is on */
+} mdsea_stats;
+
+const char *mdsea_b200_version(void);
+
+/* replaces _BaseSimulator.__post_init__ device-side state (simulator.py:51-97); the O(N^2)
+ * pair table of :122-137 is deliberately not reproduced. */
+int mdsea_b200_create(const mdsea_params *params, mdsea_ctx **out);
+void mdsea_b200_destroy(mdsea_ctx *ctx);
+const char *mdsea_b200_last_error(const mdsea_ctx *ctx); /* ctx may be NULL: last create() error */
+
+/* r_vec / v_vec upload (simulator.py:54-59): (ndim, N) float64 host arrays, GLOBAL particle order.
+ * With world > 1 every rank passes the full arrays and keeps the particles it owns. */
+int mdsea_b200_set_state(mdsea_ctx *ctx, const double *r_soa, const double *v_soa);
+/* download of r_vec, v_vec, acc in original particle order; any pointer may be NULL.
+ * With world > 1 each rank fills only the entries of particles it owns (others untouched)
+ * and returns their ids in `owned_ids` (capacity N, may be NULL) / count in *n_owned. */
+int mdsea_b200_get_state(mdsea_ctx *ctx, double *r_soa, double *v_soa, double *acc_soa,
+                         int64_t *owned_ids, int64_t *n_owned);
+
+/* replaces `for step in simrange: advance(); update_files()` (simulator.py:583-586) for
+ * args->nsteps consecutive steps: apply_bc, algorithm_verlet/simple, apply_field,
+ * apply_special, update_energies (simulator.py:560-568) and the buffering of the five
+ * dataset rows; then copies the buffered rows to `rows`.  Blocks until the copies landed. */
+int mdsea_b200_run(mdsea_ctx *ctx, const mdsea_run_args *args, const mdsea_rows *rows);
+/* same, but returns after enqueueing; mdsea_b200_wait blocks until rows are in host memory. */
+int mdsea_b200_run_async(mdsea_ctx *ctx, const mdsea_run_args *args, const mdsea_rows *rows);
+int mdsea_b200_wait(mdsea_ctx *ctx);
+
+/* replaces _BaseSimulator.update_acc (simulator.py:295-311) on the current positions: evaluates
+ * the accelerations, keeps them as ctx state (sim.acc) and optionally returns them and the mean
+ * potential energy of update_mean_pe (simulator.py:247-250). acc_soa / mean_pe may be NULL. */
+int mdsea_b200_update_acc(mdsea_ctx *ctx, double *acc_soa, double *mean_pe);
+
+/* replaces _BaseSimulator.update_dists(radius=None) (simulator.py:257-280) for small N:
+ * dists[P], drunits[P][ndim], P = N(N-1)/2 in itertools.combinations order (simulator.py:122-126). */
+int mdsea_b200_update_dists(mdsea_ctx *ctx, double *dists, double *drunits);
+
+/* cutoff-path test hooks (bit-exact contracts):
+ *   cells:     cell_of[i] = canonical linear cell id of particle i; order[k] = id of the k-th
+ *              particle after the stable (cell id, particle id) sort.
+ *   neighbors: CSR over ORIGINAL particle ids, each row ascending ids j != i with
+ *              |r_i - r_j|^2_minimg < (r_cutoff+skin)^2 at the last rebuild.
+ * Two-call pattern: pass idx == NULL to obtain *n_entries first. offsets has N+1 entries. */
+int mdsea_b200_get_cells(mdsea_ctx *ctx, int32_t *cell_of, int32_t *order, int32_t ncell_dim[3]);
+int mdsea_b200_get_neighbors(mdsea_ctx *ctx, int64_t *n_entries, int64_t *offsets, int32_t *idx);
+
+/* seeds self.temp / temp_init (simulator.py:79-80) -- the value written to the `temp` dataset until a
+ * quench changes it; reset_ke != 0 puts mean_ke back to None (simulator.py:75). */
+int mdsea_b200_set_temperature(mdsea_ctx *ctx, double temp, int32_t reset_ke);
+
+int mdsea_b200_get_stats(mdsea_ctx *ctx, mdsea_stats *out);
+/* index of the first step whose energies were NaN/Inf, or -1.  The reference writes NaN rows
+ * silently; this library does the same and lets the host decide. */
+int mdsea_b200_first_nonfinite_step(mdsea_ctx *ctx, int64_t *step);
+/* 1: record CUDA-event timings per kernel family into mdsea_stats.ms_* (adds event overhead) */
+int mdsea_b200_set_profiling(mdsea_ctx *ctx, int32_t on);
+/* the CUDA stream the kernels are launched on (cudaStream_t as void*), for event timing by the caller */
+void *mdsea_b200_stream(mdsea_ctx *ctx);
+
+/* multi-GPU plumbing: rank 0 obtains an id (128 bytes), the host side broadcasts it
+ * (torch.distributed / file / env), every rank calls comm_init before set_state. */
+int mdsea_b200_nccl_unique_id(void *out128);
+int mdsea_b200_comm_init(mdsea_ctx *ctx, const void *unique_id128);
+
+/* device micro-benchmarks used by bench.py for the roofline denominators that
+ * MEASURED_PEAKS.json does not hold: dependent-free FMA throughput of the fp32 / fp64
+ * CUDA-core pipes in TFLOP/s (FMA = 2 flop). */
+int mdsea_b200_measure_fma_peak(int32_t device, int32_t fp64, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDSEA_B200_H */

@@ -1,0 +1,391 @@
+// K1: tiled all-pairs force + potential-energy kernels (small N, no neighbour list).
+//
+// Replaces, per force evaluation, the reference's update_dists (simulator.py:257-280: pair table
+// gathers, minimum image through rint of a true division, norm), Potential.force
+// (potentials.py:43-48) and the bincount scatter of update_acc (simulator.py:295-311), plus the
+// sum of update_mean_pe (simulator.py:247-250).  Nothing of size O(N^2) is ever stored:
+// every thread owns one particle i, j-particles are staged tile by tile in shared memory
+// (broadcast reads), and the j range is split over blockIdx.y so that N = 4096 still fills
+// 148 SMs.  Each (i, j-chunk) partial force is written once, coalesced, to
+// fpart[chunk][dim][i]; the integrator sums the chunks in fixed order (no atomics, run-to-run
+// deterministic).  Sign convention: dr = r_j - r_i, a_i += dr * (dV/dr)/(r m)  (simulator.py:266,301-305).
+#include "ctx.h"
+
+#define AP_TI 128  // particles i per block == j tile length
+
+// ---------------------------------------------------------------------------------------------
+// pair kernels (sqrt-free where the exponents allow it)
+//   s = (dV/dr) / (r m)   so that   a_i += dr * s
+//   u = V / (lambda eps)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T md_ipow(T b, int e) {
+    T r = T(1);
+    while (e > 0) {
+        if (e & 1) r *= b;
+        b *= b;
+        e >>= 1;
+    }
+    return r;
+}
+
+struct PotF64 {
+    double c;      // LJ: 6 lambda eps / m ; Mie: lambda eps / m
+    double sigma, sigma2, a2, m, n;
+    int    mi, ni;
+};
+struct PotF32 {
+    float c;       // same as PotF64::c but divided by the fixed-point unit h (forces come out in real units)
+    float sigma_s, sigma2_s, a2_s, m, n;  // lengths in fixed-point units
+    int   mi, ni;
+};
+
+template <int POTK>
+__device__ __forceinline__ void md_pair(double r2, bool ok, const PotF64 &P, double &s, double &u) {
+    if (POTK == POTF_LJ) {
+        double inv = ok ? md_rcp(r2) : 0.0;
+        double t2 = P.sigma2 * inv;
+        double t6 = t2 * t2 * t2;
+        double w = fma(-2.0, t6, 1.0);
+        s = (P.c * inv) * (t6 * w);
+        u = fma(t6, t6, -t6);
+    } else {
+        double aprs = P.a2 + r2;
+        double inv = ok ? md_rcp(aprs) : 0.0;
+        double tm, tn;
+        if (P.mi >= 0 && P.ni >= 0 && !((P.mi | P.ni) & 1)) {
+            double t2 = P.sigma2 * inv;
+            tm = md_ipow(t2, P.mi >> 1);
+            tn = md_ipow(t2, P.ni >> 1);
+        } else {
+            double t = P.sigma * sqrt(inv);
+            tm = (P.mi >= 0) ? md_ipow(t, P.mi) : pow(t, P.m);
+            tn = (P.ni >= 0) ? md_ipow(t, P.ni) : pow(t, P.n);
+        }
+        tm = ok ? tm : 0.0;
+        tn = ok ? tn : 0.0;
+        s = P.c * inv * (P.n * tn - P.m * tm);
+        u = tm - tn;
+    }
+}
+
+template <int POTK>
+__device__ __forceinline__ void md_pair(float r2, bool ok, const PotF32 &P, float &s, float &u) {
+    if (POTK == POTF_LJ) {
+        float inv = ok ? __frcp_rn(r2) : 0.0f;
+        float t2 = P.sigma2_s * inv;
+        float t6 = t2 * t2 * t2;
+        float w = fmaf(-2.0f, t6, 1.0f);
+        s = (P.c * inv) * (t6 * w);
+        u = fmaf(t6, t6, -t6);
+    } else {
+        float aprs = P.a2_s + r2;
+        float inv = ok ? __frcp_rn(aprs) : 0.0f;
+        float tm, tn;
+        if (P.mi >= 0 && P.ni >= 0 && !((P.mi | P.ni) & 1)) {
+            float t2 = P.sigma2_s * inv;
+            tm = md_ipow(t2, P.mi >> 1);
+            tn = md_ipow(t2, P.ni >> 1);
+        } else {
+            float t = P.sigma_s * sqrtf(inv);
+            tm = (P.mi >= 0) ? md_ipow(t, P.mi) : powf(t, P.m);
+            tn = (P.ni >= 0) ? md_ipow(t, P.ni) : powf(t, P.n);
+        }
+        tm = ok ? tm : 0.0f;
+        tn = ok ? tn : 0.0f;
+        s = P.c * inv * (P.n * tn - P.m * tm);
+        u = tm - tn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 kernel
+// ---------------------------------------------------------------------------------------------
+template <int NDIM, int POTK, bool CUT, bool PBC>
+__global__ void __launch_bounds__(AP_TI)
+k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF64 P, double rc2,
+               double *__restrict__ fpart, double *__restrict__ pe_part,
+               unsigned long long *__restrict__ cnt_part) {
+    __shared__ double sj[NDIM][AP_TI];
+    __shared__ double red[32];
+    __shared__ unsigned redu[32];
+
+    const int  i = blockIdx.x * AP_TI + threadIdx.x;
+    const bool active = i < n;
+    const int  ic = active ? i : n - 1;
+    double ri[NDIM], f[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        ri[d] = r[(size_t)d * n + ic];
+        f[d] = 0.0;
+    }
+    double   pe = 0.0;
+    unsigned cnt = 0;
+    const int j0 = blockIdx.y * jchunk;
+    const int j1 = min(n, j0 + jchunk);
+
+    for (int jt = j0; jt < j1; jt += AP_TI) {
+        __syncthreads();
+        const int jl = jt + threadIdx.x;
+        if (jl < j1) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) sj[d][threadIdx.x] = r[(size_t)d * n + jl];
+        }
+        __syncthreads();
+        const int nj = min(AP_TI, j1 - jt);
+#pragma unroll 4
+        for (int k = 0; k < nj; ++k) {
+            double dd[NDIM], r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                double x = sj[d][k] - ri[d];
+                if (PBC) x = md_minimg(x, box.L, box.invL);
+                dd[d] = x;
+                r2 = fma(x, x, r2);
+            }
+            bool ok = (jt + k) != ic;
+            if (CUT) ok = ok && (r2 < rc2);
+            double s, u;
+            md_pair<POTK>(r2, ok, P, s, u);
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) f[d] = fma(dd[d], s, f[d]);
+            pe += u;
+            cnt += ok ? 1u : 0u;
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) fpart[((size_t)blockIdx.y * NDIM + d) * n + i] = f[d];
+    } else {
+        pe = 0.0;
+        cnt = 0;
+    }
+    double   bpe = md_block_sum(pe, red);
+    unsigned bc = md_block_sum(cnt, redu);
+    if (threadIdx.x == 0) {
+        const int b = blockIdx.y * gridDim.x + blockIdx.x;
+        pe_part[b] = bpe;
+        cnt_part[b] = bc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 kernel: positions as 32-bit fixed point (unit h = L/2^32 periodic, L/2^31 walls).
+// The integer subtraction of two fixed-point coordinates is exact and -- for the periodic box --
+// wraps to the minimum image for free; I2F then rounds RELATIVE to the separation, which keeps
+// the pair geometry at ~6e-8 relative where fp32 absolute coordinates would lose 1e-6 * L.
+// Pairs within 2^12 units of the half-box tie, and pairs within 2e-6 (relative) of the cutoff,
+// are re-evaluated from the fp64 positions so that the image and in/out-of-cutoff decisions are
+// exactly those of the fp64 path.  Per-tile fp32 partial sums are folded into fp64 accumulators.
+// ---------------------------------------------------------------------------------------------
+template <int NDIM, int POTK, bool CUT, bool PBC>
+__global__ void __launch_bounds__(AP_TI)
+k_allpairs_f32(const uint32_t *__restrict__ q, const double *__restrict__ r64, int n, int jchunk, BoxDev box,
+               PotF32 P, float rc2s, double rc2, double inv_h, double *__restrict__ fpart,
+               double *__restrict__ pe_part, unsigned long long *__restrict__ cnt_part) {
+    __shared__ uint32_t sj[NDIM][AP_TI];
+    __shared__ double   red[32];
+    __shared__ unsigned redu[32];
+
+    const int  i = blockIdx.x * AP_TI + threadIdx.x;
+    const bool active = i < n;
+    const int  ic = active ? i : n - 1;
+    uint32_t qi[NDIM];
+    double   F[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        qi[d] = q[(size_t)d * n + ic];
+        F[d] = 0.0;
+    }
+    double   PE = 0.0;
+    unsigned cnt = 0;
+    const int j0 = blockIdx.y * jchunk;
+    const int j1 = min(n, j0 + jchunk);
+    const float cut_lo = rc2s * (1.0f - 2e-6f), cut_hi = rc2s * (1.0f + 2e-6f);
+
+    for (int jt = j0; jt < j1; jt += AP_TI) {
+        __syncthreads();
+        const int jl = jt + threadIdx.x;
+        if (jl < j1) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) sj[d][threadIdx.x] = q[(size_t)d * n + jl];
+        }
+        __syncthreads();
+        const int nj = min(AP_TI, j1 - jt);
+        float f[NDIM], pe = 0.0f;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) f[d] = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < nj; ++k) {
+            float dd[NDIM], r2 = 0.0f;
+            bool  slow = false;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                const int di = (int)(sj[d][k] - qi[d]);
+                if (PBC) slow = slow || ((uint32_t)abs(di) >= 0x7ffff000u);
+                const float x = (float)di;
+                dd[d] = x;
+                r2 = fmaf(x, x, r2);
+            }
+            bool ok = (jt + k) != ic;
+            if (CUT) {
+                slow = slow || (r2 > cut_lo && r2 < cut_hi);
+                ok = ok && (r2 < rc2s);
+            }
+            if (__builtin_expect(slow, 0)) {
+                double r2d = 0.0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    double x = r64[(size_t)d * n + (jt + k)] - r64[(size_t)d * n + ic];
+                    if (PBC) x = md_minimg(x, box.L, box.invL);
+                    r2d = fma(x, x, r2d);
+                    dd[d] = (float)(x * inv_h);
+                }
+                r2 = (float)(r2d * inv_h * inv_h);
+                ok = (jt + k) != ic;
+                if (CUT) ok = ok && (r2d < rc2);
+            }
+            float s, u;
+            md_pair<POTK>(r2, ok, P, s, u);
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) f[d] = fmaf(dd[d], s, f[d]);
+            pe += u;
+            cnt += ok ? 1u : 0u;
+        }
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) F[d] += (double)f[d];
+        PE += (double)pe;
+    }
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) fpart[((size_t)blockIdx.y * NDIM + d) * n + i] = F[d];
+    } else {
+        PE = 0.0;
+        cnt = 0;
+    }
+    double   bpe = md_block_sum(PE, red);
+    unsigned bc = md_block_sum(cnt, redu);
+    if (threadIdx.x == 0) {
+        const int b = blockIdx.y * gridDim.x + blockIdx.x;
+        pe_part[b] = bpe;
+        cnt_part[b] = bc;
+    }
+}
+
+// positions -> 32-bit fixed point (flat over ndim*n elements)
+__global__ void k_to_fixed(const double *__restrict__ r, uint32_t *__restrict__ q, size_t E, double scale) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) q[e] = (uint32_t)(unsigned long long)__double2ll_rn(r[e] * scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int md_allpairs_setup(mdsea_ctx *c) {
+    const int n = (int)c->n;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->p.device);
+    c->ap_ti = AP_TI;
+    c->ap_blocks_x = md_div_up(n, AP_TI);
+    // j split: enough blocks for ~8 resident 128-thread CTAs per SM, a whole multiple of the SM count,
+    // but never chunks shorter than one tile.
+    int want = sms * 8;
+    int nsplit = want / c->ap_blocks_x;
+    if (nsplit < 1) nsplit = 1;
+    int max_split = md_div_up(n, AP_TI);
+    if (nsplit > max_split) nsplit = max_split;
+    c->ap_nsplit = nsplit;
+    c->ap_jchunk = md_div_up(n, nsplit);
+    c->ap_nsplit = md_div_up(n, c->ap_jchunk);
+    c->n_pe_part = c->ap_blocks_x * c->ap_nsplit;
+    MD_CUDA(c, cudaMalloc(&c->d_fpart, sizeof(double) * c->E * c->ap_nsplit));
+    MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
+    MD_CUDA(c, cudaMalloc(&c->d_cnt_part, sizeof(unsigned long long) * c->n_pe_part));
+    MD_CUDA(c, cudaMemset(c->d_pe_part, 0, sizeof(double) * c->n_pe_part));
+    MD_CUDA(c, cudaMemset(c->d_cnt_part, 0, sizeof(unsigned long long) * c->n_pe_part));
+    if (c->p.precision == MDSEA_FP32) MD_CUDA(c, cudaMalloc(&c->d_rhi, sizeof(uint32_t) * c->E));
+    return MDSEA_OK;
+}
+
+template <int NDIM, int POTK, bool CUT, bool PBC>
+static void launch_f64(mdsea_ctx *c, dim3 grid, const PotF64 &P, double rc2) {
+    k_allpairs_f64<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(
+        c->d_r, (int)c->n, c->ap_jchunk, c->box, P, rc2, c->d_fpart, c->d_pe_part, c->d_cnt_part);
+}
+template <int NDIM, int POTK, bool CUT, bool PBC>
+static void launch_f32(mdsea_ctx *c, dim3 grid, const PotF32 &P, float rc2s, double rc2, double inv_h) {
+    k_allpairs_f32<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(
+        (const uint32_t *)c->d_rhi, c->d_r, (int)c->n, c->ap_jchunk, c->box, P, rc2s, rc2, inv_h, c->d_fpart,
+        c->d_pe_part, c->d_cnt_part);
+}
+
+#define AP_DISPATCH(LAUNCH, ...)                                                              \
+    do {                                                                                      \
+        const bool cut = c->p.r_cutoff > 0, pbc = c->box.pbc != 0;                            \
+        const int  pk = c->pot.fast;                                                          \
+        const int  key = (c->ndim - 1) * 8 + (pk == POTF_LJ ? 0 : 4) + (cut ? 2 : 0) + (pbc ? 1 : 0); \
+        switch (key) {                                                                        \
+            case 0: LAUNCH<1, POTF_LJ, false, false>(__VA_ARGS__); break;                     \
+            case 1: LAUNCH<1, POTF_LJ, false, true>(__VA_ARGS__); break;                      \
+            case 2: LAUNCH<1, POTF_LJ, true, false>(__VA_ARGS__); break;                      \
+            case 3: LAUNCH<1, POTF_LJ, true, true>(__VA_ARGS__); break;                       \
+            case 4: LAUNCH<1, POTF_MIE, false, false>(__VA_ARGS__); break;                    \
+            case 5: LAUNCH<1, POTF_MIE, false, true>(__VA_ARGS__); break;                     \
+            case 6: LAUNCH<1, POTF_MIE, true, false>(__VA_ARGS__); break;                     \
+            case 7: LAUNCH<1, POTF_MIE, true, true>(__VA_ARGS__); break;                      \
+            case 8: LAUNCH<2, POTF_LJ, false, false>(__VA_ARGS__); break;                     \
+            case 9: LAUNCH<2, POTF_LJ, false, true>(__VA_ARGS__); break;                      \
+            case 10: LAUNCH<2, POTF_LJ, true, false>(__VA_ARGS__); break;                     \
+            case 11: LAUNCH<2, POTF_LJ, true, true>(__VA_ARGS__); break;                      \
+            case 12: LAUNCH<2, POTF_MIE, false, false>(__VA_ARGS__); break;                   \
+            case 13: LAUNCH<2, POTF_MIE, false, true>(__VA_ARGS__); break;                    \
+            case 14: LAUNCH<2, POTF_MIE, true, false>(__VA_ARGS__); break;                    \
+            case 15: LAUNCH<2, POTF_MIE, true, true>(__VA_ARGS__); break;                     \
+            case 16: LAUNCH<3, POTF_LJ, false, false>(__VA_ARGS__); break;                    \
+            case 17: LAUNCH<3, POTF_LJ, false, true>(__VA_ARGS__); break;                     \
+            case 18: LAUNCH<3, POTF_LJ, true, false>(__VA_ARGS__); break;                     \
+            case 19: LAUNCH<3, POTF_LJ, true, true>(__VA_ARGS__); break;                      \
+            case 20: LAUNCH<3, POTF_MIE, false, false>(__VA_ARGS__); break;                   \
+            case 21: LAUNCH<3, POTF_MIE, false, true>(__VA_ARGS__); break;                    \
+            case 22: LAUNCH<3, POTF_MIE, true, false>(__VA_ARGS__); break;                    \
+            default: LAUNCH<3, POTF_MIE, true, true>(__VA_ARGS__); break;                     \
+        }                                                                                     \
+    } while (0)
+
+int md_allpairs_force(mdsea_ctx *c) {
+    const dim3 grid(c->ap_blocks_x, c->ap_nsplit);
+    const PotDev &pd = c->pot;
+    const double rc2 = c->p.r_cutoff > 0 ? c->p.r_cutoff * c->p.r_cutoff : 0.0;
+    if (c->profiling) cudaEventRecord(c->ev_a, c->stream);
+    if (c->p.precision == MDSEA_FP64) {
+        PotF64 P;
+        P.c = (pd.fast == POTF_LJ ? 6.0 : 1.0) * pd.lam_eps * pd.inv_mass;
+        P.sigma = pd.sigma; P.sigma2 = pd.sigma2; P.a2 = pd.a2; P.m = pd.m; P.n = pd.n; P.mi = pd.mi; P.ni = pd.ni;
+        AP_DISPATCH(launch_f64, c, grid, P, rc2);
+        c->stats.kernel_launches += 1;
+    } else {
+        const double units = c->box.pbc ? 4294967296.0 : 2147483648.0;
+        const double h = c->box.L / units, inv_h = units / c->box.L;
+        k_to_fixed<<<md_div_up((long long)c->E, 256), 256, 0, c->stream>>>(c->d_r, (uint32_t *)c->d_rhi, c->E, inv_h);
+        PotF32 P;
+        P.c = (float)((pd.fast == POTF_LJ ? 6.0 : 1.0) * pd.lam_eps * pd.inv_mass * inv_h);
+        P.sigma_s = (float)(pd.sigma * inv_h);
+        P.sigma2_s = (float)(pd.sigma2 * inv_h * inv_h);
+        P.a2_s = (float)(pd.a2 * inv_h * inv_h);
+        P.m = (float)pd.m; P.n = (float)pd.n; P.mi = pd.mi; P.ni = pd.ni;
+        (void)h;
+        AP_DISPATCH(launch_f32, c, grid, P, (float)(rc2 * inv_h * inv_h), rc2, inv_h);
+        c->stats.kernel_launches += 2;
+    }
+    if (c->profiling) {
+        cudaEventRecord(c->ev_b, c->stream);
+        cudaEventSynchronize(c->ev_b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+        c->stats.ms_force += ms;
+    }
+    MD_CUDA(c, cudaGetLastError());
+    c->stats.force_evals += 1;
+    c->stats.pair_evals_executed += (long long)c->n * (long long)c->n;
+    return MDSEA_OK;
+}

@@ -1,0 +1,464 @@
+// C ABI of libmdsea_b200 (include/mdsea_b200.h): context life cycle, state transfer and the step loop.
+#include <math.h>
+#include <string.h>
+
+#include "ctx.h"
+
+static std::string g_err;
+std::string &md_global_error() { return g_err; }
+void md_set_error(mdsea_ctx *ctx, const char *msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+}
+
+extern "C" const char *mdsea_b200_version(void) { return "mdsea_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *mdsea_b200_last_error(const mdsea_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+static int bad(mdsea_ctx *c, const char *m) {
+    md_set_error(c, m);
+    return MDSEA_ERR_BAD_ARG;
+}
+
+static int int_exponent(double x) {
+    if (x >= 0 && x <= 64 && floor(x) == x) return (int)x;
+    return -1;
+}
+
+extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
+    if (!p || !out) return bad(nullptr, "create: NULL argument");
+    *out = nullptr;
+    if (p->abi_version != MDSEA_B200_ABI_VERSION) return bad(nullptr, "create: abi_version mismatch");
+    if (p->ndim < 1 || p->ndim > 3) return bad(nullptr, "create: ndim must be 1, 2 or 3");
+    if (p->num_particles < 1 || p->num_particles > 2000000000LL) return bad(nullptr, "create: num_particles out of range");
+    if (!(p->boxlen > 0) || !(p->mass > 0) || !isfinite(p->dt)) return bad(nullptr, "create: boxlen/mass/dt invalid");
+    if (p->algorithm != MDSEA_ALGO_VERLET && p->algorithm != MDSEA_ALGO_SIMPLE) return bad(nullptr, "create: unknown algorithm");
+    if (p->precision != MDSEA_FP64 && p->precision != MDSEA_FP32) return bad(nullptr, "create: unknown precision");
+    if (p->pot_kind != MDSEA_POT_IDEAL && p->pot_kind != MDSEA_POT_BOUNDED_MIE) return bad(nullptr, "create: unknown pot_kind");
+    if (p->ring_rows < 1) return bad(nullptr, "create: ring_rows must be >= 1");
+    if (p->force_evals_per_step != 1 && p->force_evals_per_step != 2) return bad(nullptr, "create: force_evals_per_step must be 1 or 2");
+    if (p->world < 1 || p->rank < 0 || p->rank >= p->world) return bad(nullptr, "create: bad rank/world");
+    if (p->pot_kind == MDSEA_POT_BOUNDED_MIE && !(p->mie_m != p->mie_n && p->mie_n > 0 && p->mie_m > 0))
+        return bad(nullptr, "create: Mie exponents must be positive and different");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        md_set_error(nullptr, "create: no CUDA device available (this library has no CPU fallback)");
+        return MDSEA_ERR_CUDA;
+    }
+    if (p->device < 0 || p->device >= ndev) return bad(nullptr, "create: device ordinal out of range");
+
+    mdsea_ctx *c = new mdsea_ctx();
+    c->p = *p;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->ndim = p->ndim;
+    c->n_global = p->num_particles;
+    c->n = p->num_particles;
+    c->E = (size_t)c->ndim * (size_t)c->n;
+    c->ring = p->ring_rows;
+
+    // potential constants (potentials.py:15-19,43-48)
+    PotDev &pd = c->pot;
+    memset(&pd, 0, sizeof(pd));
+    pd.inv_mass = 1.0 / p->mass;
+    if (p->pot_kind == MDSEA_POT_IDEAL) {
+        pd.fast = POTF_IDEAL;
+    } else {
+        const double m = p->mie_m, n = p->mie_n;
+        const double lam = (m / (m - n)) * pow(m / n, n / (m - n));
+        pd.lam_eps = lam * p->epsilon;
+        pd.sigma = p->sigma;
+        pd.sigma2 = p->sigma * p->sigma;
+        pd.a2 = p->mie_a * p->mie_a;
+        pd.m = m;
+        pd.n = n;
+        pd.mi = int_exponent(m);
+        pd.ni = int_exponent(n);
+        pd.fast = (m == 12.0 && n == 6.0 && p->mie_a == 0.0) ? POTF_LJ : POTF_MIE;
+    }
+    BoxDev &b = c->box;
+    b.L = p->boxlen;
+    b.invL = 1.0 / p->boxlen;
+    b.halfL = 0.5 * p->boxlen;
+    b.Lh = (float)p->boxlen;
+    b.Ll = (float)(p->boxlen - (double)b.Lh);
+    b.invLf = (float)(1.0 / p->boxlen);
+    b.pbc = p->pbc ? 1 : 0;
+
+    c->cutoff_path = false;
+    if (p->r_cutoff > 0 && pd.fast != POTF_IDEAL) {
+        // the cell/neighbour-list path needs a 3-D periodic box with at least 3 cells per side
+        const double rl = p->r_cutoff + (p->skin > 0 ? p->skin : 0.0);
+        const int nc = (int)floor(p->boxlen / rl);
+        c->cutoff_path = (p->ndim == 3 && p->pbc && nc >= 3);
+    }
+    if (p->world > 1 && !c->cutoff_path) {
+        delete c;
+        return bad(nullptr, "create: world > 1 needs the cutoff path (3-D, pbc, >= 3 cells per side); all-pairs runs are replicas only");
+    }
+    if (p->num_particles > 2000000 && !c->cutoff_path) {
+        delete c;
+        return bad(nullptr, "create: all-pairs mode is limited to 2e6 particles; set r_cutoff for the cell-list path");
+    }
+
+#define CK(expr)                                                                               \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            char _b[512];                                                                      \
+            snprintf(_b, sizeof(_b), "create: CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                                  \
+            md_set_error(nullptr, _b);                                                         \
+            mdsea_b200_destroy(c);                                                             \
+            return MDSEA_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_batch_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+    CK(cudaEventCreate(&c->ev_a));
+    CK(cudaEventCreate(&c->ev_b));
+    CK(cudaMalloc(&c->d_pe_rows, sizeof(double) * c->ring));
+    CK(cudaMalloc(&c->d_ke_rows, sizeof(double) * c->ring));
+    CK(cudaMalloc(&c->d_temp_rows, sizeof(double) * c->ring));
+    CK(cudaMalloc(&c->d_quench, sizeof(double) * 2 * (c->ring + 1)));
+    CK(cudaMalloc(&c->d_sc, sizeof(StepScalars)));
+    CK(cudaMallocHost(&c->h_sc, sizeof(StepScalars)));
+    CK(cudaMallocHost(&c->h_quench, sizeof(double) * 2 * (c->ring + 1)));
+    memset(c->h_sc, 0, sizeof(StepScalars));
+    c->h_sc->temp = 0.0;
+    c->h_sc->scale = 1.0;
+    c->h_sc->first_nonfinite_step = -1;
+    CK(cudaMemcpy(c->d_sc, c->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice));
+
+    int st = MDSEA_OK;
+    if (!c->cutoff_path) {
+        CK(cudaMalloc(&c->d_r, sizeof(double) * c->E));
+        CK(cudaMalloc(&c->d_v, sizeof(double) * c->E));
+        CK(cudaMalloc(&c->d_acc, sizeof(double) * c->E));
+        CK(cudaMemset(c->d_acc, 0, sizeof(double) * c->E));
+        CK(cudaMalloc(&c->d_r_rows, sizeof(double) * c->E * c->ring));
+        CK(cudaMalloc(&c->d_v_rows, sizeof(double) * c->E * c->ring));
+        c->n_ke_part = md_div_up((long long)c->E, 256);
+        CK(cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
+        st = md_allpairs_setup(c);
+    } else {
+        st = md_cells_setup(c);
+    }
+    if (st != MDSEA_OK) {
+        g_err = c->err;
+        mdsea_b200_destroy(c);
+        return st;
+    }
+#undef CK
+    *out = c;
+    return MDSEA_OK;
+}
+
+extern "C" void mdsea_b200_destroy(mdsea_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->p.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    md_cells_free(c);
+    cudaFree(c->d_r); cudaFree(c->d_v); cudaFree(c->d_acc); cudaFree(c->d_fpart);
+    cudaFree(c->d_pe_part); cudaFree(c->d_cnt_part); cudaFree(c->d_ke_part);
+    cudaFree(c->d_rhi); cudaFree(c->d_rlo);
+    cudaFree(c->d_r_rows); cudaFree(c->d_v_rows);
+    cudaFree(c->d_pe_rows); cudaFree(c->d_ke_rows); cudaFree(c->d_temp_rows);
+    cudaFree(c->d_quench); cudaFree(c->d_sc);
+    if (c->h_sc) cudaFreeHost(c->h_sc);
+    if (c->h_quench) cudaFreeHost(c->h_quench);
+    if (c->ev_batch_done) cudaEventDestroy(c->ev_batch_done);
+    if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+extern "C" void *mdsea_b200_stream(mdsea_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int mdsea_b200_set_profiling(mdsea_ctx *c, int32_t on) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    c->profiling = on != 0;
+    return MDSEA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------------
+int md_cutoff_set_state(mdsea_ctx *c, const double *r, const double *v);
+int md_cutoff_get_state(mdsea_ctx *c, double *r, double *v, double *a, int64_t *ids, int64_t *n_owned);
+
+extern "C" int mdsea_b200_set_state(mdsea_ctx *c, const double *r, const double *v) {
+    if (!c || !r || !v) return bad(c, "set_state: NULL argument");
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    if (c->cutoff_path) {
+        MD_TRY(md_cutoff_set_state(c, r, v));
+    } else {
+        MD_CUDA(c, cudaMemcpyAsync(c->d_r, r, sizeof(double) * c->E, cudaMemcpyHostToDevice, c->stream));
+        MD_CUDA(c, cudaMemcpyAsync(c->d_v, v, sizeof(double) * c->E, cudaMemcpyHostToDevice, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->have_state = true;
+    c->acc_valid = false;
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_set_temperature(mdsea_ctx *c, double temp, int32_t reset_ke) {
+    // self.temp / self.temp_init seed (simulator.py:79-80); reset_ke puts mean_ke back to None (:75)
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    MD_CUDA(c, cudaMemcpy(c->h_sc, c->d_sc, sizeof(StepScalars), cudaMemcpyDeviceToHost));
+    c->h_sc->temp = temp;
+    if (reset_ke) { c->h_sc->ke_valid = 0; c->h_sc->ke_prev = 0.0; }
+    MD_CUDA(c, cudaMemcpy(c->d_sc, c->h_sc, sizeof(StepScalars), cudaMemcpyHostToDevice));
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_get_state(mdsea_ctx *c, double *r, double *v, double *a, int64_t *ids, int64_t *n_owned) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    if (!c->have_state) { md_set_error(c, "get_state: no state set"); return MDSEA_ERR_STATE; }
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    if (c->cutoff_path) return md_cutoff_get_state(c, r, v, a, ids, n_owned);
+    if (r) MD_CUDA(c, cudaMemcpyAsync(r, c->d_r, sizeof(double) * c->E, cudaMemcpyDeviceToHost, c->stream));
+    if (v) MD_CUDA(c, cudaMemcpyAsync(v, c->d_v, sizeof(double) * c->E, cudaMemcpyDeviceToHost, c->stream));
+    if (a) MD_CUDA(c, cudaMemcpyAsync(a, c->d_acc, sizeof(double) * c->E, cudaMemcpyDeviceToHost, c->stream));
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_owned) *n_owned = c->n;
+    if (ids) for (long long i = 0; i < c->n; ++i) ids[i] = i;
+    return MDSEA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// force evaluation dispatch: fills the partial-force source used by the integrator
+// ---------------------------------------------------------------------------------------------
+struct ForceSrc { const double *f; int nparts; size_t stride; };
+
+static int eval_forces(mdsea_ctx *c, ForceSrc *src) {
+    if (c->pot.fast == POTF_IDEAL) {
+        // ff_ideal returns 0 (potentials.py:62-64): acc = 0, PE = 0; no kernel needed beyond a clear
+        MD_CUDA(c, cudaMemsetAsync(c->d_acc, 0, sizeof(double) * c->E, c->stream));
+        src->f = c->d_acc; src->nparts = 1; src->stride = 0;
+        c->stats.force_evals += 1;
+        return MDSEA_OK;
+    }
+    if (c->cutoff_path) {
+        MD_TRY(md_cutoff_force(c));
+        src->f = c->d_acc; src->nparts = 1; src->stride = 0;
+        return MDSEA_OK;
+    }
+    MD_TRY(md_allpairs_force(c));
+    src->f = c->d_fpart; src->nparts = c->ap_nsplit; src->stride = c->E;
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_update_acc(mdsea_ctx *c, double *acc, double *mean_pe) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    if (!c->have_state) { md_set_error(c, "update_acc: no state set"); return MDSEA_ERR_STATE; }
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    ForceSrc s;
+    MD_TRY(eval_forces(c, &s));
+    if (s.f != c->d_acc) MD_TRY(md_reduce_acc(c, s.f, s.nparts, s.stride));
+    c->acc_valid = true;
+    if (mean_pe) {
+        // sum the per-block partials on the host (diagnostic path, not the step loop)
+        std::vector<double> h(c->n_pe_part > 0 ? c->n_pe_part : 1, 0.0);
+        if (c->pot.fast != POTF_IDEAL && c->n_pe_part > 0)
+            MD_CUDA(c, cudaMemcpyAsync(h.data(), c->d_pe_part, sizeof(double) * c->n_pe_part, cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        double t = 0.0;
+        for (int k = 0; k < c->n_pe_part; ++k) t += h[k];
+        *mean_pe = (c->pot.fast == POTF_IDEAL) ? 0.0 : t * c->pot.lam_eps * 0.5 / (double)c->n_global;
+    }
+    if (acc) {
+        if (c->cutoff_path) return md_cutoff_get_state(c, nullptr, nullptr, acc, nullptr, nullptr);
+        MD_CUDA(c, cudaMemcpyAsync(acc, c->d_acc, sizeof(double) * c->E, cudaMemcpyDeviceToHost, c->stream));
+    }
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_update_dists(mdsea_ctx *c, double *dists, double *units) {
+    if (!c || !dists || !units) return bad(c, "update_dists: NULL argument");
+    if (!c->have_state) { md_set_error(c, "update_dists: no state set"); return MDSEA_ERR_STATE; }
+    if (c->cutoff_path || c->n > 32768) { md_set_error(c, "update_dists: only available in all-pairs mode with N <= 32768"); return MDSEA_ERR_UNSUPPORTED; }
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    const long long P = c->n * (c->n - 1) / 2;
+    double *dd = nullptr, *du = nullptr;
+    MD_CUDA(c, cudaMalloc(&dd, sizeof(double) * (P > 0 ? P : 1)));
+    MD_CUDA(c, cudaMalloc(&du, sizeof(double) * (P > 0 ? P : 1) * c->ndim));
+    int st = md_pair_dists(c, dd, du);
+    if (st == MDSEA_OK) {
+        cudaMemcpyAsync(dists, dd, sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(units, du, sizeof(double) * P * c->ndim, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(dd); cudaFree(du);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the step loop (simulator.py:560-568, 583-586)
+// ---------------------------------------------------------------------------------------------
+int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt);
+
+static int allpairs_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
+    const bool verlet = c->p.algorithm == MDSEA_ALGO_VERLET;
+    const bool reuse = verlet && c->p.force_evals_per_step == 1 && c->box.pbc;
+    ForceSrc s;
+    for (int k = 0; k < a->nsteps; ++k) {
+        if (verlet) {
+            if (reuse && c->acc_valid) {
+                // a(t) == a(t+dt) of the previous step; the wrap does not change it
+                MD_TRY(md_kick_drift(c, true, true, c->d_acc, 1, 0));
+            } else {
+                MD_TRY(md_apply_bc(c));
+                MD_TRY(eval_forces(c, &s));                                   // simulator.py:540
+                MD_TRY(md_kick_drift(c, false, true, s.f, s.nparts, s.stride));
+            }
+        } else {
+            MD_TRY(md_kick_drift(c, true, false, nullptr, 0, 0));           // simulator.py:533
+        }
+        MD_TRY(eval_forces(c, &s));                                           // simulator.py:544 / :535
+        MD_TRY(md_kick_finish(c, s.f, s.nparts, s.stride, k, a->record_coords, g_dt));
+        c->acc_valid = true;
+        MD_TRY(md_finalize_step(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k));
+    }
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows) {
+    if (!c || !a || !rows) return bad(c, "run: NULL argument");
+    if (!c->have_state) { md_set_error(c, "run: set_state has not been called"); return MDSEA_ERR_STATE; }
+    if (a->nsteps < 1 || a->nsteps > c->ring) return bad(c, "run: nsteps must be in 1..ring_rows");
+    if (!rows->pe || !rows->ke || !rows->temp) return bad(c, "run: pe/ke/temp row buffers are required");
+    if (a->record_coords && (!rows->r || !rows->v)) return bad(c, "run: record_coords needs r and v row buffers");
+    if (!(a->k_boltzmann > 0)) return bad(c, "run: k_boltzmann must be positive");
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+
+    // quench targets of this batch -> device
+    // (pinned staging; the previous batch has fully drained at this point, so it is free to overwrite)
+    for (int k = 0; k < 2 * (a->nsteps + 1); ++k)
+        c->h_quench[k] = (a->quench_targets && k < 2 * a->nsteps) ? a->quench_targets[k] : NAN;
+    MD_CUDA(c, cudaMemcpyAsync(c->d_quench, c->h_quench, sizeof(double) * 2 * (a->nsteps + 1), cudaMemcpyHostToDevice, c->stream));
+    MD_TRY(md_prepare_first(c, a->k_boltzmann));
+
+    const double g_dt = a->gravity_acceleration * c->p.dt;
+    if (c->cutoff_path) MD_TRY(md_cutoff_steps(c, a, g_dt));
+    else MD_TRY(allpairs_steps(c, a, g_dt));
+    c->stats.steps += a->nsteps;
+
+    // buffered rows -> caller (copy stream, overlaps with whatever the compute stream does next)
+    MD_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));
+    MD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_done, 0));
+    const size_t rowb = sizeof(double) * (size_t)c->ndim * (size_t)c->n_global;
+    if (a->record_coords && !c->cutoff_path) {
+        MD_CUDA(c, cudaMemcpyAsync(rows->r, c->d_r_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
+        MD_CUDA(c, cudaMemcpyAsync(rows->v, c->d_v_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    MD_CUDA(c, cudaMemcpyAsync(rows->pe, c->d_pe_rows, sizeof(double) * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
+    MD_CUDA(c, cudaMemcpyAsync(rows->ke, c->d_ke_rows, sizeof(double) * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
+    MD_CUDA(c, cudaMemcpyAsync(rows->temp, c->d_temp_rows, sizeof(double) * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
+    MD_CUDA(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(StepScalars), cudaMemcpyDeviceToHost, c->copy_stream));
+    MD_CUDA(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    // the ring is reused by the next batch: make the compute stream wait for the copies
+    MD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+    c->pending = true;
+    c->pending_rows = *rows;
+    c->pending_nsteps = a->nsteps;
+    c->pending_record = a->record_coords;
+    return MDSEA_OK;
+}
+
+int md_cutoff_finish_rows(mdsea_ctx *c);
+
+extern "C" int mdsea_b200_wait(mdsea_ctx *c) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    if (!c->pending) return MDSEA_OK;
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    MD_CUDA(c, cudaEventSynchronize(c->ev_copy_done));
+    c->pending = false;
+    if (c->cutoff_path) MD_TRY(md_cutoff_finish_rows(c));
+    c->stats.pair_evals_unique = (long long)c->h_sc->pairs_unique;
+    if (c->h_sc->overflow_flag) {
+        md_set_error(c, "run: neighbour/ghost buffer capacity exceeded (raise max_neighbors)");
+        return MDSEA_ERR_CAPACITY;
+    }
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_run(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows) {
+    MD_TRY(mdsea_b200_run_async(c, a, rows));
+    return mdsea_b200_wait(c);
+}
+
+extern "C" int mdsea_b200_get_stats(mdsea_ctx *c, mdsea_stats *out) {
+    if (!c || !out) return MDSEA_ERR_BAD_ARG;
+    *out = c->stats;
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_first_nonfinite_step(mdsea_ctx *c, int64_t *step) {
+    if (!c || !step) return MDSEA_ERR_BAD_ARG;
+    *step = c->h_sc ? c->h_sc->first_nonfinite_step : -1;
+    return MDSEA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FMA throughput micro-benchmark (roofline denominator for the force kernels)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_fma_peak(T *out, int iters, T a, T b) {
+    T x0 = a + threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    T s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == T(123456789)) out[0] = s;
+}
+
+extern "C" int mdsea_b200_measure_fma_peak(int32_t device, int32_t fp64, double *tflops) {
+    if (!tflops) return MDSEA_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { g_err = "measure_fma_peak: no CUDA device"; return MDSEA_ERR_CUDA; }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    void *out = nullptr;
+    cudaMalloc(&out, 64);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = sms * 8, threads = 256, iters = fp64 ? 2000 : 4000;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        if (fp64) k_fma_peak<double><<<blocks, threads>>>((double *)out, iters, 1.0000001, 1e-9);
+        else k_fma_peak<float><<<blocks, threads>>>((float *)out, iters, 1.0000001f, 1e-9f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) { g_err = "measure_fma_peak: kernel failed"; return MDSEA_ERR_CUDA; }
+    *tflops = best;
+    return MDSEA_OK;
+}

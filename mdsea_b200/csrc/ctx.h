@@ -1,0 +1,77 @@
+// Host-side context of one solver instance (one GPU / one rank).
+#pragma once
+#include "common.cuh"
+
+struct CellState;   // cutoff path (cells.cu / nbr.cu)
+struct CommState;   // domain decomposition (comm.cu)
+
+struct mdsea_ctx {
+    mdsea_params p;
+    std::string  err;
+    int          ndim = 0;
+    long long    n = 0;        // particles resident on this rank (== N when world == 1)
+    long long    n_global = 0;
+    size_t       E = 0;        // ndim * n  (flat SoA length)
+    PotDev       pot;
+    BoxDev       box;
+    bool         cutoff_path = false;
+    bool         have_state = false;
+    bool         acc_valid = false;   // d_acc holds a(r) for the current positions
+    bool         profiling = false;
+
+    cudaStream_t stream = nullptr;       // compute stream
+    cudaStream_t copy_stream = nullptr;  // D2H of buffered rows
+    cudaEvent_t  ev_batch_done = nullptr, ev_copy_done = nullptr;
+    cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
+
+    // state, SoA (ndim, n) float64
+    double *d_r = nullptr, *d_v = nullptr, *d_acc = nullptr;
+    // all-pairs force partials [nsplit][ndim][n] and per-block reductions
+    double *d_fpart = nullptr;
+    int     ap_ti = 128, ap_nsplit = 1, ap_jchunk = 0, ap_blocks_x = 0;
+    double *d_pe_part = nullptr;           // per force-kernel block
+    unsigned long long *d_cnt_part = nullptr;
+    int     n_pe_part = 0;
+    double *d_ke_part = nullptr;           // per integrator block
+    int     n_ke_part = 0;
+    // fp32 hi/lo split of the positions for the fp32 all-pairs kernel
+    float  *d_rhi = nullptr, *d_rlo = nullptr;
+
+    // ring buffer of rows
+    int     ring = 0;
+    double *d_r_rows = nullptr, *d_v_rows = nullptr;  // [ring][E]
+    double *d_pe_rows = nullptr, *d_ke_rows = nullptr, *d_temp_rows = nullptr;  // [ring]
+    double *d_quench = nullptr;                       // [ring][2]
+    StepScalars *d_sc = nullptr;
+    StepScalars *h_sc = nullptr;                      // pinned mirror
+    double *h_quench = nullptr;                       // pinned staging of the batch's quench targets
+
+    mdsea_stats stats;
+    CellState  *cells = nullptr;
+    CommState  *comm = nullptr;
+
+    // pending async run
+    bool       pending = false;
+    mdsea_rows pending_rows;
+    int        pending_nsteps = 0;
+    int        pending_record = 0;
+};
+
+void md_set_error(mdsea_ctx *ctx, const char *msg);
+
+// allpairs.cu
+int md_allpairs_setup(mdsea_ctx *c);
+int md_allpairs_force(mdsea_ctx *c);          // fills d_fpart / d_pe_part / d_cnt_part from d_r
+// integrate.cu
+int md_apply_bc(mdsea_ctx *c);
+int md_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, const double *fsrc, int nparts, size_t stride);
+int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt);
+int md_reduce_acc(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride);
+int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index);
+int md_prepare_first(mdsea_ctx *c, double kb);
+int md_pair_dists(mdsea_ctx *c, double *d_dists, double *d_units);
+// cells.cu / nbr.cu (cutoff path)
+int md_cells_setup(mdsea_ctx *c);
+void md_cells_free(mdsea_ctx *c);
+int md_cutoff_force(mdsea_ctx *c);            // rebuilds the list when flagged, then forces
+int md_cutoff_after_set_state(mdsea_ctx *c);

@@ -1,0 +1,265 @@
+// K5: integrator kernels.  Every operation of apply_pbc / apply_hbc (simulator.py:156-179),
+// algorithm_verlet / algorithm_simple (:530-544), apply_field (:201-205), the _quench velocity
+// scaling (:192-195) and update_mean_ke (:241-245) is per COMPONENT, so the kernels run flat over
+// the ndim*N elements of the SoA arrays: fully coalesced, no gathers, positions read once.
+//
+//   kick_drift : [boundary condition] ; [v += a dt/2] ; r += v dt        (before a force evaluation)
+//   kick_finish: v += a dt/2 ; gravity ; quench scale ; sum v^2 ; row(r, v) into the device ring
+//   finalize   : fixed-order reduction of the per-block partial sums -> mean_pe, mean_ke, temp row;
+//                temperature bookkeeping for the next step's quench
+#include "ctx.h"
+
+#define IG_THREADS 256
+
+__device__ __forceinline__ double md_sum_parts(const double *__restrict__ f, int nparts, size_t stride, size_t e) {
+    double a = f[e];
+    for (int p = 1; p < nparts; ++p) a += f[(size_t)p * stride + e];
+    return a;
+}
+
+__global__ void __launch_bounds__(IG_THREADS)
+k_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *__restrict__ fsrc, int nparts, size_t stride,
+             double *__restrict__ acc_out, size_t E, int do_bc, int do_kick, int pbc, double L, double radius,
+             double restitution, double dt) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double x = r[e], u = v[e];
+    if (do_bc) {
+        if (pbc) {  // one-shot strict wrap, simulator.py:165-166
+            if (x < 0.0) x += L;
+            if (x > L) x -= L;
+        } else {  // clamp + reflect, simulator.py:172-179
+            if (x - radius < 0.0) { x = radius; u *= -restitution; }
+            if (x + radius > L) { x = L - radius; u *= -restitution; }
+        }
+    }
+    if (do_kick) {
+        const double a = md_sum_parts(fsrc, nparts, stride, e);
+        if (acc_out) acc_out[e] = a;
+        u += __dmul_rn(__dmul_rn(0.5, a), dt);  // v += 0.5 * acc * dt, evaluation order of simulator.py:540
+    }
+    x += __dmul_rn(u, dt);                      // r += v * dt, simulator.py:542
+    r[e] = x;
+    v[e] = u;
+}
+
+__global__ void __launch_bounds__(IG_THREADS)
+k_apply_bc(double *__restrict__ r, double *__restrict__ v, size_t E, int pbc, double L, double radius, double restitution) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double x = r[e];
+    if (pbc) {
+        if (x < 0.0) x += L;
+        if (x > L) x -= L;
+        r[e] = x;
+    } else {
+        double u = v[e];
+        if (x - radius < 0.0) { x = radius; u *= -restitution; }
+        if (x + radius > L) { x = L - radius; u *= -restitution; }
+        r[e] = x;
+        v[e] = u;
+    }
+}
+
+__global__ void __launch_bounds__(IG_THREADS)
+k_reduce_acc(const double *__restrict__ fsrc, int nparts, size_t stride, double *__restrict__ acc, size_t E) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < E) acc[e] = md_sum_parts(fsrc, nparts, stride, e);
+}
+
+__global__ void __launch_bounds__(IG_THREADS)
+k_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ fsrc, int nparts,
+              size_t stride, double *__restrict__ acc_out, size_t E, size_t last_dim_start, double dt, double g_dt,
+              const StepScalars *__restrict__ sc, double *__restrict__ ke_part, double *__restrict__ r_row,
+              double *__restrict__ v_row) {
+    __shared__ double red[32];
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v2 = 0.0;
+    if (e < E) {
+        const double a = md_sum_parts(fsrc, nparts, stride, e);
+        if (acc_out) acc_out[e] = a;
+        double u = v[e] + __dmul_rn(__dmul_rn(0.5, a), dt);  // simulator.py:544
+        if (g_dt != 0.0 && e >= last_dim_start) u -= g_dt;   // v[-1] -= g * dt, simulator.py:205
+        const double scale = sc->scale;                       // (T_target / T)^0.5, simulator.py:195
+        if (scale != 1.0) u *= scale;
+        v[e] = u;
+        v2 = u * u;
+        if (r_row) {
+            r_row[e] = r[e];
+            v_row[e] = u;
+        }
+    }
+    const double b = md_block_sum(v2, red);
+    if (threadIdx.x == 0) ke_part[blockIdx.x] = b;
+}
+
+// single block; deterministic fixed-order tree over the partial sums
+__global__ void __launch_bounds__(256)
+k_finalize(const double *__restrict__ pe_part, const unsigned long long *__restrict__ cnt_part, int n_pe,
+           const double *__restrict__ ke_part, int n_ke, double pe_factor /* lam_eps / 2 / N */,
+           double ke_factor /* 0.5 m / N */, double kb, StepScalars *__restrict__ sc, double *__restrict__ pe_rows,
+           double *__restrict__ ke_rows, double *__restrict__ temp_rows, int row, const double *__restrict__ quench_next,
+           long long step_index) {
+    __shared__ double red[32];
+    __shared__ unsigned long long redc[32];
+    double pe = 0.0, ke = 0.0;
+    unsigned long long cnt = 0;
+    for (int k = threadIdx.x; k < n_pe; k += blockDim.x) {
+        pe += pe_part[k];
+        cnt += cnt_part[k];
+    }
+    for (int k = threadIdx.x; k < n_ke; k += blockDim.x) ke += ke_part[k];
+    pe = md_block_sum(pe, red);
+    ke = md_block_sum(ke, red);
+    // 64-bit count
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        __syncthreads();
+        if (lane == 0) redc[warp] = cnt;
+        __syncthreads();
+        if (warp == 0) {
+            cnt = lane < (int)(blockDim.x >> 5) ? redc[lane] : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double mean_pe = pe * pe_factor;  // sum over unique pairs / N, simulator.py:249
+        const double mean_ke = ke * ke_factor;  // 0.5 m mean(v.v), simulator.py:244
+        pe_rows[row] = mean_pe;
+        ke_rows[row] = mean_ke;
+        temp_rows[row] = sc->temp;              // self.temp as written by update_files, simulator.py:147
+        if (!(isfinite(mean_pe) && isfinite(mean_ke)) && sc->first_nonfinite_step < 0) sc->first_nonfinite_step = step_index;
+        sc->ke_prev = mean_ke;
+        sc->ke_valid = 1;
+        sc->pairs_unique += cnt >> 1;           // every unique pair was visited from both ends
+        sc->steps_done += 1;
+        // quench bookkeeping for the NEXT step (simulator.py:185-195, 233-239)
+        double scale = 1.0, temp = sc->temp;
+        if (quench_next) {
+            for (int t = 0; t < 2; ++t) {
+                const double target = quench_next[t];
+                if (target == target) {  // not NaN
+                    temp = (2.0 / 3.0) * mean_ke / kb;
+                    if (temp != 0.0) scale *= sqrt(target / temp);
+                }
+            }
+        }
+        sc->temp = temp;
+        sc->scale = scale;
+    }
+}
+
+// quench bookkeeping for the first step of a batch (uses the scalars left by the previous batch)
+__global__ void k_prepare_first(StepScalars *sc, const double *quench_first, double kb) {
+    double scale = 1.0, temp = sc->temp;
+    if (quench_first) {
+        for (int t = 0; t < 2; ++t) {
+            const double target = quench_first[t];
+            if (target == target) {
+                if (sc->ke_valid) temp = (2.0 / 3.0) * sc->ke_prev / kb;
+                if (temp != 0.0) scale *= sqrt(target / temp);
+            }
+        }
+    }
+    sc->temp = temp;
+    sc->scale = scale;
+}
+
+// update_dists(radius=None) for small N (simulator.py:257-280): one thread per unique pair in
+// itertools.combinations order.
+__global__ void k_pair_dists(const double *__restrict__ r, int n, int ndim, long long P, int pbc, double L, double invL,
+                             double *__restrict__ dists, double *__restrict__ units) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    // invert p = i*n - i(i+1)/2 + (j - i - 1)
+    const double nn = (double)n - 0.5;
+    long long i = (long long)floor(nn - sqrt(nn * nn - 2.0 * (double)p));
+    while (i > 0 && i * n - i * (i + 1) / 2 > p) --i;
+    while ((i + 1) * n - (i + 1) * (i + 2) / 2 <= p) ++i;
+    const long long j = p - (i * n - i * (i + 1) / 2) + i + 1;
+    double d[3], r2 = 0.0;
+    for (int k = 0; k < ndim; ++k) {
+        double x = __dsub_rn(r[(size_t)k * n + j], r[(size_t)k * n + i]);
+        if (pbc) x = __dsub_rn(x, __dmul_rn(rint(__ddiv_rn(x, L)), L));
+        d[k] = x;
+        r2 = __dadd_rn(r2, __dmul_rn(x, x));
+    }
+    const double dist = __dsqrt_rn(r2);
+    dists[p] = dist;
+    for (int k = 0; k < ndim; ++k) units[(size_t)p * ndim + k] = __ddiv_rn(d[k], dist);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host wrappers
+// ---------------------------------------------------------------------------------------------
+static inline int ig_grid(const mdsea_ctx *c) { return md_div_up((long long)c->E, IG_THREADS); }
+
+int md_apply_bc(mdsea_ctx *c) {
+    k_apply_bc<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, c->E, c->box.pbc, c->box.L, c->p.radius,
+                                                         c->p.restitution);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, const double *fsrc, int nparts, size_t stride) {
+    double *acc_out = (do_kick && fsrc != c->d_acc) ? c->d_acc : nullptr;
+    k_kick_drift<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
+                                                           do_bc ? 1 : 0, do_kick ? 1 : 0, c->box.pbc, c->box.L,
+                                                           c->p.radius, c->p.restitution, c->p.dt);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_reduce_acc(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride) {
+    k_reduce_acc<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(fsrc, nparts, stride, c->d_acc, c->E);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt) {
+    double *acc_out = (fsrc != c->d_acc) ? c->d_acc : nullptr;
+    double *rr = record ? c->d_r_rows + (size_t)row * c->E : nullptr;
+    double *vr = record ? c->d_v_rows + (size_t)row * c->E : nullptr;
+    k_kick_finish<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
+                                                            (size_t)(c->ndim - 1) * c->n, c->p.dt, g_dt, c->d_sc,
+                                                            c->d_ke_part, rr, vr);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index) {
+    const double N = (double)c->n_global;
+    const double pe_factor = (c->pot.fast == POTF_IDEAL) ? 0.0 : c->pot.lam_eps * 0.5 / N;
+    const double ke_factor = 0.5 * c->p.mass / N;
+    const double *qn = next_row_valid ? c->d_quench + (size_t)(row + 1) * 2 : nullptr;
+    k_finalize<<<1, 256, 0, c->stream>>>(c->d_pe_part, c->d_cnt_part, c->n_pe_part, c->d_ke_part, c->n_ke_part, pe_factor,
+                                         ke_factor, kb, c->d_sc, c->d_pe_rows, c->d_ke_rows, c->d_temp_rows, row, qn,
+                                         step_index);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_prepare_first(mdsea_ctx *c, double kb) {
+    k_prepare_first<<<1, 1, 0, c->stream>>>(c->d_sc, c->d_quench, kb);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_pair_dists(mdsea_ctx *c, double *d_dists, double *d_units) {
+    const long long P = c->n * (c->n - 1) / 2;
+    if (P == 0) return MDSEA_OK;
+    k_pair_dists<<<md_div_up(P, 256), 256, 0, c->stream>>>(c->d_r, (int)c->n, c->ndim, P, c->box.pbc, c->box.L,
+                                                           c->box.invL, d_dists, d_units);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}

@@ -1,0 +1,332 @@
+"""ContinuousPotentialSolver -- mdsea's solver API over the B200 step loop.
+
+Drop-in for ``mdsea.simulator.ContinuousPotentialSolver`` (mdsea/simulator.py:19-49, 511-589): same
+dataclass fields, same public attributes (``r_vec v_vec acc dists drunits mean_ke mean_pe temp step dt``),
+same methods (``run_simulation advance update_acc update_dists update_energies update_files``), same
+initial conditions (gen.py under the caller's ``np.random.seed``), same dataset rows.  What changed is
+where the work happens: the state lives on the GPU, every step of ``advance`` runs in the CUDA kernels
+of ``csrc/`` through the C ABI (include/mdsea_b200.h), rows are buffered in a device ring and flushed
+to the HDF5 datasets every ``flush_every`` steps.  There is no NumPy fallback for the step loop.
+
+New keyword fields (defaults keep the reference's behaviour):
+    precision             "fp64" (default) | "fp32"  -- arithmetic of the pair kernel; state is always float64
+    r_cutoff              None => all pairs (the reference's only working mode); a number => plain truncation
+                          at dist < r_cutoff through the cell-list / Verlet-list kernels (3-D periodic boxes
+                          with >= 3 cells per side; otherwise the all-pairs kernel applies the cutoff)
+    skin                  Verlet skin of the neighbour list (default 0.3 sigma)
+    flush_every           rows buffered on the device between HDF5 flushes (default: sized from memory)
+    force_evals_per_step  1 (default, periodic boxes): a(t+dt) is reused as the next step's a(t);
+                          2: evaluate twice per step exactly like simulator.py:540,544
+    device                CUDA device ordinal
+"""
+from __future__ import annotations
+
+import logging
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from mdsea_b200 import _capi, quicker
+from mdsea_b200.config import Config
+from mdsea_b200.constants import DTYPE
+from mdsea_b200.core import SysManager
+from mdsea_b200.gen import PosGen, VelGen
+from mdsea_b200.helpers import ProgressBar, get_dt
+from mdsea_b200.potentials import Potential
+
+log = logging.getLogger(__name__)
+
+_ALGORITHMS = {"verlet": 0, "simple": 1}
+_PRECISIONS = {"fp64": 0, "fp32": 1}
+
+
+def _pinned_empty(shape):
+    """Page-locked float64 host buffer (torch is used for allocation only); plain numpy if CUDA is absent."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            t = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+            a = t.numpy()
+            a.setflags(write=True)
+            _pinned_empty._keep.append(t)
+            return a
+    except Exception:  # pragma: no cover
+        pass
+    return np.empty(shape, dtype=np.float64)
+
+
+_pinned_empty._keep = []
+
+
+@dataclass
+class _BaseSimulator:
+    sm: SysManager = field()
+    dt: Optional[float] = field(default=None)
+    pot: Potential = field(default_factory=Potential.ideal)
+    restitution_coeff: float = field(default=1.0)
+    isothermal: bool = field(default=False)
+    gravity: bool = field(default=False)
+    r_cutoff: Optional[float] = field(default=None)
+    # --- new, B200-side knobs -------------------------------------------------------------------
+    precision: str = field(default="fp64")
+    skin: Optional[float] = field(default=None)
+    flush_every: Optional[int] = field(default=None)
+    force_evals_per_step: Optional[int] = field(default=None)
+    device: int = field(default=0)
+    max_neighbors: int = field(default=0)
+
+    def __post_init__(self) -> None:
+        sm = self.sm
+        # initial state: same generators, same RNG call order as simulator.py:54-59
+        self._r = PosGen(ndim=sm.NDIM, boxlen=sm.LEN_BOX, nparticles=sm.NUM_PARTICLES).simplecubic()
+        self._v = VelGen(ndim=sm.NDIM, nparticles=sm.NUM_PARTICLES).mb(sm.MASS, sm.TEMP, Config.k_boltzmann)
+        self._acc = np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
+        self.ndnp_zeroes = np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
+        self._dists = self._drunits = self.pairs_indexes = None
+        self.mean_ke = None
+        self.mean_pe = None
+        self.temp_init = sm.TEMP
+        self.temp = sm.TEMP
+        self.step = 0
+        if self.dt is None:  # simulator.py:86-87
+            self.dt = get_dt(radius=sm.RADIUS_PARTICLE, mean_speed=float(quicker.norm(self._v, axis=0).mean()))
+        self.apply_restcoeff = bool(self.restitution_coeff < 1)
+        self.pbarr = ProgressBar("Simulator", sm.STEPS, __name__)
+        self._FLIPID = quicker.flipid(sm.NDIM)
+
+        if self.precision not in _PRECISIONS:
+            raise ValueError(f"precision '{self.precision}' not in {tuple(_PRECISIONS)}")
+        self._ctx = None
+        self._device_fresh = False   # device holds a newer state than the host copies
+        self._host_exposed = True    # host arrays may have been edited -> upload before the next device op
+
+    # -- device context --------------------------------------------------------------------------
+    def _algorithm_code(self) -> int:
+        return 0
+
+    def _ensure_ctx(self):
+        if self._ctx is not None:
+            return self._ctx
+        sm = self.sm
+        pp = self.pot.device_params()  # NotImplementedError for foreign callables
+        n, nd = sm.NUM_PARTICLES, sm.NDIM
+        k = self.flush_every
+        if k is None:
+            row_bytes = 2 * nd * n * 8
+            k = max(1, min(256, (256 << 20) // max(row_bytes, 1)))
+        k = max(1, min(int(k), max(1, sm.STEPS)))
+        self._k = k
+        fe = self.force_evals_per_step
+        if fe is None:
+            fe = 1 if sm.PBC else 2
+        if fe == 1 and not sm.PBC:
+            raise ValueError("force_evals_per_step=1 needs periodic boundaries (hard walls move particles between evaluations)")
+        sigma = pp["sigma"]
+        self._ctx = _capi.Context(
+            ndim=nd, num_particles=n, boxlen=float(sm.LEN_BOX), mass=float(sm.MASS), radius=float(sm.RADIUS_PARTICLE),
+            dt=float(self.dt), pbc=1 if sm.PBC else 0, algorithm=self._algorithm_code(),
+            restitution=float(self.restitution_coeff), pot_kind=pp["kind"], precision=_PRECISIONS[self.precision],
+            epsilon=pp["epsilon"], sigma=sigma, mie_m=pp["m"], mie_n=pp["n"], mie_a=pp["a"],
+            r_cutoff=float(self.r_cutoff) if self.r_cutoff else 0.0,
+            skin=float(self.skin) if self.skin is not None else 0.3 * sigma,
+            force_evals_per_step=int(fe), ring_rows=k, device=int(self.device), max_neighbors=int(self.max_neighbors),
+        )
+        self._ctx.set_temperature(self.temp, reset_ke=self.mean_ke is None)
+        self._rows = dict(r=_pinned_empty((k, nd, n)), v=_pinned_empty((k, nd, n)),
+                          pe=_pinned_empty((k,)), ke=_pinned_empty((k,)), temp=_pinned_empty((k,)))
+        return self._ctx
+
+    def _sync_to_device(self):
+        ctx = self._ensure_ctx()
+        if self._host_exposed:
+            ctx.set_state(self._r, self._v)
+            self._host_exposed = False
+            self._device_fresh = False
+        return ctx
+
+    def _sync_to_host(self):
+        if self._device_fresh and self._ctx is not None:
+            self._r, self._v, self._acc, _ = self._ctx.get_state()
+            self._device_fresh = False
+
+    # -- state attributes (host views of the device state) -----------------------------------------
+    @property
+    def r_vec(self) -> np.ndarray:
+        self._sync_to_host()
+        self._host_exposed = True
+        return self._r
+
+    @r_vec.setter
+    def r_vec(self, value):
+        self._sync_to_host()
+        self._r = np.array(value, dtype=DTYPE)
+        self._host_exposed = True
+
+    @property
+    def v_vec(self) -> np.ndarray:
+        self._sync_to_host()
+        self._host_exposed = True
+        return self._v
+
+    @v_vec.setter
+    def v_vec(self, value):
+        self._sync_to_host()
+        self._v = np.array(value, dtype=DTYPE)
+        self._host_exposed = True
+
+    @property
+    def acc(self) -> np.ndarray:
+        self._sync_to_host()
+        return self._acc
+
+    @acc.setter
+    def acc(self, value):
+        self._acc = np.array(value, dtype=DTYPE)
+
+    @property
+    def dists(self):
+        return self._dists
+
+    @property
+    def drunits(self):
+        return self._drunits
+
+    # -- reference methods ---------------------------------------------------------------------------
+    def update_files(self) -> None:
+        """Write the current state as row ``self.step`` of the five datasets (simulator.py:143-150)."""
+        values = [[self.r_vec], [self.v_vec], [self.mean_pe], [self.mean_ke], [self.temp]]
+        for dataset, val in zip(self.sm.all_dsnames, values):
+            self.sm.update_ds(dataset, val, self.step)
+
+    def update_dists(self, radius: Optional[float] = None, where: str = "inside") -> np.ndarray:
+        """Pair distances / unit vectors in combinations order, computed on the device
+        (simulator.py:257-293).  Small N only: the output is O(N^2)."""
+        if where not in ("inside", "outside"):
+            raise ValueError(f"'{where}' is not a valid value for 'where'. Try 'inside' or 'outside' instead.")
+        ctx = self._sync_to_device()
+        d, u = ctx.update_dists()
+        if radius is None:
+            self.pairs_indexes = np.repeat(True, d.shape[0])
+        else:
+            self.pairs_indexes = d < radius if where == "inside" else d > radius
+            d, u = d[self.pairs_indexes], u[self.pairs_indexes]
+        self._dists, self._drunits = d, u
+        return d
+
+    def update_acc(self, radius: float = None) -> np.ndarray:
+        """Accelerations for the current positions, evaluated by the force kernels (simulator.py:295-311)."""
+        if radius is not None:
+            raise NotImplementedError("update_acc(radius=...) is broken in the reference (simulator.py:289-309); "
+                                      "use the solver's r_cutoff field instead")
+        ctx = self._sync_to_device()
+        self._acc, self._last_pe = ctx.update_acc()
+        return self._acc
+
+    def update_mean_pe(self):
+        ctx = self._sync_to_device()
+        _, self.mean_pe = ctx.update_acc()
+        return self.mean_pe
+
+    def update_mean_ke(self):
+        v = self.v_vec
+        self.mean_ke = 0.5 * self.sm.MASS * float(np.einsum("dn,dn->n", v, v).mean())
+        return self.mean_ke
+
+    def update_energies(self) -> None:
+        self.update_mean_pe()
+        self.update_mean_ke()
+
+    def update_temp(self) -> Optional[float]:
+        if self.mean_ke is None:
+            log.warning("Cannot update the temperature without first evaluating the mean kinetic energy.")
+            return None
+        self.temp = (2 / 3) * self.mean_ke / Config.k_boltzmann
+        return self.temp
+
+    @property
+    def com(self):
+        if self.sm.PBC:
+            log.warning("COM computation not available for PBC yet!")
+            return
+        return np.mean(self.r_vec, axis=1)
+
+
+@dataclass
+class ContinuousPotentialSolver(_BaseSimulator):
+    algorithm: str = field(default="verlet")
+
+    def __post_init__(self) -> None:
+        super().__post_init__()
+        if self.algorithm not in _ALGORITHMS:  # simulator.py:524-528
+            raise KeyError(f"Algorithm '{self.algorithm}' not found in {tuple(_ALGORITHMS.keys())}")
+
+    def _algorithm_code(self) -> int:
+        return _ALGORITHMS[self.algorithm]
+
+    # -- batches of steps on the device ------------------------------------------------------------
+    def _quench_targets(self, first_step: int, nsteps: int):
+        """Per-step (isothermal, scheduled) quench targets in the reference's call order (simulator.py:185-190)."""
+        if not self.isothermal and not self.sm.QUENCH_STEP:
+            return None
+        q = np.full((nsteps, 2), np.nan)
+        for k in range(nsteps):
+            s = first_step + k
+            if self.isothermal:
+                q[k, 0] = self.temp_init
+            if s in self.sm.QUENCH_STEP:
+                q[k, 1] = self.sm.QUENCH_T.pop(0)
+            if s == 0 and self.mean_ke is None and not np.isnan(q[k]).all():
+                log.warning("Cannot update the temperature without first evaluating the mean kinetic energy.")
+        return q if not np.isnan(q).all() else None
+
+    def _run_batch(self, first_step: int, nsteps: int, record: bool):
+        if self.apply_restcoeff:
+            raise NotImplementedError  # apply_collision_damping, simulator.py:546-548,565-566
+        ctx = self._sync_to_device()
+        q = self._quench_targets(first_step, nsteps)
+        g = Config.gravity_acceleration if self.gravity else 0.0
+        rows = ctx.run(nsteps, kb=Config.k_boltzmann, g=g, quench=q, record=record, rows=self._rows)
+        self._device_fresh = True
+        self.mean_pe = float(rows["pe"][nsteps - 1])
+        self.mean_ke = float(rows["ke"][nsteps - 1])
+        self.temp = float(rows["temp"][nsteps - 1])
+        return rows
+
+    def advance(self):
+        """Advance the simulation one step (simulator.py:560-568)."""
+        self._run_batch(self.step, 1, record=False)
+
+    def run_simulation(self) -> None:
+        """Run steps ``self.step .. STEPS-1`` and store one row per step (simulator.py:570-589)."""
+        sm = self.sm
+        simrange = range(self.step, sm.STEPS)
+        if len(simrange) == 0:
+            self.update_files()
+        self.pbarr.set_start()
+        self._ensure_ctx()
+        s = simrange.start
+        while s < sm.STEPS:
+            n = min(self._k, sm.STEPS - s)
+            for i in range(s, s + n):
+                self.pbarr.log_progress(i)
+            rows = self._run_batch(s, n, record=True)
+            sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], s)
+            sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], s)
+            sm.update_ds_block(sm.potenergy_dsname, rows["pe"][:n], s)
+            sm.update_ds_block(sm.kinenergy_dsname, rows["ke"][:n], s)
+            sm.update_ds_block(sm.temp_dsname, rows["temp"][:n], s)
+            s += n
+            self.step = s - 1
+        bad = self._ctx.first_nonfinite_step()
+        if bad >= 0:
+            log.warning("Non-finite energies from step %d on (the reference writes NaN rows silently as well; "
+                        "check Config.k_boltzmann / dt).", bad)
+        self.pbarr.set_finish()
+        self.pbarr.log_duration()
+
+    def stats(self) -> dict:
+        """Counters of the device context (force evaluations, pair interactions, launches, rebuilds)."""
+        return self._ensure_ctx().stats()

@@ -231,6 +231,18 @@ class OracleSolver:
         self.acc = acc
         return acc
 
+    def pair_force_scale(self):
+        """S_i = sum_j |f_ij| / m: magnitude of the terms update_acc adds up for particle i.  Used as the
+        denominator of the fp32 force tolerance (backward-error sense): near a lattice |F_i| << S_i, and
+        no fp32 pair arithmetic can resolve F_i to 1e-5 of itself."""
+        dr, dists = self.pair_geometry()
+        ii, jj = self._i, self._j
+        if self.r_cutoff is not None:
+            keep = dists < self.r_cutoff
+            dists, ii, jj = dists[keep], ii[keep], jj[keep]
+        mag = np.abs(self.pot.dvdr(dists)) / self.mass
+        return np.bincount(ii, mag, minlength=self.n) + np.bincount(jj, mag, minlength=self.n)
+
     # -- energies -------------------------------------------------------------
     def update_energies(self):
         """simulator.py:241-255: PE = sum_pairs V / N (dists of the LAST force eval);

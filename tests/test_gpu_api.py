@@ -1,0 +1,123 @@
+"""GPU: the reference-facing Python API end to end -- SysManager.new -> ContinuousPotentialSolver ->
+run_simulation -> data.h5 -> SysManager.load -> Analyser -- against the reference's golden rows."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from test_host_cpu import in_tmp_cwd  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(kw, solver_kw, pot, seed):
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    with config_context(k_boltzmann=1.0):
+        sm = SysManager.new(**kw)
+        np.random.seed(seed)
+        sim = ContinuousPotentialSolver(sm, pot=pot, **solver_kw)
+        sim.run_simulation()
+    return sm, sim
+
+
+def test_readme_example_end_to_end(in_tmp_cwd):  # noqa: F811
+    from mdsea_b200.analytics import Analyser
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+
+    g = load_golden("c1_readme_2d_n36")
+    sm, sim = _run(dict(simid="_mdsea_docs_example", ndim=2, num_particles=36, steps=500, vol_fraction=0.2,
+                        radius_particle=0.5), dict(flush_every=64), Potential.lennardjones(1, 1), 0)
+    assert sim.dt == float(g["dt"]) and sim.step == 499
+    sm2 = SysManager.load("_mdsea_docs_example")
+    pe, ke, temp = sm2.get_ds("pot_energy"), sm2.get_ds("kin_energy"), sm2.get_ds("temp")
+    np.testing.assert_allclose(pe[:150], g["pot_energy"][:150], rtol=1e-10)
+    np.testing.assert_allclose(ke[:150], g["kin_energy"][:150], rtol=1e-10)
+    np.testing.assert_allclose(pe, g["pot_energy"], rtol=1e-6)
+    np.testing.assert_array_equal(temp, g["temp"])
+    r = sm2.get_ds("r_coords")
+    assert r.shape == (500, 2, 36)
+    for n, k in enumerate(int(k) for k in g["keep_rows"]):
+        if k <= 100:
+            assert np.abs(r[k] - g["r_rows"][n]).max() < 1e-9 * sm.LEN_BOX
+    # energy drift no worse than the reference's own (7.3e-4 relative spread over the 500 steps)
+    E = pe + ke
+    Eref = g["pot_energy"] + g["kin_energy"]
+    assert (E.max() - E.min()) / abs(E.mean()) <= 1.05 * (Eref.max() - Eref.min()) / abs(Eref.mean())
+    an = Analyser(sm2)
+    assert an.r_vecs.shape == (500, 36, 2) and an.speeds.shape == (500, 36)
+    np.testing.assert_allclose(an.total_energy, E)
+    # state attributes after the run
+    np.testing.assert_array_equal(sim.r_vec, r[499])
+    assert sim.mean_pe == pe[499] and sim.mean_ke == ke[499] and sim.temp == 1.0
+    st = sim.stats()
+    assert st["steps"] == 500 and st["force_evals"] == 501  # a(t+dt) reused: one evaluation per step + the first
+
+
+def test_strict_two_evals_and_fp32_modes(in_tmp_cwd):  # noqa: F811
+    from mdsea_b200.potentials import Potential
+
+    g = load_golden("lj_3d_n512")
+    kw = dict(simid="x", ndim=3, num_particles=512, steps=60, vol_fraction=0.3, radius_particle=0.5)
+    sm, sim = _run(kw, dict(force_evals_per_step=2), Potential.lennardjones(1, 1), 0)
+    assert sim.stats()["force_evals"] == 120
+    np.testing.assert_allclose(sm.get_ds("pot_energy"), g["pot_energy"][:60], rtol=1e-10)
+    sm, sim = _run(kw, dict(precision="fp32"), Potential.lennardjones(1, 1), 0)
+    np.testing.assert_allclose(sm.get_ds("pot_energy"), g["pot_energy"][:60], rtol=1e-5)
+    np.testing.assert_allclose(sm.get_ds("kin_energy"), g["kin_energy"][:60], rtol=1e-5)
+
+
+def test_hbc_boundedmie_gravity_quench_through_api(in_tmp_cwd):  # noqa: F811
+    from mdsea_b200.potentials import Potential
+
+    g = load_golden("initsetup_boundedmie_hbc")  # examples/initsetup.py
+    sm, sim = _run(dict(simid="i", ndim=3, num_particles=27, steps=240, vol_fraction=0.1, radius_particle=0.5, pbc=False,
+                        temp=1), {}, Potential.boundedmie(a=0.2, epsilon=1, sigma=1, m=12, n=6), 8)
+    np.testing.assert_allclose(sm.get_ds("pot_energy")[:100], g["pot_energy"][:100], rtol=1e-10)
+    np.testing.assert_allclose(sm.get_ds("kin_energy")[:100], g["kin_energy"][:100], rtol=1e-10)
+
+    g = load_golden("gravity_hbc_3d")
+    sm, sim = _run(dict(simid="g", ndim=3, num_particles=27, steps=60, vol_fraction=0.1, radius_particle=0.5, pbc=False),
+                   dict(gravity=True), Potential.lennardjones(1, 1), 7)
+    np.testing.assert_allclose(sm.get_ds("kin_energy"), g["kin_energy"], rtol=1e-10)
+
+    g = load_golden("quench_3d")
+    sm, sim = _run(dict(simid="q", ndim=3, num_particles=64, steps=40, vol_fraction=0.3, radius_particle=0.5,
+                        quench_temps=[0.5, 0.1], quench_timings=[0.25, 0.75]), dict(flush_every=7),
+                   Potential.lennardjones(1, 1), 6)
+    np.testing.assert_allclose(sm.get_ds("temp"), g["temp"], rtol=1e-10)
+    np.testing.assert_allclose(sm.get_ds("kin_energy"), g["kin_energy"], rtol=1e-10)
+
+    g = load_golden("isothermal_2d")
+    sm, sim = _run(dict(simid="t", ndim=2, num_particles=36, steps=40, vol_fraction=0.2, radius_particle=0.5),
+                   dict(isothermal=True, flush_every=16), Potential.lennardjones(1, 1), 4)
+    np.testing.assert_allclose(sm.get_ds("temp"), g["temp"], rtol=1e-10)
+    np.testing.assert_allclose(sm.get_ds("kin_energy"), g["kin_energy"], rtol=1e-10)
+
+
+def test_manual_stepping_and_attribute_edits(in_tmp_cwd):  # noqa: F811
+    """for sim.step in range(...): sim.advance(); sim.update_files() -- the reference's own loop body."""
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    g = load_golden("lj_3d_n64")
+    with config_context(k_boltzmann=1.0):
+        sm = SysManager.new(simid="m", ndim=3, num_particles=64, steps=10, vol_fraction=0.3, radius_particle=0.5)
+        np.random.seed(0)
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), force_evals_per_step=2)
+        for sim.step in range(0, 10):
+            sim.advance()
+            sim.update_files()
+        np.testing.assert_allclose(sm.get_ds("pot_energy"), g["pot_energy"][:10], rtol=1e-10)
+        acc = sim.update_acc()
+        assert acc.shape == (3, 64)
+        d = sim.update_dists()
+        assert d.shape == (64 * 63 // 2,) and sim.drunits.shape == (64 * 63 // 2, 3)
+        # editing the state on the host is picked up by the next device call
+        sim.v_vec[:] = 0.0
+        sim.advance()
+        assert sim.mean_ke < 1e-3

@@ -1,0 +1,186 @@
+"""CPU: host-side mirror of the reference interface (no compute calls into the CUDA library)."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden
+
+
+@pytest.fixture()
+def in_tmp_cwd(tmp_path, monkeypatch):
+    """Simfile paths are cwd-relative and frozen at first import (constants/fileman.py); repoint them."""
+    monkeypatch.chdir(tmp_path)
+    from mdsea_b200.constants import fileman as cfm
+
+    base = str(tmp_path / "simfiles")
+    monkeypatch.setattr(cfm, "DIR_SIMFILES", base)
+    monkeypatch.setattr(cfm, "SIM_PATH", base + "/{}")
+    monkeypatch.setattr(cfm, "VIS_PATH", base + "/{}/vis")
+    monkeypatch.setattr(cfm, "PNG_PATH", base + "/{}/vis/png")
+    monkeypatch.setattr(cfm, "MP4_PATH", base + "/{}/vis/mp4")
+    monkeypatch.setattr(cfm, "BLENDER_PATH", base + "/{}/vis/blender")
+    monkeypatch.setattr(cfm, "DATA_PATH", base + "/{}/data.h5")
+    monkeypatch.setattr(cfm, "SETTINGS_PATH", base + "/{}/settings.pkl")
+    return tmp_path
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_initial_conditions_bit_exact(name):
+    """gen.py parity: lattice, Maxwell-Boltzmann velocities (global RNG call order, np.prod quirk), LEN_BOX, dt."""
+    from mdsea_b200 import quicker
+    from mdsea_b200.config import config_context
+    from mdsea_b200.gen import PosGen, VelGen
+    from mdsea_b200.helpers import get_dt, nsphere_volume
+
+    g = load_golden(name)
+    nd, n = int(g["sm_ndim"]), int(g["sm_num_particles"])
+    radius, vf = float(g["sm_radius_particle"]), float(g["sm_vol_fraction"])
+    L = (n * nsphere_volume(nd, radius) / vf) ** (1 / nd)
+    assert L == float(g["boxlen"])
+    r0 = PosGen(ndim=nd, boxlen=L, nparticles=n).simplecubic()
+    np.testing.assert_array_equal(r0, g["r0"])
+    with config_context(k_boltzmann=1.0):
+        from mdsea_b200.config import Config
+
+        np.random.seed(int(g["seed"]))
+        v0 = VelGen(ndim=nd, nparticles=n).mb(float(g["sm_mass"]) if "sm_mass" in g else 1,
+                                               float(g["sm_temp"]) if "sm_temp" in g else 1, Config.k_boltzmann)
+    np.testing.assert_array_equal(v0, g["v0"])
+    if "solver_dt" not in g:
+        assert get_dt(radius, float(quicker.norm(v0, axis=0).mean())) == float(g["dt"])
+
+
+def test_sysmanager_contract(in_tmp_cwd):
+    from mdsea_b200.core import SysManager
+
+    sm = SysManager.new(simid="abc", ndim=2, num_particles=36, steps=5, vol_fraction=0.2, radius_particle=0.5,
+                        quench_temps=[0.5], quench_timings=[0.4])
+    root = in_tmp_cwd / "simfiles" / "abc"
+    assert (root / "data.h5").exists() and (root / "settings.pkl").exists()
+    for d in ("vis", "vis/png", "vis/mp4", "vis/blender"):
+        assert (root / d).is_dir()
+    assert sm.all_dsnames == ["r_coords", "v_coords", "pot_energy", "kin_energy", "temp"]
+    assert sm.QUENCH_STEP == [2] and abs(sm.LEN_BOX - 11.889981892818033) < 1e-12
+    with open(root / "settings.pkl", "rb") as f:
+        st = pickle.load(f)
+    assert sorted(st) == sorted(["radius_particle", "num_particles", "vol_fraction", "steps", "ndim", "mass", "temp", "pbc",
+                                 "quench_temps", "quench_steps", "quench_timings", "new_sim", "simid"])
+    # the file is closed after initfilesys; the first update_ds reopens it and retries (core.py:329-340)
+    assert not sm.dfile.id.valid
+    sm.update_ds("pot_energy", [1.5], 0)
+    sm.update_ds("r_coords", [np.ones((2, 36))], 4)
+    assert sm.dfile.id.valid
+    sm.update_ds_block("kin_energy", np.arange(3.0), 1)
+    sm2 = SysManager.load("abc")
+    assert sm2.NUM_PARTICLES == 36 and sm2.STEPS == 5 and not sm2.new_sim
+    assert sm2.get_ds("r_coords").shape == (5, 2, 36) and sm2.get_ds("pot_energy")[0] == 1.5
+    np.testing.assert_array_equal(sm2.get_ds("kin_energy"), [0, 0, 1, 2, 0])
+    np.testing.assert_array_equal(sm2.get_ds("r_coords")[4], 1.0)
+    with pytest.raises(SystemExit):
+        sm2.initfilesys()
+    with pytest.raises(FileNotFoundError):
+        SysManager.load("missing")
+    sm.delete()
+    assert not root.exists()
+
+
+def test_potentials_match_oracle_and_map_to_device():
+    from mdsea_b200.potentials import Potential
+    from oracle.oracle_np import MiePotential
+
+    r = np.linspace(0.8, 3.0, 50)
+    lj = Potential.lennardjones(0.7, 1.1)
+    o = MiePotential(epsilon=0.7, sigma=1.1)
+    np.testing.assert_allclose(lj.force(r), o.dvdr(r), rtol=1e-14)
+    np.testing.assert_allclose(lj.potential(r), o.energy(r), rtol=1e-14)
+    bm = Potential.boundedmie(a=0.2, epsilon=1, sigma=1, m=12, n=6)
+    ob = MiePotential(a=0.2)
+    np.testing.assert_allclose(bm.force(r), ob.dvdr(r), rtol=1e-14)
+    assert abs(lj.potminimum() - 1.1 * 2 ** (1 / 6)) < 1e-6
+    assert lj.device_params() == dict(kind=1, epsilon=0.7, sigma=1.1, m=12.0, n=6.0, a=0.0)
+    assert Potential.mie(1, 1, 9, 6).device_params()["m"] == 9.0
+    assert bm.device_params()["a"] == 0.2
+    assert Potential.ideal().device_params()["kind"] == 0 and Potential.ideal().force(r) == 0
+    with pytest.raises(NotImplementedError):
+        Potential(force=lambda r: -r, potential=lambda r: r * r / 2).device_params()
+
+
+def test_config_context():
+    from mdsea_b200.config import Config, config_context
+
+    kb = Config.k_boltzmann
+    assert abs(kb - 1.380649e-23) < 1e-30
+    with config_context(k_boltzmann=1.0):
+        assert Config.k_boltzmann == 1.0
+    assert Config.k_boltzmann == kb
+    with pytest.raises(AttributeError):
+        Config.update({"nope": 1})
+
+
+def test_solver_argument_errors_without_gpu(in_tmp_cwd):
+    """Error behaviour of the reference that does not need the device."""
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    sm = SysManager.new(simid="e", ndim=2, num_particles=16, steps=3, vol_fraction=0.2, radius_particle=0.5)
+    with config_context(k_boltzmann=1.0):
+        with pytest.raises(KeyError):
+            ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), algorithm="leapfrog")
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), restitution_coeff=0.5)
+        with pytest.raises(NotImplementedError):
+            sim.advance()
+        sim = ContinuousPotentialSolver(sm, pot=Potential(force=lambda r: r, potential=lambda r: r))
+        with pytest.raises(NotImplementedError):
+            sim.run_simulation()
+        with pytest.raises(ValueError):
+            ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), precision="fp16")
+    with pytest.raises(AssertionError):  # simplecubic needs a perfect ndim-th power (gen.py:147-148)
+        ContinuousPotentialSolver(SysManager.new(simid="f", ndim=2, num_particles=15, steps=1, vol_fraction=0.2,
+                                                 radius_particle=0.5, initfilesys=False))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """The shared library builds for sm_100a without a GPU, loads, and exports what include/mdsea_b200.h declares."""
+    from mdsea_b200 import _build, _capi
+
+    lib_path = _build.build()
+    assert os.path.exists(lib_path)
+    lib = ctypes.CDLL(lib_path)
+    hdr = open(os.path.join(ROOT, "include", "mdsea_b200.h")).read()
+    declared = set(re.findall(r"\b(mdsea_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared and declared == set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.mdsea_b200_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.mdsea_b200_version()
+    # struct layout agreement between the header and the ctypes mirror
+    assert ctypes.sizeof(_capi.Params) == 200 and ctypes.sizeof(_capi.RunArgs) == 32 and ctypes.sizeof(_capi.Rows) == 40
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device, creating a context raises."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mdsea_b200 import _capi
+
+    with pytest.raises(_capi.MdseaError) as ei:
+        _capi.Context(ndim=2, num_particles=4, boxlen=4.0, mass=1.0, radius=0.5, dt=0.01, pbc=1, pot_kind=1,
+                      epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0)
+    assert ei.value.status == -2
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mdsea_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+                assert "/root/reference" not in src, fn
