@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- LJ pair-interactions/s and timesteps/s of the ContinuousPotentialSolver step loop on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--precision fp64|fp32]
+    python bench.py --impl reference ...      # the CPU implementation of the same path on the host cores
+
+One bench "step" = one pass of the hot path over one batch: `md_steps` consecutive MD timesteps of the
+workload, issued as ONE call of the C ABI (mdsea_b200_run).  Prints ONE JSON line (rank 0).
+
+value    unique in-cutoff LJ pair interactions per second, whole job, state resident in HBM, timed with CUDA
+         events on the library's stream (rows are still buffered in the device ring every step).
+e2e      same metric through the C ABI with HOST buffers: every step uploads the batch's initial (r, v) from
+         pinned memory and copies the batch's dataset rows back, inside the timed region.
+roofline dominant kernel: the force kernel (CUDA-core FP pipe; peak = FMA micro-benchmark run here, because
+         MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks), plus the HBM-bound integrator.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_UNIQUE_PAIR = {3: 45.0, 2: 34.0, 1: 23.0}
+
+WORKLOADS = {
+    # configs[1] of BASELINE.json: 3-D LJ fluid, 4096 particles, vf 0.3, all-pairs tiled kernel
+    "c2": dict(name="3D LJ fluid N=4096 vf=0.3 all-pairs (BASELINE configs[1])", ndim=3, per_row=16, vf=0.3,
+               r_cutoff=0.0, skin=0.0, md_steps=200, precision="fp64"),
+    # configs[2]: 3-D LJ liquid, 1M particles, cell list + Verlet skin
+    "c3": dict(name="3D LJ liquid N=1e6 vf=0.3 rc=2.5 skin=0.3 cell+Verlet list (BASELINE configs[2])", ndim=3,
+               per_row=100, vf=0.3, r_cutoff=2.5, skin=0.3, md_steps=20, precision="fp32"),
+}
+
+
+# ---------------------------------------------------------------------------------------------------
+def initial_state(ndim, per_row, vf, seed=0):
+    """gen.py initial conditions (lattice + Maxwell-Boltzmann, k_B = 1) through the product's own generators."""
+    from mdsea_b200 import quicker
+    from mdsea_b200.gen import PosGen, VelGen
+    from mdsea_b200.helpers import get_dt, nsphere_volume
+
+    n = per_row ** ndim
+    L = (n * nsphere_volume(ndim, 0.5) / vf) ** (1 / ndim)
+    r0 = PosGen(ndim=ndim, boxlen=L, nparticles=n).simplecubic()
+    np.random.seed(seed)
+    v0 = VelGen(ndim=ndim, nparticles=n).mb(1.0, 1.0, 1.0)
+    dt = get_dt(0.5, float(quicker.norm(v0, axis=0).mean()))
+    return n, L, r0, v0, dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.lines, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU restatement of the reference's algorithm (oracle/), the only
+# place bench.py executes oracle code.  The reference itself is Python and cannot travel to the GPU box.
+# ---------------------------------------------------------------------------------------------------
+def cpu_allpairs_numpy(wl, steps, warmup):
+    from oracle.oracle_np import MiePotential, OracleSolver
+
+    n, L, r0, v0, dt = initial_state(wl["ndim"], wl["per_row"], wl["vf"])
+    o = OracleSolver(r=r0, v=v0, boxlen=L, dt=dt, pot=MiePotential())
+    for _ in range(warmup):
+        o.advance()
+    p0 = o.pairs_evaluated
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.advance()
+    t = time.perf_counter() - t0
+    return dict(pairs=o.pairs_evaluated - p0, seconds=t, md_steps=steps, n=n, cores=1,
+                sample=f"{steps} verlet step(s) = {2 * steps} force evaluations of the same N={n} state, NumPy float64 "
+                       f"restatement of the reference (single-threaded like the reference)")
+
+
+def run_reference_arm(args, wl):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    if wl["r_cutoff"] > 0:
+        from oracle import oracle_c
+
+        res = oracle_c.bench_cutoff(wl, steps=args.steps, warmup=args.warmup)
+    else:
+        res = cpu_allpairs_numpy(wl, args.steps, args.warmup)
+    value = res["pairs"] / res["seconds"]
+    line = {
+        "impl": "reference", "metric": "LJ pair-interactions/s", "value": value, "unit": "pair-interactions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "timesteps_per_s": res["md_steps"] / res["seconds"],
+        "config": {"workload": wl["name"], "md_steps_per_step": res["md_steps"] // max(args.steps, 1), "k_boltzmann": 1.0},
+        "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def make_ctx(wl, n, L, dt, device, precision, ring, rank=0, world=1, proc_grid=(1, 1, 1), evals=1):
+    from mdsea_b200 import _capi
+
+    return _capi.Context(ndim=wl["ndim"], num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0,
+                         pot_kind=1, precision=0 if precision == "fp64" else 1, epsilon=1.0, sigma=1.0, mie_m=12.0,
+                         mie_n=6.0, mie_a=0.0, r_cutoff=wl["r_cutoff"], skin=wl["skin"], force_evals_per_step=evals,
+                         ring_rows=ring, device=device, rank=rank, world=world, proc_grid=proc_grid)
+
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from mdsea_b200 import _capi
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    precision = args.precision or wl["precision"]
+    md_steps = args.md_steps or wl["md_steps"]
+    n, L, r0, v0, dt = initial_state(wl["ndim"], wl["per_row"], wl["vf"], seed=rank)
+    ndim = wl["ndim"]
+
+    ctx = make_ctx(wl, n, L, dt, local, precision, md_steps, evals=args.evals)
+    ctx.set_temperature(1.0)
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    r_pin, v_pin = pin((ndim, n)), pin((ndim, n))
+    r_pin[:], v_pin[:] = r0, v0
+    rows = dict(r=pin((md_steps, ndim, n)), v=pin((md_steps, ndim, n)), pe=pin((md_steps,)), ke=pin((md_steps,)),
+                temp=pin((md_steps,)))
+    rows_dev = dict(r=None, v=None, pe=rows["pe"], ke=rows["ke"], temp=rows["temp"])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(body, steps):
+        """steps x body(), each bracketed by its own event pair on the library's stream, L2 flushed in between."""
+        evs = []
+        for _ in range(steps):
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            body()
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    # ---------------- device-resident throughput ("value") ----------------
+    ctx.set_state(r_pin, v_pin)
+    def body_dev():
+        ctx.run(md_steps, kb=1.0, record=True, rows=rows_dev)
+    for _ in range(args.warmup):
+        body_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s0 = ctx.stats()
+    t_wall0 = time.perf_counter()
+    ms = timed_loop(body_dev, args.steps)
+    t_wall = time.perf_counter() - t_wall0
+    barrier()
+    s1 = ctx.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    pairs = s1["pair_evals_unique"] - s0["pair_evals_unique"]
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    fevals = s1["force_evals"] - s0["force_evals"]
+    t_dev = sum(ms) * 1e-3
+    energy_ok = bool(np.isfinite(rows["pe"]).all() and np.isfinite(rows["ke"]).all())
+
+    # ---------------- end to end through the C ABI with host buffers ----------------
+    def body_e2e():
+        ctx.set_state(r_pin, v_pin)
+        ctx.run(md_steps, kb=1.0, record=True, rows=rows)
+    body_e2e()
+    barrier()
+    p0 = ctx.stats()["pair_evals_unique"]
+    e2e_times = []
+    for _ in range(args.steps):
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        body_e2e()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    e2e_pairs = ctx.stats()["pair_evals_unique"] - p0
+    t_e2e = sum(e2e_times)
+    h2d = 2 * ndim * n * 8
+    d2h = md_steps * (2 * ndim * n + 3) * 8
+
+    # ---------------- per-kernel roofline numbers (library's own CUDA-event timers) ----------------
+    ctx.set_state(r_pin, v_pin)
+    ctx.run(md_steps, kb=1.0, record=True, rows=rows_dev)
+    ctx.set_profiling(True)
+    q0 = ctx.stats()
+    ctx.run(md_steps, kb=1.0, record=True, rows=rows_dev)
+    q1 = ctx.stats()
+    ctx.set_profiling(False)
+    f_evals = q1["force_evals"] - q0["force_evals"]
+    f_ms = (q1["ms_force"] - q0["ms_force"]) / max(f_evals, 1)
+    f_pairs = (q1["pair_evals_unique"] - q0["pair_evals_unique"]) / max(f_evals, 1)
+    flops = FLOP_PER_UNIQUE_PAIR[ndim] * f_pairs
+    fp64 = precision == "fp64"
+    peak_tf = _capi.measure_fma_peak(local, fp64=fp64)
+    achieved_tf = flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    i_ms = (q1["ms_integrate"] - q0["ms_integrate"]) / max(md_steps, 1)
+    integ_bytes = (15 * 8 + 2 * 8) * ndim * n / ndim  # r,v,a read + r,v write + row r,v write, per particle-component group
+    integ_bytes = n * ndim * (5 * 8 + 2 * 8)          # per component: read r,v,a; write r,v; write row r,v
+    roof_hbm = None
+    if i_ms > 0:
+        roof_hbm = {"bound": "hbm", "kernel": "fused integrator (kick_finish + kick_drift)", "achieved": integ_bytes / (i_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": integ_bytes / (i_ms * 1e-3) / 1e9 / hbm_peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+
+    # ---------------- aggregate over ranks ----------------
+    t_dev_max, t_e2e_max, tot_pairs, tot_e2e_pairs = t_dev, t_e2e, pairs, e2e_pairs
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        pp = torch.tensor([pairs, e2e_pairs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(pp, op=dist.ReduceOp.SUM)
+        t_dev_max, t_e2e_max = tt.tolist()
+        tot_pairs, tot_e2e_pairs = pp.tolist()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            if wl["r_cutoff"] > 0:
+                from oracle import oracle_c
+
+                res = oracle_c.bench_cutoff(wl, steps=2, warmup=0)
+            else:
+                res = cpu_allpairs_numpy(wl, 2, 0)
+            cpu = {"value": res["pairs"] / res["seconds"], "unit": "pair-interactions/s", "cores": res["cores"],
+                   "kind": "port", "sample": res["sample"], "timesteps_per_s": res["md_steps"] / res["seconds"],
+                   "host_nproc": os.cpu_count()}
+        line = {
+            "metric": "LJ pair-interactions/s", "value": tot_pairs / t_dev_max, "unit": "pair-interactions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if fp64 else "f32 pair math, f64 state", "data": "synthetic",
+            "timesteps_per_s": world * args.steps * md_steps / t_dev_max,
+            "config": {"workload": wl["name"], "particles_per_gpu": n, "md_steps_per_step": md_steps,
+                       "force_evals_per_md_step": fevals / (args.steps * md_steps), "precision": precision,
+                       "k_boltzmann": 1.0, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": "replicas only (all-pairs does not shard)" if wl["r_cutoff"] <= 0 else f"dd{world}"},
+            "e2e": {"value": tot_e2e_pairs / t_e2e_max, "unit": "pair-interactions/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "timesteps_per_s": world * args.steps * md_steps / t_e2e_max,
+                    "ms_per_step": 1e3 * t_e2e_max / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64" if fp64 else "fp32", "kernel": "all-pairs force" if wl["r_cutoff"] <= 0 else "neighbour-list force",
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "flop_per_unique_pair": FLOP_PER_UNIQUE_PAIR[ndim], "unique_pairs_per_launch": f_pairs,
+                         "ms_per_launch": f_ms,
+                         "peak_source": "FMA micro-benchmark of the CUDA-core pipe measured in this run "
+                                        "(MEASURED_PEAKS.json has no CUDA-core FP peak)"},
+            "roofline_hbm": roof_hbm,
+            "cpu_baseline": cpu, "clocks": clocks, "energies_finite": energy_ok,
+            "host_wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None, choices=["fp64", "fp32"])
+    ap.add_argument("--md-steps", type=int, default=None, help="MD timesteps per bench step (one C-ABI run call)")
+    ap.add_argument("--evals", type=int, default=1, choices=[1, 2], help="force evaluations per MD step (2 = reference-faithful)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,8 +97,9 @@ typedef struct {
 } mdsea_run_args;
 
 /* caller-owned host buffers receiving the rows of one run() call, in HDF5 row layout
- * (core.py:236-242).  r/v may be NULL (energies only).  Pinned memory makes the copies
- * asynchronous with respect to the host. */
+ * (core.py:236-242).  r/v may be NULL: with record_coords the rows are then still written to the
+ * device ring (the on-device buffering of the dataset writes) but not copied to the host.
+ * Pinned memory makes the copies asynchronous with respect to the host. */
 typedef struct {
     double *r;    /* [nsteps][ndim][N]  -> r_coords rows */
     double *v;    /* [nsteps][ndim][N]  -> v_coords rows */

@@ -191,8 +191,8 @@ class Context:
             assert qbuf.shape == (nsteps, 2)
             a.quench_targets = qbuf.ctypes.data_as(C.POINTER(C.c_double))
         rw = Rows()
-        rw.r = rows["r"].ctypes.data if record else None
-        rw.v = rows["v"].ctypes.data if record else None
+        rw.r = rows["r"].ctypes.data if (record and rows.get("r") is not None) else None
+        rw.v = rows["v"].ctypes.data if (record and rows.get("v") is not None) else None
         rw.pe, rw.ke, rw.temp = rows["pe"].ctypes.data, rows["ke"].ctypes.data, rows["temp"].ctypes.data
         fn = self.lib.mdsea_b200_run_async if asynchronous else self.lib.mdsea_b200_run
         self._ck(fn(self.h, C.byref(a), C.byref(rw)))

@@ -9,6 +9,8 @@
 // 148 SMs.  Each (i, j-chunk) partial force is written once, coalesced, to
 // fpart[chunk][dim][i]; the integrator sums the chunks in fixed order (no atomics, run-to-run
 // deterministic).  Sign convention: dr = r_j - r_i, a_i += dr * (dV/dr)/(r m)  (simulator.py:266,301-305).
+#include <stdlib.h>
+
 #include "ctx.h"
 
 #define AP_TI 128  // particles i per block == j tile length
@@ -72,7 +74,7 @@ __device__ __forceinline__ void md_pair(double r2, bool ok, const PotF64 &P, dou
 template <int POTK>
 __device__ __forceinline__ void md_pair(float r2, bool ok, const PotF32 &P, float &s, float &u) {
     if (POTK == POTF_LJ) {
-        float inv = ok ? __frcp_rn(r2) : 0.0f;
+        float inv = ok ? md_rcpf(r2) : 0.0f;
         float t2 = P.sigma2_s * inv;
         float t6 = t2 * t2 * t2;
         float w = fmaf(-2.0f, t6, 1.0f);
@@ -80,7 +82,7 @@ __device__ __forceinline__ void md_pair(float r2, bool ok, const PotF32 &P, floa
         u = fmaf(t6, t6, -t6);
     } else {
         float aprs = P.a2_s + r2;
-        float inv = ok ? __frcp_rn(aprs) : 0.0f;
+        float inv = ok ? md_rcpf(aprs) : 0.0f;
         float tm, tn;
         if (P.mi >= 0 && P.ni >= 0 && !((P.mi | P.ni) & 1)) {
             float t2 = P.sigma2_s * inv;
@@ -101,11 +103,94 @@ __device__ __forceinline__ void md_pair(float r2, bool ok, const PotF32 &P, floa
 // ---------------------------------------------------------------------------------------------
 // fp64 kernel
 // ---------------------------------------------------------------------------------------------
+// exact reference image of one component (rare path, out of line): d - rint(d / L) * L, IEEE division
+__device__ __noinline__ double ap_exact_image(double x0, double L) {
+    return __dsub_rn(x0, __dmul_rn(rint(__ddiv_rn(x0, L)), L));
+}
+
+// one j tile against this thread's particle.  SELF: the tile contains particle i itself (diagonal tile).
+// The hot loop is branch-free so that ptxas can interleave the unrolled pairs (the fp64 pipe has a long
+// dependent chain per pair): the minimum image uses rint(x * (1/L)); a pair whose imaged component lands
+// within ~1e-6 L of the half-box tie -- where rint(x / L) of the reference could choose the other image --
+// is masked out of the hot loop, remembered in a 128-bit per-thread mask, and redone afterwards with the
+// exact IEEE expression of simulator.py:272.
+template <int NDIM, int POTK, bool CUT, bool PBC, bool SELF>
+__device__ __forceinline__ void ap_tile_f64(const double (*sj)[AP_TI], int nj, int self_k, const double *ri,
+                                            const BoxDev &box, const PotF64 &P, double rc2, int tie_hi,
+                                            double *f, double &pe, unsigned &cnt) {
+    const int L_hi = __double2hiint(box.L), L_lo = __double2loint(box.L);
+#pragma unroll 1
+    for (int k0 = 0; k0 < nj; k0 += 32) {
+        unsigned flagged = 0u;
+        if (k0 + 32 <= nj) {
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                const int k = k0 + b;
+                double dd[NDIM], r2 = 0.0;
+                int    amax = 0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    double x = sj[d][k] - ri[d];
+                    if (PBC) {
+                        // |x| < 1.5 L for any sane state, so rint(x/L) is -1, 0 or +1: subtract copysign(L, x)
+                        // when |x| > L/2 (sign transplant on the integer pipe, one DSETP + one predicated DADD).
+                        // Anything that is still >= ~L/2 afterwards (near-tie, or |x| >= 1.5 L) is flagged.
+                        const int    hi = __double2hiint(x);
+                        const double Ls = __hiloint2double((hi & 0x80000000) | L_hi, L_lo);
+                        if (fabs(x) > box.halfL) x -= Ls;
+                        amax = max(amax, __double2hiint(x) & 0x7fffffff);
+                    }
+                    dd[d] = x;
+                    r2 = fma(x, x, r2);
+                }
+                bool ok = true;
+                if (PBC) {
+                    const bool tie = amax >= tie_hi;
+                    flagged |= (tie ? 1u : 0u) << b;
+                    ok = !tie;
+                }
+                if (SELF) ok = ok && (k != self_k);
+                if (CUT) ok = ok && (r2 < rc2);
+                double s, u;
+                md_pair<POTK>(r2, ok, P, s, u);
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) f[d] = fma(dd[d], s, f[d]);
+                pe += u;
+                cnt += ok ? 1u : 0u;
+            }
+        } else {  // ragged tail of the last tile: everything through the exact path below
+            flagged = (1u << (nj - k0)) - 1u;
+        }
+        // rare: exact redo of the masked pairs
+        while (flagged) {
+            const int b = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const int k = k0 + b;
+            double dd[NDIM], r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                double x = sj[d][k] - ri[d];
+                if (PBC) x = ap_exact_image(x, box.L);
+                dd[d] = x;
+                r2 = fma(x, x, r2);
+            }
+            bool ok = !SELF || (k != self_k);
+            if (CUT) ok = ok && (r2 < rc2);
+            double s, u;
+            md_pair<POTK>(r2, ok, P, s, u);
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) f[d] = fma(dd[d], s, f[d]);
+            pe += u;
+            cnt += ok ? 1u : 0u;
+        }
+    }
+}
+
 template <int NDIM, int POTK, bool CUT, bool PBC>
 __global__ void __launch_bounds__(AP_TI)
 k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF64 P, double rc2,
                double *__restrict__ fpart, double *__restrict__ pe_part,
-               unsigned long long *__restrict__ cnt_part) {
+               unsigned long long *__restrict__ cnt_part, StepScalars *__restrict__ sc) {
     __shared__ double sj[NDIM][AP_TI];
     __shared__ double red[32];
     __shared__ unsigned redu[32];
@@ -121,8 +206,10 @@ k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF
     }
     double   pe = 0.0;
     unsigned cnt = 0;
-    const int j0 = blockIdx.y * jchunk;
+    const int j0 = blockIdx.y * jchunk;   // jchunk is a multiple of AP_TI: tiles are aligned with the i blocks
     const int j1 = min(n, j0 + jchunk);
+    // any |x| >= L/2 (1 - 2e-6) shares or exceeds this high word (20 mantissa bits: band ~1e-6 L, conservative)
+    const int tie_hi = __double2hiint(box.halfL * (1.0 - 2e-6));
 
     for (int jt = j0; jt < j1; jt += AP_TI) {
         __syncthreads();
@@ -133,25 +220,10 @@ k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF
         }
         __syncthreads();
         const int nj = min(AP_TI, j1 - jt);
-#pragma unroll 4
-        for (int k = 0; k < nj; ++k) {
-            double dd[NDIM], r2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < NDIM; ++d) {
-                double x = sj[d][k] - ri[d];
-                if (PBC) x = md_minimg(x, box.L, box.invL);
-                dd[d] = x;
-                r2 = fma(x, x, r2);
-            }
-            bool ok = (jt + k) != ic;
-            if (CUT) ok = ok && (r2 < rc2);
-            double s, u;
-            md_pair<POTK>(r2, ok, P, s, u);
-#pragma unroll
-            for (int d = 0; d < NDIM; ++d) f[d] = fma(dd[d], s, f[d]);
-            pe += u;
-            cnt += ok ? 1u : 0u;
-        }
+        if (jt == (int)(blockIdx.x * AP_TI))
+            ap_tile_f64<NDIM, POTK, CUT, PBC, true>(sj, nj, ic - jt, ri, box, P, rc2, tie_hi, f, pe, cnt);
+        else
+            ap_tile_f64<NDIM, POTK, CUT, PBC, false>(sj, nj, -1, ri, box, P, rc2, tie_hi, f, pe, cnt);
     }
     if (active) {
 #pragma unroll
@@ -166,6 +238,7 @@ k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF
         const int b = blockIdx.y * gridDim.x + blockIdx.x;
         pe_part[b] = bpe;
         cnt_part[b] = bc;
+        atomicAdd(&sc->pairs_directed, (unsigned long long)bc);  // integer: order-independent, stats only
     }
 }
 
@@ -178,11 +251,82 @@ k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF
 // are re-evaluated from the fp64 positions so that the image and in/out-of-cutoff decisions are
 // exactly those of the fp64 path.  Per-tile fp32 partial sums are folded into fp64 accumulators.
 // ---------------------------------------------------------------------------------------------
+// exact (fp64) separation of one component of one pair, rare path
+template <bool PBC>
+__device__ __noinline__ double ap_exact_sep(const double *__restrict__ r64, size_t j, size_t i, double L, double invL) {
+    double x = r64[j] - r64[i];
+    if (PBC) x = md_minimg(x, L, invL);
+    return x;
+}
+
+template <int NDIM, int POTK, bool CUT, bool PBC, bool SELF>
+__device__ __forceinline__ void ap_tile_f32(const uint32_t (*sj)[AP_TI], int nj, int self_k, int jt, int ic, int n,
+                                            const uint32_t *qi, const double *__restrict__ r64, const BoxDev &box,
+                                            const PotF32 &P, float rc2s, float cut_lo, float cut_hi, double rc2,
+                                            double inv_h, float *f, float &pe, unsigned &cnt) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < nj; k0 += 32) {
+        unsigned flagged = 0u;
+        if (k0 + 32 <= nj) {
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                const int k = k0 + b;
+                float    dd[NDIM], r2 = 0.0f;
+                uint32_t amax = 0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    const int di = (int)(sj[d][k] - qi[d]);
+                    if (PBC) amax = max(amax, (uint32_t)abs(di));
+                    const float x = (float)di;
+                    dd[d] = x;
+                    r2 = fmaf(x, x, r2);
+                }
+                bool slow = PBC && (amax >= 0x7ffff000u);
+                if (CUT) slow = slow || (r2 > cut_lo && r2 < cut_hi);
+                flagged |= (slow ? 1u : 0u) << b;
+                bool ok = !slow;
+                if (SELF) ok = ok && (k != self_k);
+                if (CUT) ok = ok && (r2 < rc2s);
+                float s, u;
+                md_pair<POTK>(r2, ok, P, s, u);
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) f[d] = fmaf(dd[d], s, f[d]);
+                pe += u;
+                cnt += ok ? 1u : 0u;
+            }
+        } else {
+            flagged = (1u << (nj - k0)) - 1u;
+        }
+        while (flagged) {
+            const int b = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const int k = k0 + b;
+            float  dd[NDIM];
+            double r2d = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                const double x = ap_exact_sep<PBC>(r64, (size_t)d * n + (jt + k), (size_t)d * n + ic, box.L, box.invL);
+                r2d = fma(x, x, r2d);
+                dd[d] = (float)(x * inv_h);
+            }
+            const float r2 = (float)(r2d * inv_h * inv_h);
+            bool ok = !SELF || (k != self_k);
+            if (CUT) ok = ok && (r2d < rc2);
+            float s, u;
+            md_pair<POTK>(r2, ok, P, s, u);
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) f[d] = fmaf(dd[d], s, f[d]);
+            pe += u;
+            cnt += ok ? 1u : 0u;
+        }
+    }
+}
+
 template <int NDIM, int POTK, bool CUT, bool PBC>
 __global__ void __launch_bounds__(AP_TI)
 k_allpairs_f32(const uint32_t *__restrict__ q, const double *__restrict__ r64, int n, int jchunk, BoxDev box,
                PotF32 P, float rc2s, double rc2, double inv_h, double *__restrict__ fpart,
-               double *__restrict__ pe_part, unsigned long long *__restrict__ cnt_part) {
+               double *__restrict__ pe_part, unsigned long long *__restrict__ cnt_part, StepScalars *__restrict__ sc) {
     __shared__ uint32_t sj[NDIM][AP_TI];
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
@@ -215,43 +359,12 @@ k_allpairs_f32(const uint32_t *__restrict__ q, const double *__restrict__ r64, i
         float f[NDIM], pe = 0.0f;
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) f[d] = 0.0f;
-#pragma unroll 4
-        for (int k = 0; k < nj; ++k) {
-            float dd[NDIM], r2 = 0.0f;
-            bool  slow = false;
-#pragma unroll
-            for (int d = 0; d < NDIM; ++d) {
-                const int di = (int)(sj[d][k] - qi[d]);
-                if (PBC) slow = slow || ((uint32_t)abs(di) >= 0x7ffff000u);
-                const float x = (float)di;
-                dd[d] = x;
-                r2 = fmaf(x, x, r2);
-            }
-            bool ok = (jt + k) != ic;
-            if (CUT) {
-                slow = slow || (r2 > cut_lo && r2 < cut_hi);
-                ok = ok && (r2 < rc2s);
-            }
-            if (__builtin_expect(slow, 0)) {
-                double r2d = 0.0;
-#pragma unroll
-                for (int d = 0; d < NDIM; ++d) {
-                    double x = r64[(size_t)d * n + (jt + k)] - r64[(size_t)d * n + ic];
-                    if (PBC) x = md_minimg(x, box.L, box.invL);
-                    r2d = fma(x, x, r2d);
-                    dd[d] = (float)(x * inv_h);
-                }
-                r2 = (float)(r2d * inv_h * inv_h);
-                ok = (jt + k) != ic;
-                if (CUT) ok = ok && (r2d < rc2);
-            }
-            float s, u;
-            md_pair<POTK>(r2, ok, P, s, u);
-#pragma unroll
-            for (int d = 0; d < NDIM; ++d) f[d] = fmaf(dd[d], s, f[d]);
-            pe += u;
-            cnt += ok ? 1u : 0u;
-        }
+        if (jt == (int)(blockIdx.x * AP_TI))
+            ap_tile_f32<NDIM, POTK, CUT, PBC, true>(sj, nj, ic - jt, jt, ic, n, qi, r64, box, P, rc2s, cut_lo, cut_hi, rc2,
+                                                    inv_h, f, pe, cnt);
+        else
+            ap_tile_f32<NDIM, POTK, CUT, PBC, false>(sj, nj, -1, jt, ic, n, qi, r64, box, P, rc2s, cut_lo, cut_hi, rc2,
+                                                     inv_h, f, pe, cnt);
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) F[d] += (double)f[d];
         PE += (double)pe;
@@ -269,6 +382,7 @@ k_allpairs_f32(const uint32_t *__restrict__ q, const double *__restrict__ r64, i
         const int b = blockIdx.y * gridDim.x + blockIdx.x;
         pe_part[b] = bpe;
         cnt_part[b] = bc;
+        atomicAdd(&sc->pairs_directed, (unsigned long long)bc);  // integer: order-independent, stats only
     }
 }
 
@@ -291,11 +405,12 @@ int md_allpairs_setup(mdsea_ctx *c) {
     // but never chunks shorter than one tile.
     int want = sms * 8;
     int nsplit = want / c->ap_blocks_x;
+    if (const char *e = getenv("MDSEA_AP_NSPLIT")) nsplit = atoi(e);  // tuning hook
     if (nsplit < 1) nsplit = 1;
     int max_split = md_div_up(n, AP_TI);
     if (nsplit > max_split) nsplit = max_split;
     c->ap_nsplit = nsplit;
-    c->ap_jchunk = md_div_up(n, nsplit);
+    c->ap_jchunk = md_div_up(md_div_up(n, nsplit), AP_TI) * AP_TI;  // whole tiles: the diagonal tile is block-uniform
     c->ap_nsplit = md_div_up(n, c->ap_jchunk);
     c->n_pe_part = c->ap_blocks_x * c->ap_nsplit;
     MD_CUDA(c, cudaMalloc(&c->d_fpart, sizeof(double) * c->E * c->ap_nsplit));
@@ -310,13 +425,13 @@ int md_allpairs_setup(mdsea_ctx *c) {
 template <int NDIM, int POTK, bool CUT, bool PBC>
 static void launch_f64(mdsea_ctx *c, dim3 grid, const PotF64 &P, double rc2) {
     k_allpairs_f64<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(
-        c->d_r, (int)c->n, c->ap_jchunk, c->box, P, rc2, c->d_fpart, c->d_pe_part, c->d_cnt_part);
+        c->d_r, (int)c->n, c->ap_jchunk, c->box, P, rc2, c->d_fpart, c->d_pe_part, c->d_cnt_part, c->d_sc);
 }
 template <int NDIM, int POTK, bool CUT, bool PBC>
 static void launch_f32(mdsea_ctx *c, dim3 grid, const PotF32 &P, float rc2s, double rc2, double inv_h) {
     k_allpairs_f32<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(
         (const uint32_t *)c->d_rhi, c->d_r, (int)c->n, c->ap_jchunk, c->box, P, rc2s, rc2, inv_h, c->d_fpart,
-        c->d_pe_part, c->d_cnt_part);
+        c->d_pe_part, c->d_cnt_part, c->d_sc);
 }
 
 #define AP_DISPATCH(LAUNCH, ...)                                                              \
@@ -356,7 +471,7 @@ int md_allpairs_force(mdsea_ctx *c) {
     const dim3 grid(c->ap_blocks_x, c->ap_nsplit);
     const PotDev &pd = c->pot;
     const double rc2 = c->p.r_cutoff > 0 ? c->p.r_cutoff * c->p.r_cutoff : 0.0;
-    if (c->profiling) cudaEventRecord(c->ev_a, c->stream);
+    md_prof_begin(c);
     if (c->p.precision == MDSEA_FP64) {
         PotF64 P;
         P.c = (pd.fast == POTF_LJ ? 6.0 : 1.0) * pd.lam_eps * pd.inv_mass;
@@ -377,13 +492,7 @@ int md_allpairs_force(mdsea_ctx *c) {
         AP_DISPATCH(launch_f32, c, grid, P, (float)(rc2 * inv_h * inv_h), rc2, inv_h);
         c->stats.kernel_launches += 2;
     }
-    if (c->profiling) {
-        cudaEventRecord(c->ev_b, c->stream);
-        cudaEventSynchronize(c->ev_b);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-        c->stats.ms_force += ms;
-    }
+    md_prof_end(c, &c->stats.ms_force);
     MD_CUDA(c, cudaGetLastError());
     c->stats.force_evals += 1;
     c->stats.pair_evals_executed += (long long)c->n * (long long)c->n;

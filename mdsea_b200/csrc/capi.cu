@@ -343,7 +343,7 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     if (!c->have_state) { md_set_error(c, "run: set_state has not been called"); return MDSEA_ERR_STATE; }
     if (a->nsteps < 1 || a->nsteps > c->ring) return bad(c, "run: nsteps must be in 1..ring_rows");
     if (!rows->pe || !rows->ke || !rows->temp) return bad(c, "run: pe/ke/temp row buffers are required");
-    if (a->record_coords && (!rows->r || !rows->v)) return bad(c, "run: record_coords needs r and v row buffers");
+    // record_coords with NULL r/v: rows are buffered in the device ring but not copied out
     if (!(a->k_boltzmann > 0)) return bad(c, "run: k_boltzmann must be positive");
     MD_CUDA(c, cudaSetDevice(c->p.device));
     if (c->pending) MD_TRY(mdsea_b200_wait(c));
@@ -364,7 +364,7 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     MD_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));
     MD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_done, 0));
     const size_t rowb = sizeof(double) * (size_t)c->ndim * (size_t)c->n_global;
-    if (a->record_coords && !c->cutoff_path) {
+    if (a->record_coords && rows->r && rows->v && !c->cutoff_path) {
         MD_CUDA(c, cudaMemcpyAsync(rows->r, c->d_r_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
         MD_CUDA(c, cudaMemcpyAsync(rows->v, c->d_v_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
     }
@@ -391,7 +391,7 @@ extern "C" int mdsea_b200_wait(mdsea_ctx *c) {
     MD_CUDA(c, cudaEventSynchronize(c->ev_copy_done));
     c->pending = false;
     if (c->cutoff_path) MD_TRY(md_cutoff_finish_rows(c));
-    c->stats.pair_evals_unique = (long long)c->h_sc->pairs_unique;
+    c->stats.pair_evals_unique = (long long)(c->h_sc->pairs_directed >> 1);
     if (c->h_sc->overflow_flag) {
         md_set_error(c, "run: neighbour/ghost buffer capacity exceeded (raise max_neighbors)");
         return MDSEA_ERR_CAPACITY;

@@ -63,7 +63,7 @@ struct StepScalars {
     int    ke_valid;   // mean_ke is not None
     double scale;      // velocity scale of the NEXT kick_finish (product of the pending quenches)
     long long first_nonfinite_step;  // -1 while energies are finite
-    unsigned long long pairs_unique; // running count of unique in-cutoff pair interactions
+    unsigned long long pairs_directed; // running count of directed in-cutoff pair evaluations (2 x unique pairs)
     unsigned long long steps_done;
     int    rebuild_flag;             // cutoff path: max displacement exceeded skin/2
     int    overflow_flag;            // capacity overflow reported by a kernel
@@ -113,6 +113,13 @@ __device__ __forceinline__ double md_rcp(double x) {
     double e = fma(-x, y, 1.0);
     double p = fma(e, e, e);
     return fma(y, p, y);
+}
+
+// fp32 reciprocal: one MUFU.RCP (<= 1 ulp), no denormal/special-case slow path
+__device__ __forceinline__ float md_rcpf(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // round-half-even to integer for |x| < 2^51 (RN add of 1.5*2^52), the semantics of np.rint

@@ -59,6 +59,19 @@ struct mdsea_ctx {
 
 void md_set_error(mdsea_ctx *ctx, const char *msg);
 
+// CUDA-event timers around a kernel family; only active in profiling mode (adds a sync per kernel)
+static inline void md_prof_begin(mdsea_ctx *c) {
+    if (c->profiling) cudaEventRecord(c->ev_a, c->stream);
+}
+static inline void md_prof_end(mdsea_ctx *c, double *acc_ms) {
+    if (!c->profiling) return;
+    cudaEventRecord(c->ev_b, c->stream);
+    cudaEventSynchronize(c->ev_b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    *acc_ms += ms;
+}
+
 // allpairs.cu
 int md_allpairs_setup(mdsea_ctx *c);
 int md_allpairs_force(mdsea_ctx *c);          // fills d_fpart / d_pe_part / d_cnt_part from d_r

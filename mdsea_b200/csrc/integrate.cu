@@ -134,7 +134,6 @@ k_finalize(const double *__restrict__ pe_part, const unsigned long long *__restr
         if (!(isfinite(mean_pe) && isfinite(mean_ke)) && sc->first_nonfinite_step < 0) sc->first_nonfinite_step = step_index;
         sc->ke_prev = mean_ke;
         sc->ke_valid = 1;
-        sc->pairs_unique += cnt >> 1;           // every unique pair was visited from both ends
         sc->steps_done += 1;
         // quench bookkeeping for the NEXT step (simulator.py:185-195, 233-239)
         double scale = 1.0, temp = sc->temp;
@@ -207,9 +206,11 @@ int md_apply_bc(mdsea_ctx *c) {
 
 int md_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, const double *fsrc, int nparts, size_t stride) {
     double *acc_out = (do_kick && fsrc != c->d_acc) ? c->d_acc : nullptr;
+    md_prof_begin(c);
     k_kick_drift<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
                                                            do_bc ? 1 : 0, do_kick ? 1 : 0, c->box.pbc, c->box.L,
                                                            c->p.radius, c->p.restitution, c->p.dt);
+    md_prof_end(c, &c->stats.ms_integrate);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;
@@ -226,9 +227,11 @@ int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, 
     double *acc_out = (fsrc != c->d_acc) ? c->d_acc : nullptr;
     double *rr = record ? c->d_r_rows + (size_t)row * c->E : nullptr;
     double *vr = record ? c->d_v_rows + (size_t)row * c->E : nullptr;
+    md_prof_begin(c);
     k_kick_finish<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
                                                             (size_t)(c->ndim - 1) * c->n, c->p.dt, g_dt, c->d_sc,
                                                             c->d_ke_part, rr, vr);
+    md_prof_end(c, &c->stats.ms_integrate);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;

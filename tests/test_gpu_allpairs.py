@@ -130,11 +130,17 @@ def test_lattice_ties_exact_image_choice():
     ref_acc = o.update_acc()
     scale = np.abs(ref_acc).max()
     assert scale > 1e-6  # the tie residual is there
-    for precision, tol in ((0, 1e-10), (1, 2e-5)):
+    pair_scale = o.pair_force_scale()
+    for precision in (0, 1):
         ctx = context_from_settings(s, precision=precision, evals=2, ring=1)
         ctx.set_state(g["r0"], g["v0"])
         acc, _ = ctx.update_acc()
-        assert np.abs(acc - ref_acc).max() <= tol * scale
+        if precision == 0:
+            assert np.abs(acc - ref_acc).max() <= 1e-10 * scale
+        else:
+            # a wrong image flips a ~scale-sized term; fp32 rounding of the cancelling lattice sums is far below that
+            assert np.abs(acc - ref_acc).max() <= 1e-2 * scale
+            assert force_rel_err_pairscale(acc, ref_acc, pair_scale) <= 1e-5
         ctx.close()
 
 
