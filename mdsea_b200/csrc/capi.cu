@@ -364,7 +364,7 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     MD_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));
     MD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_done, 0));
     const size_t rowb = sizeof(double) * (size_t)c->ndim * (size_t)c->n_global;
-    if (a->record_coords && rows->r && rows->v && !c->cutoff_path) {
+    if (a->record_coords && rows->r && rows->v && c->p.world == 1) {
         MD_CUDA(c, cudaMemcpyAsync(rows->r, c->d_r_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
         MD_CUDA(c, cudaMemcpyAsync(rows->v, c->d_v_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
     }

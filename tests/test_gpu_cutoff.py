@@ -1,0 +1,213 @@
+"""GPU parity of the cut-off path (cell list + Verlet list + list force kernels) against the C oracle.
+
+Bit-exact contracts: cell ids, the (cell, id)-sorted order, the neighbour list at every
+rebuild, and the rebuild schedule.  Toleranced: forces / energies / trajectories (fp64 1e-10, fp32 1e-5 in the
+metrics of tests/conftest.py; trajectories over <= 100 steps: 1e-9 L in fp64, 1e-3 in fp32).
+"""
+import numpy as np
+import pytest
+
+from conftest import force_rel_err, force_rel_err_pairscale
+from oracle import oracle_c
+from oracle.oracle_np import MiePotential, OracleSolver, box_length, default_dt, lattice_positions, mb_velocities
+
+pytestmark = pytest.mark.gpu
+
+RC, SKIN = 2.5, 0.3
+
+
+def _ctx(n, L, dt, precision=0, evals=2, ring=32, rc=RC, skin=SKIN, **kw):
+    from mdsea_b200 import _capi
+
+    return _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1,
+                         precision=precision, epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=rc, skin=skin,
+                         force_evals_per_step=evals, ring_rows=ring, device=0, **kw)
+
+
+def _liquid(per_row, seed=0, vf=0.3, melt_steps=40):
+    """gen.py start (lattice + MB), then a short C-oracle run so that the state is no longer a lattice."""
+    n = per_row ** 3
+    L = box_length(3, n, 0.5, vf)
+    np.random.seed(seed)
+    r0 = lattice_positions(3, n, L)
+    v0 = mb_velocities(3, n, 1.0, 1.0, 1.0)
+    # the gen.py quirk leaves vy = vz ~ 0; add a seeded isotropic kick so that the test state is a 3-D liquid
+    rng = np.random.default_rng(seed)
+    v0 = v0 + rng.normal(scale=0.7, size=v0.shape)
+    dt = default_dt(0.5, v0)
+    if melt_steps:
+        s = oracle_c.CutoffSystem(r0, v0, L, RC, SKIN, dt)
+        s.run(melt_steps)
+        r0, v0, _ = s.state()
+        s.close()
+    return n, L, r0, v0, dt
+
+
+def _random(n, L, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-0.02 * L, 1.02 * L, size=(3, n)), rng.normal(size=(3, n))
+
+
+@pytest.mark.parametrize("n,L", [(1000, 14.0), (5000, 20.0), (40000, 41.0)])
+def test_cells_and_order_bit_exact(n, L):
+    r, v = _random(n, L, seed=n)
+    ctx = _ctx(n, L, 1e-3)
+    ctx.set_state(r, v)
+    cell_of, order, nc = ctx.get_cells()
+    ref_cell, ref_order, ref_nc = oracle_c.cells(r, L, RC + SKIN)
+    assert nc == (ref_nc,) * 3
+    np.testing.assert_array_equal(cell_of, ref_cell)
+    np.testing.assert_array_equal(order, ref_order)
+    ctx.close()
+
+
+def test_cells_on_lattice_and_box_edges():
+    n, L, r0, v0, dt = _liquid(12, melt_steps=0)   # perfect lattice: particles sit exactly on cell-boundary multiples
+    r0 = r0.copy()
+    r0[0, :5] = [0.0, L, -1e-300, np.nextafter(L, 0), 1.5 * L]
+    ctx = _ctx(n, L, dt)
+    ctx.set_state(r0, v0)
+    cell_of, order, nc = ctx.get_cells()
+    ref_cell, ref_order, _ = oracle_c.cells(r0, L, RC + SKIN)
+    np.testing.assert_array_equal(cell_of, ref_cell)
+    np.testing.assert_array_equal(order, ref_order)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,L", [(1000, 14.0), (8000, 24.0)])
+def test_neighbor_list_bit_exact_random(n, L):
+    r, v = _random(n, L, seed=7 + n)
+    ctx = _ctx(n, L, 1e-3, max_neighbors=256)
+    ctx.set_state(r, v)
+    off, idx = ctx.get_neighbors()
+    ref_off, ref_idx = oracle_c.neighbors(r, L, RC + SKIN, brute=(n <= 1000))
+    np.testing.assert_array_equal(off, ref_off)
+    np.testing.assert_array_equal(idx, ref_idx)
+    ctx.close()
+
+
+def test_neighbor_list_bit_exact_lattice_ties():
+    """On the perfect lattice many pair distances coincide; 0.3 sigma skin puts shells right at the list radius."""
+    n, L, r0, v0, dt = _liquid(12, melt_steps=0)
+    for skin in (SKIN, 2.0 * L / 12 * np.sqrt(5.0) / 2.0 - RC):  # second value: list radius exactly on a lattice shell
+        ctx = _ctx(n, L, dt, skin=skin, max_neighbors=128)
+        ctx.set_state(r0, v0)
+        off, idx = ctx.get_neighbors()
+        ref_off, ref_idx = oracle_c.neighbors(r0, L, RC + skin)
+        np.testing.assert_array_equal(off, ref_off)
+        np.testing.assert_array_equal(idx, ref_idx)
+        ctx.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_forces_and_pe_vs_oracle(precision):
+    n, L, r, v, dt = _liquid(16)
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref_acc, ref_pe = o.forces()
+    ctx = _ctx(n, L, dt, precision=precision)
+    ctx.set_state(r, v)
+    acc, pe = ctx.update_acc()
+    if precision == 0:
+        assert force_rel_err(acc, ref_acc) <= 1e-10
+        assert abs(pe - ref_pe) <= 1e-10 * abs(ref_pe)
+    else:
+        onp = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(), r_cutoff=RC)
+        assert force_rel_err_pairscale(acc, ref_acc, onp.pair_force_scale()) <= 1e-5
+        assert force_rel_err(acc, ref_acc) <= 1e-4
+        assert abs(pe - ref_pe) <= 1e-5 * abs(ref_pe)
+    ctx.close()
+    o.close()
+
+
+@pytest.mark.parametrize("evals", [2, 1])
+def test_fp64_run_matches_oracle_with_identical_rebuild_schedule(evals):
+    n, L, r, v, dt = _liquid(16)
+    steps = 100
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref = o.run(steps, record=True)
+    oc = o.counters()
+    ctx = _ctx(n, L, dt, precision=0, evals=evals, ring=25)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    pe, ke, rr = [], [], []
+    for _ in range(steps // 25):
+        rows = ctx.run(25, kb=1.0)
+        pe.append(rows["pe"].copy()); ke.append(rows["ke"].copy()); rr.append(rows["r"].copy())
+    pe, ke, rr = np.concatenate(pe), np.concatenate(ke), np.concatenate(rr)
+    np.testing.assert_allclose(pe, ref["pe"], rtol=1e-10)
+    np.testing.assert_allclose(ke, ref["ke"], rtol=1e-10)
+    assert np.abs(rr - ref["r"]).max() <= 1e-9 * L
+    st = ctx.stats()
+    assert st["list_rebuilds"] == oc["rebuilds"] and oc["rebuilds"] >= 3
+    assert st["force_evals"] == (2 * steps if evals == 2 else steps + 1)
+    if evals == 2:
+        assert st["pair_evals_unique"] == oc["pairs_unique"]
+    # the list in force at the end is the oracle's, entry for entry
+    off, idx = ctx.get_neighbors()
+    ref_off, ref_idx = o.neighbor_list()
+    np.testing.assert_array_equal(off, ref_off)
+    np.testing.assert_array_equal(idx, ref_idx)
+    ctx.close()
+    o.close()
+
+
+def test_fp32_run_matches_oracle():
+    n, L, r, v, dt = _liquid(16)
+    steps = 100
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref = o.run(steps, record=True)
+    ctx = _ctx(n, L, dt, precision=1, evals=1, ring=50)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    rows1 = {k: v.copy() for k, v in ctx.run(50, kb=1.0).items()}
+    rows2 = ctx.run(50, kb=1.0)
+    pe = np.concatenate([rows1["pe"], rows2["pe"]]); ke = np.concatenate([rows1["ke"], rows2["ke"]])
+    np.testing.assert_allclose(pe, ref["pe"], rtol=1e-5)
+    np.testing.assert_allclose(ke, ref["ke"], rtol=1e-5)
+    assert np.abs(rows2["r"][-1] - ref["r"][-1]).max() <= 1e-3
+    assert np.abs(rows2["v"][-1] - ref["v"][-1]).max() <= 1e-3
+    ctx.close()
+    o.close()
+
+
+def test_cutoff_path_from_lattice_start_through_python_api(tmp_path, monkeypatch):
+    """SysManager / ContinuousPotentialSolver with r_cutoff: gen.py start, rows in original particle order."""
+    from test_host_cpu import in_tmp_cwd  # noqa: F401
+
+    monkeypatch.chdir(tmp_path)
+    from mdsea_b200.config import config_context
+    from mdsea_b200.constants import fileman as cfm
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    base = str(tmp_path / "simfiles")
+    for name, suffix in (("DIR_SIMFILES", ""), ("SIM_PATH", "/{}"), ("VIS_PATH", "/{}/vis"), ("PNG_PATH", "/{}/vis/png"),
+                         ("MP4_PATH", "/{}/vis/mp4"), ("BLENDER_PATH", "/{}/vis/blender"), ("DATA_PATH", "/{}/data.h5"),
+                         ("SETTINGS_PATH", "/{}/settings.pkl")):
+        monkeypatch.setattr(cfm, name, base + suffix)
+    with config_context(k_boltzmann=1.0):
+        sm = SysManager.new(simid="cut", ndim=3, num_particles=14 ** 3, steps=30, vol_fraction=0.3, radius_particle=0.5)
+        np.random.seed(0)
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), r_cutoff=RC, skin=SKIN, force_evals_per_step=2)
+        r0, v0, dt = sim.r_vec.copy(), sim.v_vec.copy(), sim.dt
+        sim.run_simulation()
+    o = oracle_c.CutoffSystem(r0, v0, sm.LEN_BOX, RC, SKIN, dt)
+    ref = o.run(30, record=True)
+    np.testing.assert_allclose(sm.get_ds("pot_energy"), ref["pe"], rtol=1e-10)
+    np.testing.assert_allclose(sm.get_ds("kin_energy"), ref["ke"], rtol=1e-10)
+    assert np.abs(sm.get_ds("r_coords") - ref["r"]).max() <= 1e-9 * sm.LEN_BOX
+    assert np.abs(sm.get_ds("v_coords") - ref["v"]).max() <= 1e-9
+    o.close()
+
+
+def test_neighbor_capacity_overflow_is_reported():
+    from mdsea_b200 import _capi
+
+    n, L, r, v, dt = _liquid(10, melt_steps=0)
+    ctx = _ctx(n, L, dt, max_neighbors=8)
+    ctx.set_state(r, v)
+    with pytest.raises(_capi.MdseaError) as ei:
+        ctx.run(1, kb=1.0)
+    assert ei.value.status == -6
+    ctx.close()
