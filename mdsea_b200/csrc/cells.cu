@@ -13,8 +13,8 @@
 // Layout in HBM: particles live in CELL-SORTED SLOT ORDER between rebuilds (SoA float64 r, v, acc with row
 // stride `cap`, plus their global id); the force kernels gather neighbours from a packed AoS copy of the
 // positions that the drift kernel refreshes every step (double4 in fp64 mode; uint4 32-bit fixed point in
-// fp32 mode, where integer subtraction gives the minimum image for free).  The neighbour list is stored
-// column-major, nbr[k * n_pad + i], so that a warp of consecutive particles reads it coalesced.
+// fp32 mode, where integer subtraction gives the minimum image for free).  The neighbour list is a sliced
+// ELLPACK (tiles of 32 particles x max_nbr rows) so that a warp of consecutive particles reads it coalesced.
 #include <algorithm>
 
 #include "ctx.h"
@@ -37,7 +37,8 @@ struct CellState {
     void   *pos4 = nullptr;               // double4[cap] (fp64) or uint4[cap] (fp32)
     unsigned long long *key = nullptr, *key_alt = nullptr;
     int    *val = nullptr, *val_alt = nullptr;
-    int    *hist = nullptr;
+    int    *hist = nullptr, *hist_tot = nullptr;
+    uint4  *qfix = nullptr;               // 32-bit fixed-point positions, refreshed at every rebuild (list prefilter)
     int     sort_blocks = 0;
     int    *cell = nullptr;               // cell id per slot (sorted)
     int    *cell_start = nullptr;         // ncell + 1
@@ -113,16 +114,17 @@ k_sort_hist(const unsigned long long *__restrict__ key, long long n, int shift, 
     hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];  // digit-major: the scan yields global offsets
 }
 
-// exclusive scan of m ints by a single block (m ~ 256 * n/2048: 1.3e5 at N = 1e6)
-__global__ void __launch_bounds__(1024) k_scan_excl(int *__restrict__ a, int m) {
-    __shared__ int part[1024];
-    const int per = (m + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(m, lo + per);
+// per-digit exclusive scan over the blocks: one CTA per digit row (nblk entries); row totals go to tot[256]
+__global__ void __launch_bounds__(256) k_sort_rowscan(int *__restrict__ hist, int nblk, int *__restrict__ tot) {
+    __shared__ int part[256];
+    int *row = hist + (size_t)blockIdx.x * nblk;
+    const int per = (nblk + 255) / 256;
+    const int lo = threadIdx.x * per, hi = min(nblk, lo + per);
     int s = 0;
-    for (int k = lo; k < hi; ++k) s += a[k];
+    for (int k = lo; k < hi; ++k) s += row[k];
     part[threadIdx.x] = s;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    for (int o = 1; o < 256; o <<= 1) {
         const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
         __syncthreads();
         part[threadIdx.x] += v;
@@ -130,20 +132,34 @@ __global__ void __launch_bounds__(1024) k_scan_excl(int *__restrict__ a, int m) 
     }
     int run = part[threadIdx.x] - s;
     for (int k = lo; k < hi; ++k) {
-        const int v = a[k];
-        a[k] = run;
+        const int v = row[k];
+        row[k] = run;
         run += v;
     }
+    if (threadIdx.x == 255) tot[blockIdx.x] = part[255];
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const unsigned long long *__restrict__ key_in, const int *__restrict__ val_in,
                unsigned long long *__restrict__ key_out, int *__restrict__ val_out, long long n, int shift,
-               const int *__restrict__ hist, int nblk) {
+               const int *__restrict__ hist, int nblk, const int *__restrict__ tot) {
     __shared__ int warp_cnt[SORT_THREADS / 32][256];
     __shared__ int digit_base[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    digit_base[threadIdx.x] = hist[threadIdx.x * nblk + blockIdx.x];
+    {   // global offset of digit d = sum of the totals of all smaller digits (256-entry block scan) + row scan
+        const int mine = tot[threadIdx.x];
+        digit_base[threadIdx.x] = mine;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const int v = threadIdx.x >= o ? digit_base[threadIdx.x - o] : 0;
+            __syncthreads();
+            digit_base[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const int excl = digit_base[threadIdx.x] - mine;
+        __syncthreads();
+        digit_base[threadIdx.x] = excl + hist[threadIdx.x * nblk + blockIdx.x];
+    }
     const long long base = (long long)blockIdx.x * SORT_CHUNK;
     for (int t = 0; t < SORT_ITEMS; ++t) {
 #pragma unroll
@@ -221,46 +237,84 @@ __device__ __forceinline__ uint32_t md_to_fixed(double x, double inv_h) {
     return (uint32_t)(unsigned long long)__double2ll_rn(x * inv_h);
 }
 __global__ void k_pack_positions(const double *__restrict__ r, long long n, long long cap, int fp32, double inv_h,
-                                 void *__restrict__ pos4) {
+                                 void *__restrict__ pos4, uint4 *__restrict__ qfix) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = r[i], y = r[cap + i], z = r[2 * cap + i];
-    if (fp32) ((uint4 *)pos4)[i] = make_uint4(md_to_fixed(x, inv_h), md_to_fixed(y, inv_h), md_to_fixed(z, inv_h), 0u);
+    const uint4 q = make_uint4(md_to_fixed(x, inv_h), md_to_fixed(y, inv_h), md_to_fixed(z, inv_h), 0u);
+    qfix[i] = q;
+    if (fp32) ((uint4 *)pos4)[i] = q;
     else ((double4 *)pos4)[i] = make_double4(x, y, z, 0.0);
+}
+
+// Neighbour-list layout: sliced ELLPACK.  Particles are grouped in tiles of 32 consecutive slots (= one warp of
+// the force kernel); tile t owns max_nbr rows of 32 ints, entry (k, lane) at t*max_nbr*32 + k*32 + lane.  The
+// force kernel reads one 128-byte row per k (coalesced); the build kernel's stores of one warp all land in the
+// same ~15 KB tile, so partially written sectors merge in L2 instead of being evicted half empty.
+__device__ __forceinline__ size_t md_nbr_index(long long i, int k, int max_nbr) {
+    return ((size_t)(i >> 5) * (size_t)max_nbr + (size_t)k) * 32u + (size_t)(i & 31);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K3: Verlet neighbour list.  One thread per particle; the 27-cell stencil of consecutive (cell-sorted)
 // particles overlaps almost completely, so the candidate loads are L1 broadcasts.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nb_scan_range(int j0, int j1, const uint4 qi, long long i, const double *__restrict__ r,
+                                              const uint4 *__restrict__ q, long long cap, double L, double halfL, double rl2,
+                                              float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ row0, int &cnt) {
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+        // prefilter in 32-bit fixed point: exact integer separations (minimum image by wrap-around), r^2 in
+        // float; only candidates within 1e-5 (relative) of the list radius -- far more than the ~5e-7 the float
+        // evaluation can be off -- go through the canonical float64 test
+        const uint4 qj = q[j];
+        const float fx = (float)(int)(qj.x - qi.x), fy = (float)(int)(qj.y - qi.y), fz = (float)(int)(qj.z - qi.z);
+        const float r2f = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+        bool in = r2f < rl2s_lo;
+        if (__builtin_expect(!in && r2f < rl2s_hi, 0)) {
+            const double ddx = md_minimg_exact(__dsub_rn(r[j], r[i]), L, halfL);
+            const double ddy = md_minimg_exact(__dsub_rn(r[cap + j], r[cap + i]), L, halfL);
+            const double ddz = md_minimg_exact(__dsub_rn(r[2 * cap + j], r[2 * cap + i]), L, halfL);
+            in = md_r2_canonical(ddx, ddy, ddz) < rl2;
+        }
+        if (in && j != (int)i) {
+            if (cnt < max_nbr) row0[cnt * 32] = j;
+            ++cnt;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NB_THREADS)
-k_nbr_build(const double *__restrict__ r, long long n_own, long long cap, const int *__restrict__ cell,
-            const int *__restrict__ cell_start, int nc, double L, double halfL, double rl2, int max_nbr, long long n_pad,
-            int *__restrict__ nbr, int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
+k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
+            const int *__restrict__ cell, const int *__restrict__ cell_start, int nc, double L, double halfL, double rl2,
+            float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
+            StepScalars *__restrict__ sc) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_own) return;
-    const double xi = r[i], yi = r[cap + i], zi = r[2 * cap + i];
+    const uint4 qi = q[i];
     const int c = cell[i];
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
+    int *row0 = nbr + md_nbr_index(i, 0, max_nbr);
     int cnt = 0;
     for (int dz = -1; dz <= 1; ++dz) {
         const int z = (cz + dz + nc) % nc;
         for (int dy = -1; dy <= 1; ++dy) {
             const int y = (cy + dy + nc) % nc;
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = (cx + dx + nc) % nc;
-                const int cc = (z * nc + y) * nc + x;
-                const int k1 = cell_start[cc + 1];
-                for (int j = cell_start[cc]; j < k1; ++j) {
-                    const double ddx = md_minimg_exact(__dsub_rn(r[j], xi), L, halfL);
-                    const double ddy = md_minimg_exact(__dsub_rn(r[cap + j], yi), L, halfL);
-                    const double ddz = md_minimg_exact(__dsub_rn(r[2 * cap + j], zi), L, halfL);
-                    const double r2 = md_r2_canonical(ddx, ddy, ddz);
-                    if (r2 < rl2 && j != (int)i) {
-                        if (cnt < max_nbr) nbr[(long long)cnt * n_pad + i] = j;
-                        ++cnt;
-                    }
-                }
+            const int row = (z * nc + y) * nc;
+            // the three x-adjacent cells are one contiguous slot range unless the stencil wraps around the box
+            if (cx > 0 && cx < nc - 1) {
+                nb_scan_range(cell_start[row + cx - 1], cell_start[row + cx + 2], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo,
+                              rl2s_hi, max_nbr, row0, cnt);
+            } else if (cx == 0) {
+                nb_scan_range(cell_start[row + nc - 1], cell_start[row + nc], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi,
+                              max_nbr, row0, cnt);
+                nb_scan_range(cell_start[row], cell_start[row + 2], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr,
+                              row0, cnt);
+            } else {
+                nb_scan_range(cell_start[row + nc - 2], cell_start[row + nc], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi,
+                              max_nbr, row0, cnt);
+                nb_scan_range(cell_start[row], cell_start[row + 1], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr,
+                              row0, cnt);
             }
         }
     }
@@ -279,7 +333,7 @@ struct LjF32 { float c6, sigma2; };    // in fixed-point units (see allpairs.cu)
 
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f64(const double4 *__restrict__ pos, long long n_own, long long cap, const int *__restrict__ nbr,
-                const int *__restrict__ nbr_cnt, long long n_pad, double L, double halfL, double rc2, LjF64 P,
+                const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, LjF64 P,
                 double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
@@ -289,9 +343,10 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long n_own, long long cap,
     if (i < n_own) {
         const double4 pi = pos[i];
         const int nn = nbr_cnt[i];
+        const int *__restrict__ row0 = nbr + md_nbr_index(i, 0, max_nbr);
 #pragma unroll 4
         for (int k = 0; k < nn; ++k) {
-            const int j = nbr[(long long)k * n_pad + i];
+            const int j = row0[k * 32];
             const double4 pj = pos[j];
             const double dx = md_minimg_list(pj.x - pi.x, L, halfL);
             const double dy = md_minimg_list(pj.y - pi.y, L, halfL);
@@ -322,7 +377,7 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long n_own, long long cap,
 
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long n_own, long long cap,
-                const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, long long n_pad, double L, double halfL,
+                const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
                 double rc2, float rc2s, double inv_h, LjF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
                 StepScalars *__restrict__ sc) {
     __shared__ double   red[32];
@@ -333,14 +388,15 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, l
     if (i < n_own) {
         const uint4 qi = pos[i];
         const int   nn = nbr_cnt[i];
+        const int *__restrict__ row0 = nbr + md_nbr_index(i, 0, max_nbr);
         const float cut_lo = rc2s * (1.0f - 2e-6f), cut_hi = rc2s * (1.0f + 2e-6f);
         for (int k0 = 0; k0 < nn; k0 += 32) {
             float    fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
             unsigned flagged = 0u;
             const int kn = min(32, nn - k0);
-#pragma unroll 4
+#pragma unroll 8
             for (int b = 0; b < kn; ++b) {
-                const int   j = nbr[(long long)(k0 + b) * n_pad + i];
+                const int   j = row0[(k0 + b) * 32];
                 const uint4 qj = pos[j];
                 const int   ix = (int)(qj.x - qi.x), iy = (int)(qj.y - qi.y), iz = (int)(qj.z - qi.z);
                 const float dx = (float)ix, dy = (float)iy, dz = (float)iz;
@@ -363,7 +419,7 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, l
             while (flagged) {  // rare: decide and evaluate from the float64 positions
                 const int b = __ffs(flagged) - 1;
                 flagged &= flagged - 1;
-                const int    j = nbr[(long long)(k0 + b) * n_pad + i];
+                const int    j = row0[(k0 + b) * 32];
                 const double ex = md_minimg_list(r64[j] - r64[i], L, halfL);
                 const double ey = md_minimg_list(r64[cap + j] - r64[cap + i], L, halfL);
                 const double ez = md_minimg_list(r64[2 * cap + j] - r64[2 * cap + i], L, halfL);
@@ -519,6 +575,8 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->val, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->val_alt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->hist, sizeof(int) * 256 * (size_t)s->sort_blocks));
+    MD_CUDA(c, cudaMalloc(&s->hist_tot, sizeof(int) * 256));
+    MD_CUDA(c, cudaMalloc(&s->qfix, sizeof(uint4) * (size_t)s->cap));
     MD_CUDA(c, cudaMalloc(&s->cell, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->cell_start, sizeof(int) * ((size_t)s->ncell + 1)));
     MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
@@ -546,7 +604,7 @@ void md_cells_free(mdsea_ctx *c) {
     CellState *s = c->cells;
     if (!s) return;
     cudaFree(s->r_alt); cudaFree(s->v_alt); cudaFree(s->rb); cudaFree(s->id); cudaFree(s->id_alt); cudaFree(s->pos4);
-    cudaFree(s->key); cudaFree(s->key_alt); cudaFree(s->val); cudaFree(s->val_alt); cudaFree(s->hist);
+    cudaFree(s->key); cudaFree(s->key_alt); cudaFree(s->val); cudaFree(s->val_alt); cudaFree(s->hist); cudaFree(s->hist_tot); cudaFree(s->qfix);
     cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->nbr); cudaFree(s->nbr_cnt); cudaFree(s->scratch);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     delete s;
@@ -584,8 +642,9 @@ static int rebuild(mdsea_ctx *c) {
     const int nblk = md_div_up(n, SORT_CHUNK);
     for (int sh : shifts) {
         k_sort_hist<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, n, sh, s->hist, nblk);
-        k_scan_excl<<<1, 1024, 0, c->stream>>>(s->hist, 256 * nblk);
-        k_sort_scatter<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, s->val, s->key_alt, s->val_alt, n, sh, s->hist, nblk);
+        k_sort_rowscan<<<256, 256, 0, c->stream>>>(s->hist, nblk, s->hist_tot);
+        k_sort_scatter<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, s->val, s->key_alt, s->val_alt, n, sh, s->hist, nblk,
+                                                             s->hist_tot);
         std::swap(s->key, s->key_alt);
         std::swap(s->val, s->val_alt);
         launches += 3;
@@ -596,10 +655,14 @@ static int rebuild(mdsea_ctx *c) {
     std::swap(c->d_v, s->v_alt);
     std::swap(s->id, s->id_alt);
     k_cell_bounds<<<g256, 256, 0, c->stream>>>(s->cell, n, s->ncell, s->cell_start);
-    k_pack_positions<<<g256, 256, 0, c->stream>>>(c->d_r, n, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4);
-    k_nbr_build<<<md_div_up(n, NB_THREADS), NB_THREADS, 0, c->stream>>>(c->d_r, n, s->cap, s->cell, s->cell_start, s->nc,
-                                                                        c->box.L, c->box.halfL, s->rl2, s->max_nbr, s->n_pad,
-                                                                        s->nbr, s->nbr_cnt, c->d_sc);
+    k_pack_positions<<<g256, 256, 0, c->stream>>>(c->d_r, n, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, s->qfix);
+    {
+        const double ih = fixed_inv_h(c);
+        const double rl2s = s->rl2 * ih * ih;
+        k_nbr_build<<<md_div_up(n, NB_THREADS), NB_THREADS, 0, c->stream>>>(
+            c->d_r, s->qfix, n, s->cap, s->cell, s->cell_start, s->nc, c->box.L, c->box.halfL, s->rl2,
+            (float)(rl2s * (1.0 - 1e-5)), (float)(rl2s * (1.0 + 1e-5)), s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
+    }
     launches += 4;
     MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
     md_prof_end(c, &c->stats.ms_rebuild);
@@ -620,7 +683,7 @@ int md_cutoff_force(mdsea_ctx *c) {
         LjF64 P;
         P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
         P.sigma2 = c->pot.sigma2;
-        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, n, s->cap, s->nbr, s->nbr_cnt, s->n_pad,
+        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, n, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
                                                             c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part, c->d_sc);
     } else {
         const double inv_h = fixed_inv_h(c);
@@ -628,7 +691,7 @@ int md_cutoff_force(mdsea_ctx *c) {
         P.c6 = (float)(6.0 * c->pot.lam_eps * c->pot.inv_mass * inv_h);
         P.sigma2 = (float)(c->pot.sigma2 * inv_h * inv_h);
         k_nbr_force_f32<<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, n, s->cap, s->nbr, s->nbr_cnt,
-                                                            s->n_pad, c->box.L, c->box.halfL, s->rc2,
+                                                            s->max_nbr, c->box.L, c->box.halfL, s->rc2,
                                                             (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc, c->d_pe_part,
                                                             c->d_sc);
     }
@@ -768,7 +831,7 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
     MD_CUDA(c, cudaMemcpy(nbr.data(), s->nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost));
     for (long long k = 0; k < n; ++k) {
         int32_t *row = idx + offsets[id[k]];
-        for (int m = 0; m < cnt[k]; ++m) row[m] = id[nbr[(size_t)m * s->n_pad + k]];
+        for (int m = 0; m < cnt[k]; ++m) row[m] = id[nbr[((size_t)(k >> 5) * s->max_nbr + m) * 32 + (k & 31)]];
         std::sort(row, row + cnt[k]);
     }
     return MDSEA_OK;

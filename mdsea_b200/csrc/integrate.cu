@@ -94,37 +94,29 @@ k_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double
 }
 
 // single block; deterministic fixed-order tree over the partial sums
-__global__ void __launch_bounds__(256)
-k_finalize(const double *__restrict__ pe_part, const unsigned long long *__restrict__ cnt_part, int n_pe,
+__global__ void __launch_bounds__(1024)
+k_finalize(const double *__restrict__ pe_part, int n_pe,
            const double *__restrict__ ke_part, int n_ke, double pe_factor /* lam_eps / 2 / N */,
            double ke_factor /* 0.5 m / N */, double kb, StepScalars *__restrict__ sc, double *__restrict__ pe_rows,
            double *__restrict__ ke_rows, double *__restrict__ temp_rows, int row, const double *__restrict__ quench_next,
            long long step_index) {
     __shared__ double red[32];
-    __shared__ unsigned long long redc[32];
     double pe = 0.0, ke = 0.0;
-    unsigned long long cnt = 0;
-    for (int k = threadIdx.x; k < n_pe; k += blockDim.x) {
-        pe += pe_part[k];
-        cnt += cnt_part[k];
+    {   // four independent accumulators per thread: the loads are latency-, not bandwidth-bound
+        double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+        const int st = blockDim.x;
+        int k = threadIdx.x;
+        for (; k + 3 * st < n_pe; k += 4 * st) { p0 += pe_part[k]; p1 += pe_part[k + st]; p2 += pe_part[k + 2 * st]; p3 += pe_part[k + 3 * st]; }
+        for (; k < n_pe; k += st) p0 += pe_part[k];
+        pe = (p0 + p1) + (p2 + p3);
+        p0 = p1 = p2 = p3 = 0;
+        k = threadIdx.x;
+        for (; k + 3 * st < n_ke; k += 4 * st) { p0 += ke_part[k]; p1 += ke_part[k + st]; p2 += ke_part[k + 2 * st]; p3 += ke_part[k + 3 * st]; }
+        for (; k < n_ke; k += st) p0 += ke_part[k];
+        ke = (p0 + p1) + (p2 + p3);
     }
-    for (int k = threadIdx.x; k < n_ke; k += blockDim.x) ke += ke_part[k];
     pe = md_block_sum(pe, red);
     ke = md_block_sum(ke, red);
-    // 64-bit count
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        __syncthreads();
-        if (lane == 0) redc[warp] = cnt;
-        __syncthreads();
-        if (warp == 0) {
-            cnt = lane < (int)(blockDim.x >> 5) ? redc[lane] : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        }
-    }
     if (threadIdx.x == 0) {
         const double mean_pe = pe * pe_factor;  // sum over unique pairs / N, simulator.py:249
         const double mean_ke = ke * ke_factor;  // 0.5 m mean(v.v), simulator.py:244
@@ -242,7 +234,7 @@ int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long 
     const double pe_factor = (c->pot.fast == POTF_IDEAL) ? 0.0 : c->pot.lam_eps * 0.5 / N;
     const double ke_factor = 0.5 * c->p.mass / N;
     const double *qn = next_row_valid ? c->d_quench + (size_t)(row + 1) * 2 : nullptr;
-    k_finalize<<<1, 256, 0, c->stream>>>(c->d_pe_part, c->d_cnt_part, c->n_pe_part, c->d_ke_part, c->n_ke_part, pe_factor,
+    k_finalize<<<1, 1024, 0, c->stream>>>(c->d_pe_part, c->n_pe_part, c->d_ke_part, c->n_ke_part, pe_factor,
                                          ke_factor, kb, c->d_sc, c->d_pe_rows, c->d_ke_rows, c->d_temp_rows, row, qn,
                                          step_index);
     c->stats.kernel_launches += 1;
