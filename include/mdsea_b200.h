@@ -106,6 +106,13 @@ typedef struct {
     double *pe;   /* [nsteps]           -> pot_energy    */
     double *ke;   /* [nsteps]           -> kin_energy    */
     double *temp; /* [nsteps]           -> temp          */
+    /* world > 1 only: each rank returns the rows of the particles it owns, compact, in its slot order:
+     * r / v are [nsteps][ndim][row_stride], ids [nsteps][row_stride] holds the particle id of every column,
+     * n_owned[k] the number of valid columns of row k.  The host scatters column j of row k to
+     * r_coords[step k][:, ids[k][j]] (every particle is owned by exactly one rank).  pe / ke are global. */
+    int32_t *ids;
+    int64_t *n_owned;
+    int64_t  row_stride; /* >= mdsea_b200_rank_capacity(ctx) */
 } mdsea_rows;
 
 typedef struct {
@@ -181,6 +188,13 @@ void *mdsea_b200_stream(mdsea_ctx *ctx);
  * (torch.distributed / file / env), every rank calls comm_init before set_state. */
 int mdsea_b200_nccl_unique_id(void *out128);
 int mdsea_b200_comm_init(mdsea_ctx *ctx, const void *unique_id128);
+/* in-process transport: `world` contexts of ONE process, each driven by its own host thread, exchange through
+ * device-to-device copies behind host barriers (all contexts of a group pass the same group_key).  Lets the
+ * multi-rank code run on a single GPU; the collective calls (set_state, run, update_acc, get_cells,
+ * get_neighbors, destroy) must then be issued by all ranks concurrently, one thread per rank. */
+int mdsea_b200_comm_init_local(mdsea_ctx *ctx, int64_t group_key);
+/* per-rank slot capacity (owned + ghost particles) of the cutoff path; the row_stride to allocate rows with */
+int64_t mdsea_b200_rank_capacity(mdsea_ctx *ctx);
 
 /* device micro-benchmarks used by bench.py for the roofline denominators that
  * MEASURED_PEAKS.json does not hold: dependent-free FMA throughput of the fp32 / fp64

@@ -54,9 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(cc, jobs))
     objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
     if jobs or not os.path.exists(LIB):
-        libs = ["-lcudart"]
-        if any(os.path.basename(s) == "comm.cu" for s in srcs):
-            libs.append("-lnccl")
+        libs = ["-lcudart", "-ldl", "-lpthread"]  # NCCL is dlopen'ed at comm_init time (see csrc/comm.cu)
         r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, *libs, "-gencode", "arch=compute_100a,code=sm_100a"],
                            capture_output=True, text=True)
         if r.returncode != 0:

@@ -40,7 +40,8 @@ class RunArgs(C.Structure):
 
 
 class Rows(C.Structure):
-    _fields_ = [("r", C.c_void_p), ("v", C.c_void_p), ("pe", C.c_void_p), ("ke", C.c_void_p), ("temp", C.c_void_p)]
+    _fields_ = [("r", C.c_void_p), ("v", C.c_void_p), ("pe", C.c_void_p), ("ke", C.c_void_p), ("temp", C.c_void_p),
+                ("ids", C.c_void_p), ("n_owned", C.c_void_p), ("row_stride", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -58,7 +59,8 @@ EXPORTS = [
     "mdsea_b200_get_state", "mdsea_b200_run", "mdsea_b200_run_async", "mdsea_b200_wait", "mdsea_b200_update_acc",
     "mdsea_b200_update_dists", "mdsea_b200_get_cells", "mdsea_b200_get_neighbors", "mdsea_b200_set_temperature",
     "mdsea_b200_get_stats", "mdsea_b200_first_nonfinite_step", "mdsea_b200_set_profiling", "mdsea_b200_stream",
-    "mdsea_b200_nccl_unique_id", "mdsea_b200_comm_init", "mdsea_b200_measure_fma_peak",
+    "mdsea_b200_nccl_unique_id", "mdsea_b200_comm_init", "mdsea_b200_comm_init_local", "mdsea_b200_rank_capacity",
+    "mdsea_b200_measure_fma_peak",
 ]
 
 _lib = None
@@ -100,6 +102,9 @@ def load():
     lib.mdsea_b200_stream.restype = vp
     lib.mdsea_b200_nccl_unique_id.argtypes = [vp]
     lib.mdsea_b200_comm_init.argtypes = [vp, vp]
+    lib.mdsea_b200_comm_init_local.argtypes = [vp, C.c_int64]
+    lib.mdsea_b200_rank_capacity.argtypes = [vp]
+    lib.mdsea_b200_rank_capacity.restype = C.c_int64
     lib.mdsea_b200_measure_fma_peak.argtypes = [i32, i32, dp]
     _lib = lib
     return lib
@@ -129,6 +134,7 @@ class Context:
                 setattr(p, k, v)
         self.params = p
         self.ndim, self.n = int(p.ndim), int(p.num_particles)
+        self.world, self.rank = int(p.world), int(p.rank)
         h = C.c_void_p()
         st = self.lib.mdsea_b200_create(C.byref(p), C.byref(h))
         if st != 0:
@@ -150,6 +156,26 @@ class Context:
         except Exception:
             pass
 
+    # -- multi-rank plumbing ----------------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        lib = load()
+        buf = C.create_string_buffer(128)
+        st = lib.mdsea_b200_nccl_unique_id(buf)
+        if st != 0:
+            raise MdseaError(st, lib.mdsea_b200_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.mdsea_b200_comm_init(self.h, buf))
+
+    def comm_init_local(self, group_key: int):
+        self._ck(self.lib.mdsea_b200_comm_init_local(self.h, int(group_key)))
+
+    def rank_capacity(self) -> int:
+        return int(self.lib.mdsea_b200_rank_capacity(self.h))
+
     def set_state(self, r, v):
         r = np.ascontiguousarray(r, dtype=np.float64)
         v = np.ascontiguousarray(v, dtype=np.float64)
@@ -160,13 +186,15 @@ class Context:
         self._ck(self.lib.mdsea_b200_set_temperature(self.h, float(temp), 1 if reset_ke else 0))
 
     def get_state(self, want_acc=True):
-        r = np.empty((self.ndim, self.n)); v = np.empty_like(r); a = np.empty_like(r) if want_acc else None
+        fill = np.empty if self.world == 1 else (lambda shp: np.full(shp, np.nan))
+        r = fill((self.ndim, self.n)); v = fill((self.ndim, self.n)); a = fill((self.ndim, self.n)) if want_acc else None
         ids = np.empty(self.n, dtype=np.int64); n_owned = C.c_int64(0)
         self._ck(self.lib.mdsea_b200_get_state(self.h, _ptr(r), _ptr(v), _ptr(a) if want_acc else None, _ptr(ids), C.byref(n_owned)))
         return r, v, a, ids[:n_owned.value]
 
     def update_acc(self, want_pe=True):
-        a = np.empty((self.ndim, self.n)); pe = C.c_double(0.0)
+        a = np.empty((self.ndim, self.n)) if self.world == 1 else np.full((self.ndim, self.n), np.nan)
+        pe = C.c_double(0.0)
         self._ck(self.lib.mdsea_b200_update_acc(self.h, _ptr(a), C.byref(pe) if want_pe else None))
         return a, pe.value
 
@@ -180,9 +208,13 @@ class Context:
         """Advance nsteps; returns dict of row arrays (views into `rows` buffers when given)."""
         E = self.ndim * self.n
         if rows is None:
-            rows = dict(r=np.empty((nsteps, self.ndim, self.n)) if record else None,
-                        v=np.empty((nsteps, self.ndim, self.n)) if record else None,
+            width = self.n if self.world == 1 else self.rank_capacity()
+            rows = dict(r=np.empty((nsteps, self.ndim, width)) if record else None,
+                        v=np.empty((nsteps, self.ndim, width)) if record else None,
                         pe=np.empty(nsteps), ke=np.empty(nsteps), temp=np.empty(nsteps))
+            if self.world > 1:
+                rows["ids"] = np.full((nsteps, width), -1, dtype=np.int32)
+                rows["n_owned"] = np.zeros(nsteps, dtype=np.int64)
         a = RunArgs()
         a.nsteps, a.record_coords, a.k_boltzmann, a.gravity_acceleration = nsteps, 1 if record else 0, float(kb), float(g)
         qbuf = None
@@ -194,6 +226,9 @@ class Context:
         rw.r = rows["r"].ctypes.data if (record and rows.get("r") is not None) else None
         rw.v = rows["v"].ctypes.data if (record and rows.get("v") is not None) else None
         rw.pe, rw.ke, rw.temp = rows["pe"].ctypes.data, rows["ke"].ctypes.data, rows["temp"].ctypes.data
+        if self.world > 1 and record and rows.get("ids") is not None:
+            rw.ids, rw.n_owned = rows["ids"].ctypes.data, rows["n_owned"].ctypes.data
+            rw.row_stride = rows["r"].shape[2]
         fn = self.lib.mdsea_b200_run_async if asynchronous else self.lib.mdsea_b200_run
         self._ck(fn(self.h, C.byref(a), C.byref(rw)))
         self._keep = (qbuf, rows)

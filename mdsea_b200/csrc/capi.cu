@@ -364,6 +364,7 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     MD_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));
     MD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_done, 0));
     const size_t rowb = sizeof(double) * (size_t)c->ndim * (size_t)c->n_global;
+    if (c->p.world > 1) MD_TRY(md_cutoff_copy_rows(c, a, rows));
     if (a->record_coords && rows->r && rows->v && c->p.world == 1) {
         MD_CUDA(c, cudaMemcpyAsync(rows->r, c->d_r_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
         MD_CUDA(c, cudaMemcpyAsync(rows->v, c->d_v_rows, rowb * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -402,6 +403,11 @@ extern "C" int mdsea_b200_wait(mdsea_ctx *c) {
 extern "C" int mdsea_b200_run(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows) {
     MD_TRY(mdsea_b200_run_async(c, a, rows));
     return mdsea_b200_wait(c);
+}
+
+extern "C" int64_t mdsea_b200_rank_capacity(mdsea_ctx *c) {
+    if (!c) return 0;
+    return c->cutoff_path ? md_cutoff_capacity(c) : c->n;
 }
 
 extern "C" int mdsea_b200_get_stats(mdsea_ctx *c, mdsea_stats *out) {

@@ -18,13 +18,64 @@
 #include <algorithm>
 
 #include "ctx.h"
+#include "comm.h"
 
 #define SORT_THREADS 256
 #define SORT_ITEMS 8
 #define SORT_CHUNK (SORT_THREADS * SORT_ITEMS)
 #define NB_THREADS 128
 
+// Spatial domain decomposition on the canonical cell grid: rank (bx, by, bz) of a px*py*pz process grid owns the
+// cells with bnd[d][b_d] <= c_d < bnd[d][b_d + 1]; its halo is the one-cell layer around that block (periodic).
+// Ownership and halo membership are functions of the canonical cell id alone, so every rank can evaluate them
+// for any particle and all ranks agree without talking to each other.
+struct Decomp {
+    int world, rank, nc;
+    int p[3];
+    int bnd[3][MD_MAXW + 1];
+};
+__host__ __device__ inline int dc_block(const Decomp &D, int d, int c) {
+    int b = 0;
+    while (b + 1 < D.p[d] && c >= D.bnd[d][b + 1]) ++b;
+    return b;
+}
+__host__ __device__ inline int dc_owner(const Decomp &D, int cx, int cy, int cz) {
+    return (dc_block(D, 2, cz) * D.p[1] + dc_block(D, 1, cy)) * D.p[0] + dc_block(D, 0, cx);
+}
+// is the cell inside rank q's block extended by the one-cell halo?  (true for q's own cells too)
+__host__ __device__ inline bool dc_in_ext(const Decomp &D, int q, int cx, int cy, int cz) {
+    const int b[3] = {q % D.p[0], (q / D.p[0]) % D.p[1], q / (D.p[0] * D.p[1])};
+    const int cc[3] = {cx, cy, cz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int lo = D.bnd[d][b[d]], len = D.bnd[d][b[d] + 1] - lo;
+        if (len + 2 >= D.nc) continue;  // block + halo covers the whole period
+        const int dd = (cc[d] - (lo - 1) + D.nc) % D.nc;
+        if (dd >= len + 2) return false;
+    }
+    return true;
+}
+
+struct PMsg {  // one particle in a rebuild-time message
+    double    r[3], v[3];
+    long long id;
+};
+
 struct CellState {
+    Decomp    D;
+    long long n_tot = 0;                  // owned + ghost slots in use
+    // multi-rank staging
+    PMsg  *sendpool = nullptr, *recvpool = nullptr;
+    long long sendpool_cap = 0;
+    int   *d_cnt = nullptr, *d_cnt_all = nullptr, *d_cursor = nullptr;  // [MAXW], [MAXW*MAXW], [MAXW]
+    int   *h_cnt_all = nullptr;           // pinned [MAXW*MAXW + 8]
+    int   *halo_flag = nullptr, *halo_scan = nullptr, *halo_idx = nullptr;  // [world][cap]
+    int   *scan_tmp = nullptr;
+    long long halo_nsend[MD_MAXW], halo_nrecv[MD_MAXW], halo_base[MD_MAXW];
+    double *halo_send = nullptr, *halo_recv = nullptr;   // packed positions, 3 doubles per entry
+    int   *id_rows = nullptr;             // [ring][cap] ids of the rows buffered on the device (world > 1)
+    std::vector<long long> row_n_own;     // owned count of every buffered row
+    int   *cell_end = nullptr;
     int       nc = 0, ncell = 0;
     double    cell_len = 0, rlist = 0, rl2 = 0, rc2 = 0, trig2 = 0;
     long long cap = 0, n_pad = 0;
@@ -82,17 +133,24 @@ __device__ __forceinline__ double md_r2_canonical(double dx, double dy, double d
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2a: keys.  key = cell id << 32 | particle id ; value = current slot
+// K2a: keys.  key = ghost << 63 | cell id << 32 | particle id ; value = current (staging) slot.
+// Owned particles sort before ghosts; within each class the order is the canonical (cell id, particle id).
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_cell_keys(const double *__restrict__ r, const int *__restrict__ id, long long n, long long cap, double L,
-                            double cl, int nc, unsigned long long *__restrict__ key, int *__restrict__ val) {
+                            double cl, int nc, Decomp D, unsigned long long *__restrict__ key, int *__restrict__ val,
+                            int *__restrict__ n_owned) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int cx = md_cell_coord(r[i], L, cl, nc);
     const int cy = md_cell_coord(r[cap + i], L, cl, nc);
     const int cz = md_cell_coord(r[2 * cap + i], L, cl, nc);
     const unsigned long long c = (unsigned long long)((cz * nc + cy) * nc + cx);
-    key[i] = (c << 32) | (unsigned)id[i];
+    unsigned long long ghost = 0ull;
+    if (D.world > 1) {
+        ghost = dc_owner(D, cx, cy, cz) != D.rank ? 1ull : 0ull;
+        if (!ghost) atomicAdd(n_owned, 1);
+    }
+    key[i] = (ghost << 63) | (c << 32) | (unsigned)id[i];
     val[i] = (int)i;
 }
 
@@ -212,7 +270,7 @@ __global__ void k_reorder(const unsigned long long *__restrict__ key, const int 
     const unsigned long long k = key[s];
     const int o = val[s];
     id_out[s] = (int)(k & 0xffffffffull);
-    cell[s] = (int)(k >> 32);
+    cell[s] = (int)((k >> 32) & 0x7fffffffull);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const double x = r_in[d * cap + o];
@@ -222,14 +280,15 @@ __global__ void k_reorder(const unsigned long long *__restrict__ key, const int 
     }
 }
 
-__global__ void k_cell_bounds(const int *__restrict__ cell, long long n, int ncell, int *__restrict__ cell_start) {
+// [cell_start[c], cell_end[c]) = slots of cell c; both arrays are zeroed first (empty cells: 0, 0).  With ghosts
+// sorted after the owned particles the slot order is no longer globally monotone in the cell id, hence two arrays.
+__global__ void k_cell_bounds(const int *__restrict__ cell, long long n, int *__restrict__ cell_start,
+                              int *__restrict__ cell_end) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int c = cell[s];
-    const int prev = s == 0 ? -1 : cell[s - 1];
-    for (int cc = prev + 1; cc <= c; ++cc) cell_start[cc] = (int)s;
-    if (s == n - 1)
-        for (int cc = c + 1; cc <= ncell; ++cc) cell_start[cc] = (int)n;
+    if (s == 0 || cell[s - 1] != c) cell_start[c] = (int)s;
+    if (s == n - 1 || cell[s + 1] != c) cell_end[c] = (int)s + 1;
 }
 
 // packed position copies for the force gathers
@@ -286,14 +345,15 @@ __device__ __forceinline__ void nb_scan_range(int j0, int j1, const uint4 qi, lo
 
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
-            const int *__restrict__ cell, const int *__restrict__ cell_start, int nc, double L, double halfL, double rl2,
-            float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
-            StepScalars *__restrict__ sc) {
+            const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
+            double L, double halfL, double rl2, float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ nbr,
+            int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_own) return;
     const uint4 qi = q[i];
     const int c = cell[i];
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
+    const int xm = (cx + nc - 1) % nc, xp = (cx + 1) % nc;
     int *row0 = nbr + md_nbr_index(i, 0, max_nbr);
     int cnt = 0;
     for (int dz = -1; dz <= 1; ++dz) {
@@ -301,21 +361,24 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
         for (int dy = -1; dy <= 1; ++dy) {
             const int y = (cy + dy + nc) % nc;
             const int row = (z * nc + y) * nc;
-            // the three x-adjacent cells are one contiguous slot range unless the stencil wraps around the box
-            if (cx > 0 && cx < nc - 1) {
-                nb_scan_range(cell_start[row + cx - 1], cell_start[row + cx + 2], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo,
-                              rl2s_hi, max_nbr, row0, cnt);
-            } else if (cx == 0) {
-                nb_scan_range(cell_start[row + nc - 1], cell_start[row + nc], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi,
-                              max_nbr, row0, cnt);
-                nb_scan_range(cell_start[row], cell_start[row + 2], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr,
-                              row0, cnt);
-            } else {
-                nb_scan_range(cell_start[row + nc - 2], cell_start[row + nc], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi,
-                              max_nbr, row0, cnt);
-                nb_scan_range(cell_start[row], cell_start[row + 1], qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr,
-                              row0, cnt);
+            // the three x-adjacent cells: merge slot ranges that happen to be contiguous (the usual case away from
+            // the periodic wrap and from the owned/ghost boundary)
+            int cs = cell_start[row + xm], ce = cell_end[row + xm];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int cc = row + (t == 0 ? cx : xp);
+                const int s1 = cell_start[cc], e1 = cell_end[cc];
+                if (ce == cs) {            // nothing pending
+                    cs = s1; ce = e1;
+                } else if (e1 != s1) {
+                    if (ce == s1) ce = e1; // contiguous: extend
+                    else {
+                        nb_scan_range(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt);
+                        cs = s1; ce = e1;
+                    }
+                }
             }
+            nb_scan_range(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt);
         }
     }
     nbr_cnt[i] = cnt < max_nbr ? cnt : max_nbr;
@@ -486,15 +549,19 @@ k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *_
 
 __global__ void __launch_bounds__(256)
 k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
-                  const int *__restrict__ id, long long n, long long cap, long long n_global, double dt, double g_dt,
-                  const StepScalars *__restrict__ sc, double *__restrict__ ke_part, double *__restrict__ r_row,
-                  double *__restrict__ v_row) {
+                  const int *__restrict__ id, long long n, long long cap, long long row_stride, int *__restrict__ id_row,
+                  double dt, double g_dt, const StepScalars *__restrict__ sc, double *__restrict__ ke_part,
+                  double *__restrict__ r_row, double *__restrict__ v_row) {
     __shared__ double red[32];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double v2 = 0.0;
     if (i < n) {
         const double scale = sc->scale;
         const int    gid = id[i];
+        // single GPU: rows are written in ORIGINAL particle order (core.py:236-238), scattered by id.
+        // multi-rank: compact rows in slot order plus the ids; the host scatters them into the shared file.
+        const long long col = id_row ? i : (long long)gid;
+        if (id_row) id_row[i] = gid;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             double u = v[d * cap + i] + __dmul_rn(__dmul_rn(0.5, acc[d * cap + i]), dt);
@@ -502,9 +569,9 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
             if (scale != 1.0) u *= scale;
             v[d * cap + i] = u;
             v2 += u * u;
-            if (r_row) {  // rows are kept in ORIGINAL particle order (core.py:236-238)
-                r_row[d * n_global + gid] = r[d * cap + i];
-                v_row[d * n_global + gid] = u;
+            if (r_row) {
+                r_row[d * row_stride + col] = r[d * cap + i];
+                v_row[d * row_stride + col] = u;
             }
         }
     }
@@ -527,6 +594,167 @@ __global__ void k_iota(int *a, long long n) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// generic exclusive scan over ints (three kernels; used for the ordered halo lists)
+// ---------------------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_block(const int *__restrict__ in, int *__restrict__ out, long long n, int *__restrict__ block_sum) {
+    __shared__ int wsum[SCAN_THREADS / 32];
+    const long long base = ((long long)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+    int v[SCAN_ITEMS], t = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        t += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += wsum[w];
+    int run = wbase + incl - t;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == SCAN_THREADS - 1) block_sum[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(1024) k_scan_top(int *__restrict__ a, int m) {
+    __shared__ int part[1024];
+    const int per = (m + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(m, lo + per);
+    int s = 0;
+    for (int k = lo; k < hi; ++k) s += a[k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int k = lo; k < hi; ++k) {
+        const int v = a[k];
+        a[k] = run;
+        run += v;
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(int *__restrict__ out, long long n, const int *__restrict__ block_sum) {
+    const long long base = ((long long)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+    const int add = block_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6: domain decomposition -- rebuild-time migration / ghost selection and per-step halo refresh
+// ---------------------------------------------------------------------------------------------------
+// pass 0 (count) / pass 1 (fill): every held particle goes to each rank whose extended block contains its cell
+__global__ void k_mr_route(const double *__restrict__ r, const double *__restrict__ v, const int *__restrict__ id, long long n,
+                           long long cap, double L, double cl, int nc, Decomp D, int fill, int *__restrict__ counter,
+                           PMsg *__restrict__ pool) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = r[i], y = r[cap + i], z = r[2 * cap + i];
+    const int cx = md_cell_coord(x, L, cl, nc), cy = md_cell_coord(y, L, cl, nc), cz = md_cell_coord(z, L, cl, nc);
+    for (int q = 0; q < D.world; ++q) {
+        if (!dc_in_ext(D, q, cx, cy, cz)) continue;
+        const int pos = atomicAdd(&counter[q], 1);
+        if (fill) {
+            PMsg m;
+            m.r[0] = x; m.r[1] = y; m.r[2] = z;
+            m.v[0] = v[i]; m.v[1] = v[cap + i]; m.v[2] = v[2 * cap + i];
+            m.id = id[i];
+            pool[pos] = m;
+        }
+    }
+}
+__global__ void k_mr_unpack(const PMsg *__restrict__ pool, long long n, long long dst0, long long cap, double *__restrict__ r,
+                            double *__restrict__ v, int *__restrict__ id) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const PMsg m = pool[k];
+    const long long s = dst0 + k;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        r[d * cap + s] = m.r[d];
+        v[d * cap + s] = m.v[d];
+    }
+    id[s] = (int)m.id;
+}
+// set_state with world > 1: keep the particles whose canonical cell this rank owns
+__global__ void k_select_owned(const double *__restrict__ rg, const double *__restrict__ vg, long long n_global, double L,
+                               double cl, int nc, Decomp D, long long cap, double *__restrict__ r, double *__restrict__ v,
+                               int *__restrict__ id, int *__restrict__ counter) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_global) return;
+    const double x = rg[g], y = rg[n_global + g], z = rg[2 * n_global + g];
+    if (dc_owner(D, md_cell_coord(x, L, cl, nc), md_cell_coord(y, L, cl, nc), md_cell_coord(z, L, cl, nc)) != D.rank) return;
+    const int s = atomicAdd(counter, 1);
+    if (s >= cap) return;
+    r[s] = x; r[cap + s] = y; r[2 * cap + s] = z;
+    v[s] = vg[g]; v[cap + s] = vg[n_global + g]; v[2 * cap + s] = vg[2 * n_global + g];
+    id[s] = (int)g;
+}
+
+// flag[q][s]: owned slot s must be SENT to rank q every step (its cell lies in q's halo); ghost slot s is
+// RECEIVED from rank q (q owns its cell).  One scan over the whole [world][n_tot] array then yields, per peer,
+// the send list followed by the receive list, both in slot order = canonical (cell id, particle id) order --
+// the same order on the sending and on the receiving rank, so no index exchange is needed.
+__global__ void k_halo_flags(const int *__restrict__ cell, long long n_own, long long n_tot, int nc, Decomp D,
+                             int *__restrict__ flag) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_tot) return;
+    const int c = cell[s];
+    const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
+    const int owner = dc_owner(D, cx, cy, cz);
+    for (int q = 0; q < D.world; ++q) {
+        int f;
+        if (s < n_own) f = (q != D.rank && dc_in_ext(D, q, cx, cy, cz)) ? 1 : 0;
+        else f = (owner == q) ? 1 : 0;
+        flag[(long long)q * n_tot + s] = f;
+    }
+}
+__global__ void k_halo_lists(const int *__restrict__ flag, const int *__restrict__ scan, long long n_tot, int world,
+                             int *__restrict__ idx) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tot * world) return;
+    if (!flag[t]) return;
+    const long long q = t / n_tot, s = t - q * n_tot;
+    idx[q * n_tot + (scan[t] - scan[q * n_tot])] = (int)s;
+}
+__global__ void k_halo_pack(const double *__restrict__ r, long long cap, const int *__restrict__ idx, long long n,
+                            double *__restrict__ buf) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int s = idx[k];
+    buf[3 * k] = r[s];
+    buf[3 * k + 1] = r[cap + s];
+    buf[3 * k + 2] = r[2 * cap + s];
+}
+__global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restrict__ idx, long long n, long long cap,
+                              double *__restrict__ r, int fp32, double inv_h, void *__restrict__ pos4) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int s = idx[k];
+    const double x = buf[3 * k], y = buf[3 * k + 1], z = buf[3 * k + 2];
+    r[s] = x; r[cap + s] = y; r[2 * cap + s] = z;
+    if (fp32) ((uint4 *)pos4)[s] = make_uint4(md_to_fixed(x, inv_h), md_to_fixed(y, inv_h), md_to_fixed(z, inv_h), 0u);
+    else ((double4 *)pos4)[s] = make_double4(x, y, z, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int bits_for(unsigned long long maxval) {
@@ -534,11 +762,28 @@ static int bits_for(unsigned long long maxval) {
     while ((maxval >> b) != 0) ++b;
     return b;
 }
+static inline double fixed_inv_h(const mdsea_ctx *c) { return 4294967296.0 / c->box.L; }
+static inline int g256(long long n) { return md_div_up(n > 0 ? n : 1, 256); }
+
+static int scan_exclusive(mdsea_ctx *c, const int *in, int *out, long long n) {
+    CellState *s = c->cells;
+    const int nb = md_div_up(n, SCAN_THREADS * SCAN_ITEMS);
+    k_scan_block<<<nb, SCAN_THREADS, 0, c->stream>>>(in, out, n, s->scan_tmp);
+    k_scan_top<<<1, 1024, 0, c->stream>>>(s->scan_tmp, nb);
+    k_scan_add<<<nb, SCAN_THREADS, 0, c->stream>>>(out, n, s->scan_tmp);
+    c->stats.kernel_launches += 3;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
 
 int md_cells_setup(mdsea_ctx *c) {
     CellState *s = new CellState();
     c->cells = s;
     const mdsea_params &p = c->p;
+    if (c->pot.fast != POTF_LJ) {
+        md_set_error(c, "cutoff path: only the Lennard-Jones member of the Mie family is implemented on the list kernels");
+        return MDSEA_ERR_UNSUPPORTED;
+    }
     const double skin = p.skin > 0 ? p.skin : 0.0;
     s->rlist = p.r_cutoff + skin;
     s->rl2 = s->rlist * s->rlist;
@@ -547,16 +792,27 @@ int md_cells_setup(mdsea_ctx *c) {
     s->nc = (int)floor(p.boxlen / s->rlist);
     s->cell_len = p.boxlen / s->nc;
     s->ncell = s->nc * s->nc * s->nc;
-    const long long n = c->n;
-    s->cap = ((n + 31) / 32) * 32;
+    const int W = p.world;
+    // decomposition
+    Decomp &D = s->D;
+    memset(&D, 0, sizeof(D));
+    D.world = W; D.rank = p.rank; D.nc = s->nc;
+    for (int d = 0; d < 3; ++d) D.p[d] = W > 1 ? p.proc_grid[d] : 1;
+    if (D.p[0] * D.p[1] * D.p[2] != W) { md_set_error(c, "cutoff path: proc_grid does not multiply to world"); return MDSEA_ERR_BAD_ARG; }
+    for (int d = 0; d < 3; ++d) {
+        if (D.p[d] < 1 || D.p[d] > MD_MAXW || D.p[d] > s->nc) { md_set_error(c, "cutoff path: proc_grid entry out of range (needs >= 1 cell per rank and dimension)"); return MDSEA_ERR_BAD_ARG; }
+        for (int k = 0; k <= D.p[d]; ++k) D.bnd[d][k] = (int)(((long long)k * s->nc) / D.p[d]);
+    }
+    const long long N = c->n_global;
+    s->cap = W == 1 ? ((N + 31) / 32) * 32 : std::min<long long>(((N + 31) / 32) * 32, ((2 * (N / W) + 65536 + 31) / 32) * 32);
     s->n_pad = s->cap;
     if (p.max_neighbors > 0) s->max_nbr = p.max_neighbors;
     else {
-        const double rho = (double)c->n_global / (p.boxlen * p.boxlen * p.boxlen);
+        const double rho = (double)N / (p.boxlen * p.boxlen * p.boxlen);
         const double expect = 4.0 / 3.0 * 3.14159265358979 * s->rlist * s->rlist * s->rlist * rho;
         s->max_nbr = ((int)(expect * 1.6) + 32 + 7) / 8 * 8;
     }
-    s->id_bits = bits_for((unsigned long long)(c->n_global - 1));
+    s->id_bits = bits_for((unsigned long long)(N - 1));
     s->cell_bits = bits_for((unsigned long long)(s->ncell - 1));
     s->sort_blocks = md_div_up(s->cap, SORT_CHUNK);
     const size_t S = sizeof(double) * 3 * (size_t)s->cap;
@@ -570,97 +826,270 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->id, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->id_alt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->pos4, (p.precision == MDSEA_FP32 ? sizeof(uint4) : sizeof(double4)) * (size_t)s->cap));
+    MD_CUDA(c, cudaMalloc(&s->qfix, sizeof(uint4) * (size_t)s->cap));
     MD_CUDA(c, cudaMalloc(&s->key, sizeof(unsigned long long) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->key_alt, sizeof(unsigned long long) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->val, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->val_alt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->hist, sizeof(int) * 256 * (size_t)s->sort_blocks));
     MD_CUDA(c, cudaMalloc(&s->hist_tot, sizeof(int) * 256));
-    MD_CUDA(c, cudaMalloc(&s->qfix, sizeof(uint4) * (size_t)s->cap));
     MD_CUDA(c, cudaMalloc(&s->cell, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->cell_start, sizeof(int) * ((size_t)s->ncell + 1)));
+    MD_CUDA(c, cudaMalloc(&s->cell_end, sizeof(int) * ((size_t)s->ncell + 1)));
     MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
     MD_CUDA(c, cudaMalloc(&s->nbr_cnt, sizeof(int) * s->cap));
-    MD_CUDA(c, cudaMalloc(&s->scratch, sizeof(double) * 3 * (size_t)c->n_global));
+    MD_CUDA(c, cudaMalloc(&s->d_cnt, sizeof(int) * (MD_MAXW + 8)));
     MD_CUDA(c, cudaMallocHost(&s->h_flag, sizeof(int) * 2));
-    const size_t rowE = (size_t)3 * (size_t)c->n_global;
-    MD_CUDA(c, cudaMalloc(&c->d_r_rows, sizeof(double) * rowE * c->ring));
-    MD_CUDA(c, cudaMalloc(&c->d_v_rows, sizeof(double) * rowE * c->ring));
-    c->n_ke_part = md_div_up(n, 256);
+    MD_CUDA(c, cudaMallocHost(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8)));
+    const size_t row_stride = W == 1 ? (size_t)N : (size_t)s->cap;
+    MD_CUDA(c, cudaMalloc(&c->d_r_rows, sizeof(double) * 3 * row_stride * c->ring));
+    MD_CUDA(c, cudaMalloc(&c->d_v_rows, sizeof(double) * 3 * row_stride * c->ring));
+    c->n_ke_part = md_div_up(s->cap, 256);
     MD_CUDA(c, cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
-    c->n_pe_part = md_div_up(n, NB_THREADS);
+    MD_CUDA(c, cudaMemset(c->d_ke_part, 0, sizeof(double) * c->n_ke_part));
+    c->n_pe_part = md_div_up(s->cap, NB_THREADS);
     MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
-    MD_CUDA(c, cudaMalloc(&c->d_cnt_part, sizeof(unsigned long long) * c->n_pe_part));
     MD_CUDA(c, cudaMemset(c->d_pe_part, 0, sizeof(double) * c->n_pe_part));
-    MD_CUDA(c, cudaMemset(c->d_cnt_part, 0, sizeof(unsigned long long) * c->n_pe_part));
-    if (c->pot.fast != POTF_LJ) {
-        md_set_error(c, "cutoff path: only the Lennard-Jones member of the Mie family is implemented on the list kernels");
-        return MDSEA_ERR_UNSUPPORTED;
+    if (W > 1) {
+        s->sendpool_cap = (long long)std::min(W, 3) * s->cap;
+        MD_CUDA(c, cudaMalloc(&s->sendpool, sizeof(PMsg) * (size_t)s->sendpool_cap));
+        MD_CUDA(c, cudaMalloc(&s->recvpool, sizeof(PMsg) * (size_t)s->cap));
+        MD_CUDA(c, cudaMalloc(&s->d_cnt_all, sizeof(int) * MD_MAXW * MD_MAXW));
+        MD_CUDA(c, cudaMalloc(&s->d_cursor, sizeof(int) * MD_MAXW));
+        MD_CUDA(c, cudaMalloc(&s->halo_flag, sizeof(int) * ((size_t)W * s->cap + 1)));
+        MD_CUDA(c, cudaMalloc(&s->halo_scan, sizeof(int) * ((size_t)W * s->cap + 1)));
+        MD_CUDA(c, cudaMalloc(&s->halo_idx, sizeof(int) * (size_t)W * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->scan_tmp, sizeof(int) * (md_div_up((long long)W * s->cap + 1, SCAN_THREADS * SCAN_ITEMS) + 1)));
+        MD_CUDA(c, cudaMalloc(&s->halo_send, sizeof(double) * 3 * (size_t)s->cap * std::min(W - 1, 3)));
+        MD_CUDA(c, cudaMalloc(&s->halo_recv, sizeof(double) * 3 * (size_t)s->cap));
+        MD_CUDA(c, cudaMalloc(&s->id_rows, sizeof(int) * (size_t)s->cap * c->ring));
+        s->row_n_own.assign(c->ring, 0);
     }
+    c->n = 0;
     return MDSEA_OK;
 }
 
 void md_cells_free(mdsea_ctx *c) {
     CellState *s = c->cells;
     if (!s) return;
+    md_comm_free(c);
     cudaFree(s->r_alt); cudaFree(s->v_alt); cudaFree(s->rb); cudaFree(s->id); cudaFree(s->id_alt); cudaFree(s->pos4);
-    cudaFree(s->key); cudaFree(s->key_alt); cudaFree(s->val); cudaFree(s->val_alt); cudaFree(s->hist); cudaFree(s->hist_tot); cudaFree(s->qfix);
-    cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->nbr); cudaFree(s->nbr_cnt); cudaFree(s->scratch);
+    cudaFree(s->key); cudaFree(s->key_alt); cudaFree(s->val); cudaFree(s->val_alt); cudaFree(s->hist); cudaFree(s->hist_tot);
+    cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
+    cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
+    cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->id_rows);
     if (s->h_flag) cudaFreeHost(s->h_flag);
+    if (s->h_cnt_all) cudaFreeHost(s->h_cnt_all);
     delete s;
     c->cells = nullptr;
 }
 
-static inline double fixed_inv_h(const mdsea_ctx *c) { return 4294967296.0 / c->box.L; }
-
 int md_cutoff_set_state(mdsea_ctx *c, const double *r, const double *v) {
     CellState *s = c->cells;
-    const long long n = c->n;
-    for (int d = 0; d < 3; ++d) {
-        MD_CUDA(c, cudaMemcpyAsync(c->d_r + d * s->cap, r + d * n, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-        MD_CUDA(c, cudaMemcpyAsync(c->d_v + d * s->cap, v + d * n, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    const long long N = c->n_global;
+    if (c->p.world == 1) {
+        for (int d = 0; d < 3; ++d) {
+            MD_CUDA(c, cudaMemcpyAsync(c->d_r + d * s->cap, r + d * N, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+            MD_CUDA(c, cudaMemcpyAsync(c->d_v + d * s->cap, v + d * N, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+        }
+        k_iota<<<g256(N), 256, 0, c->stream>>>(s->id, N);
+        c->stats.kernel_launches += 1;
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->n = N;
+    } else {
+        if (!c->comm) { md_set_error(c, "set_state: world > 1 needs comm_init first"); return MDSEA_ERR_STATE; }
+        double *rg = nullptr, *vg = nullptr;
+        MD_CUDA(c, cudaMalloc(&rg, sizeof(double) * 3 * N));
+        MD_CUDA(c, cudaMalloc(&vg, sizeof(double) * 3 * N));
+        MD_CUDA(c, cudaMemcpyAsync(rg, r, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
+        MD_CUDA(c, cudaMemcpyAsync(vg, v, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
+        MD_CUDA(c, cudaMemsetAsync(s->d_cnt, 0, sizeof(int), c->stream));
+        k_select_owned<<<g256(N), 256, 0, c->stream>>>(rg, vg, N, c->box.L, s->cell_len, s->nc, s->D, s->cap, c->d_r, c->d_v,
+                                                       s->id, s->d_cnt);
+        c->stats.kernel_launches += 1;
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(rg); cudaFree(vg);
+        if (s->h_flag[0] > s->cap) { md_set_error(c, "set_state: particle capacity of this rank exceeded"); return MDSEA_ERR_CAPACITY; }
+        c->n = s->h_flag[0];
     }
-    k_iota<<<md_div_up(n, 256), 256, 0, c->stream>>>(s->id, n);
-    c->stats.kernel_launches += 1;
-    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    s->n_tot = c->n;
     s->need_rebuild = true;
-    c->stats.n_local = n;
+    c->stats.n_local = c->n;
+    c->stats.n_ghost = 0;
+    return MDSEA_OK;
+}
+
+// multi-rank front end of a rebuild: route every held particle to the ranks that need it (as owner or as ghost),
+// exchange, and leave the union in the staging arrays (r_alt, v_alt, id_alt); returns the new n_tot.
+static int mr_assemble(mdsea_ctx *c) {
+    CellState *s = c->cells;
+    const int W = c->p.world, me = c->p.rank;
+    const long long n = c->n;
+    MD_CUDA(c, cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * MD_MAXW, c->stream));
+    k_mr_route<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, 0, s->d_cnt,
+                                               nullptr);
+    MD_TRY(md_comm_allgather_i32(c, s->d_cnt, MD_MAXW, s->d_cnt_all));
+    MD_CUDA(c, cudaMemcpyAsync(s->h_cnt_all, s->d_cnt_all, sizeof(int) * MD_MAXW * W, cudaMemcpyDeviceToHost, c->stream));
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    long long soff[MD_MAXW + 1], roff[MD_MAXW + 1];
+    int cursor[MD_MAXW];
+    soff[0] = roff[0] = 0;
+    for (int q = 0; q < W; ++q) {
+        soff[q + 1] = soff[q] + s->h_cnt_all[me * MD_MAXW + q];
+        roff[q + 1] = roff[q] + s->h_cnt_all[q * MD_MAXW + me];
+        cursor[q] = (int)soff[q];
+    }
+    if (soff[W] > s->sendpool_cap || roff[W] > s->cap) {
+        md_set_error(c, "rebuild: migration/ghost buffer capacity exceeded on this rank");
+        return MDSEA_ERR_CAPACITY;
+    }
+    MD_CUDA(c, cudaMemcpyAsync(s->d_cursor, cursor, sizeof(int) * W, cudaMemcpyHostToDevice, c->stream));
+    k_mr_route<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, 1,
+                                               s->d_cursor, s->sendpool);
+    void  *sp[MD_MAXW], *rp[MD_MAXW];
+    size_t sb[MD_MAXW], rbytes[MD_MAXW];
+    for (int q = 0; q < W; ++q) {
+        sp[q] = s->sendpool + soff[q];
+        rp[q] = s->recvpool + roff[q];
+        sb[q] = q == me ? 0 : sizeof(PMsg) * (size_t)(soff[q + 1] - soff[q]);
+        rbytes[q] = q == me ? 0 : sizeof(PMsg) * (size_t)(roff[q + 1] - roff[q]);
+    }
+    MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes));
+    // stage = [what I keep] + [what every peer sent], any order (the sort below canonicalises it)
+    for (int q = 0; q < W; ++q) {
+        const long long cnt = roff[q + 1] - roff[q];
+        if (!cnt) continue;
+        const PMsg *src = q == me ? s->sendpool + soff[me] : s->recvpool + roff[q];
+        k_mr_unpack<<<g256(cnt), 256, 0, c->stream>>>(src, cnt, roff[q], s->cap, s->r_alt, s->v_alt, s->id_alt);
+        c->stats.kernel_launches += 1;
+    }
+    c->stats.kernel_launches += 2;
+    MD_CUDA(c, cudaGetLastError());
+    s->n_tot = roff[W];
+    return MDSEA_OK;
+}
+
+static int build_halo_lists(mdsea_ctx *c) {
+    CellState *s = c->cells;
+    const int W = c->p.world;
+    const long long nt = s->n_tot, tot = nt * W;
+    k_halo_flags<<<g256(nt), 256, 0, c->stream>>>(s->cell, c->n, nt, s->nc, s->D, s->halo_flag);
+    MD_CUDA(c, cudaMemsetAsync(s->halo_flag + tot, 0, sizeof(int), c->stream));  // sentinel: scan[tot] = grand total
+    MD_TRY(scan_exclusive(c, s->halo_flag, s->halo_scan, tot + 1));
+    k_halo_lists<<<g256(tot), 256, 0, c->stream>>>(s->halo_flag, s->halo_scan, nt, W, s->halo_idx);
+    c->stats.kernel_launches += 2;
+    // list sizes from the scan at the segment starts (A) and at the owned/ghost split of each segment (B)
+    int *h = s->h_cnt_all;  // pinned scratch, >= 2 * MD_MAXW + 1 ints
+    for (int q = 0; q <= W; ++q)
+        MD_CUDA(c, cudaMemcpyAsync(&h[q], s->halo_scan + (size_t)q * nt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    for (int q = 0; q < W; ++q)
+        MD_CUDA(c, cudaMemcpyAsync(&h[MD_MAXW + 1 + q], s->halo_scan + (size_t)q * nt + c->n, sizeof(int), cudaMemcpyDeviceToHost,
+                                   c->stream));
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < W; ++q) {
+        s->halo_nsend[q] = h[MD_MAXW + 1 + q] - h[q];
+        s->halo_nrecv[q] = h[q + 1] - h[MD_MAXW + 1 + q];
+        s->halo_base[q] = (long long)q * nt;
+    }
+    return MDSEA_OK;
+}
+
+// per step: owned boundary positions -> the ranks that hold them as ghosts
+static int halo_exchange(mdsea_ctx *c) {
+    CellState *s = c->cells;
+    const int W = c->p.world, me = c->p.rank;
+    md_prof_begin(c);
+    void  *sp[MD_MAXW], *rp[MD_MAXW];
+    size_t sb[MD_MAXW], rbytes[MD_MAXW];
+    long long so = 0, ro = 0;
+    for (int q = 0; q < W; ++q) {
+        sp[q] = s->halo_send + 3 * so;
+        rp[q] = s->halo_recv + 3 * ro;
+        sb[q] = rbytes[q] = 0;
+        if (q == me) continue;
+        const long long ns = s->halo_nsend[q], nr = s->halo_nrecv[q];
+        if (ns) {
+            k_halo_pack<<<g256(ns), 256, 0, c->stream>>>(c->d_r, s->cap, s->halo_idx + s->halo_base[q], ns, s->halo_send + 3 * so);
+            c->stats.kernel_launches += 1;
+        }
+        sb[q] = sizeof(double) * 3 * (size_t)ns;
+        rbytes[q] = sizeof(double) * 3 * (size_t)nr;
+        so += ns;
+        ro += nr;
+    }
+    MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes));
+    ro = 0;
+    for (int q = 0; q < W; ++q) {
+        if (q == me) continue;
+        const long long nr = s->halo_nrecv[q];
+        if (nr) {
+            k_halo_unpack<<<g256(nr), 256, 0, c->stream>>>(s->halo_recv + 3 * ro, s->halo_idx + s->halo_base[q] + s->halo_nsend[q], nr,
+                                                           s->cap, c->d_r, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4);
+            c->stats.kernel_launches += 1;
+        }
+        ro += nr;
+    }
+    md_prof_end(c, &c->stats.ms_comm);
+    MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;
 }
 
 static int rebuild(mdsea_ctx *c) {
     CellState *s = c->cells;
-    const long long n = c->n;
+    const int W = c->p.world;
     md_prof_begin(c);
-    const int g256 = md_div_up(n, 256);
-    k_cell_keys<<<g256, 256, 0, c->stream>>>(c->d_r, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->key, s->val);
+    if (W > 1) MD_TRY(mr_assemble(c));
+    else s->n_tot = c->n;
+    const long long nt = s->n_tot;
+    const double *src_r = W > 1 ? s->r_alt : c->d_r, *src_v = W > 1 ? s->v_alt : c->d_v;
+    const int    *src_id = W > 1 ? s->id_alt : s->id;
+    double *dst_r = W > 1 ? c->d_r : s->r_alt, *dst_v = W > 1 ? c->d_v : s->v_alt;
+    int    *dst_id = W > 1 ? s->id : s->id_alt;
+    MD_CUDA(c, cudaMemsetAsync(s->d_cnt + MD_MAXW, 0, sizeof(int), c->stream));
+    k_cell_keys<<<g256(nt), 256, 0, c->stream>>>(src_r, src_id, nt, s->cap, c->box.L, s->cell_len, s->nc, s->D, s->key, s->val,
+                                                 s->d_cnt + MD_MAXW);
     int launches = 1;
-    // LSD passes over the id bits, then over the cell bits (= stable sort by cell id, then by particle id)
+    // LSD passes over the id bits, then the cell bits, then (multi-rank) the ghost bit:
+    // = stable sort by (ghost, cell id, particle id)
     std::vector<int> shifts;
     for (int b = 0; b < s->id_bits; b += 8) shifts.push_back(b);
     for (int b = 0; b < s->cell_bits; b += 8) shifts.push_back(32 + b);
-    const int nblk = md_div_up(n, SORT_CHUNK);
+    if (W > 1) shifts.push_back(56);
+    const int nblk = md_div_up(nt, SORT_CHUNK);
     for (int sh : shifts) {
-        k_sort_hist<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, n, sh, s->hist, nblk);
+        k_sort_hist<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, nt, sh, s->hist, nblk);
         k_sort_rowscan<<<256, 256, 0, c->stream>>>(s->hist, nblk, s->hist_tot);
-        k_sort_scatter<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, s->val, s->key_alt, s->val_alt, n, sh, s->hist, nblk,
+        k_sort_scatter<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, s->val, s->key_alt, s->val_alt, nt, sh, s->hist, nblk,
                                                              s->hist_tot);
         std::swap(s->key, s->key_alt);
         std::swap(s->val, s->val_alt);
         launches += 3;
     }
-    k_reorder<<<g256, 256, 0, c->stream>>>(s->key, s->val, n, s->cap, c->d_r, c->d_v, s->r_alt, s->v_alt, s->rb, s->id_alt,
-                                           s->cell);
-    std::swap(c->d_r, s->r_alt);
-    std::swap(c->d_v, s->v_alt);
-    std::swap(s->id, s->id_alt);
-    k_cell_bounds<<<g256, 256, 0, c->stream>>>(s->cell, n, s->ncell, s->cell_start);
-    k_pack_positions<<<g256, 256, 0, c->stream>>>(c->d_r, n, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, s->qfix);
+    k_reorder<<<g256(nt), 256, 0, c->stream>>>(s->key, s->val, nt, s->cap, src_r, src_v, dst_r, dst_v, s->rb, dst_id, s->cell);
+    if (W == 1) {
+        std::swap(c->d_r, s->r_alt);
+        std::swap(c->d_v, s->v_alt);
+        std::swap(s->id, s->id_alt);
+    } else {
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt + MD_MAXW, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->n = s->h_flag[0];
+        c->stats.n_local = c->n;
+        c->stats.n_ghost = nt - c->n;
+    }
+    MD_CUDA(c, cudaMemsetAsync(s->cell_start, 0, sizeof(int) * ((size_t)s->ncell + 1), c->stream));
+    MD_CUDA(c, cudaMemsetAsync(s->cell_end, 0, sizeof(int) * ((size_t)s->ncell + 1), c->stream));
+    k_cell_bounds<<<g256(nt), 256, 0, c->stream>>>(s->cell, nt, s->cell_start, s->cell_end);
+    k_pack_positions<<<g256(nt), 256, 0, c->stream>>>(c->d_r, nt, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4,
+                                                      s->qfix);
+    if (W > 1) MD_TRY(build_halo_lists(c));
     {
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
-        k_nbr_build<<<md_div_up(n, NB_THREADS), NB_THREADS, 0, c->stream>>>(
-            c->d_r, s->qfix, n, s->cap, s->cell, s->cell_start, s->nc, c->box.L, c->box.halfL, s->rl2,
+        k_nbr_build<<<md_div_up(c->n > 0 ? c->n : 1, NB_THREADS), NB_THREADS, 0, c->stream>>>(
+            c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2,
             (float)(rl2s * (1.0 - 1e-5)), (float)(rl2s * (1.0 + 1e-5)), s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
     }
     launches += 4;
@@ -678,7 +1107,8 @@ int md_cutoff_force(mdsea_ctx *c) {
     if (s->need_rebuild) MD_TRY(rebuild(c));
     const long long n = c->n;
     md_prof_begin(c);
-    const int grid = md_div_up(n, NB_THREADS);
+    const int grid = md_div_up(n > 0 ? n : 1, NB_THREADS);
+    c->n_pe_part = grid;
     if (c->p.precision == MDSEA_FP64) {
         LjF64 P;
         P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
@@ -705,33 +1135,43 @@ int md_cutoff_force(mdsea_ctx *c) {
 static int cut_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, bool do_drift) {
     CellState *s = c->cells;
     md_prof_begin(c);
-    k_cut_kick_drift<<<md_div_up(c->n, 256), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->rb, c->n, s->cap, do_bc, do_kick,
-                                                                  do_drift, c->box.L, c->box.halfL, c->p.dt, s->trig2,
-                                                                  c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc);
+    k_cut_kick_drift<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->rb, c->n, s->cap, do_bc, do_kick, do_drift,
+                                                        c->box.L, c->box.halfL, c->p.dt, s->trig2, c->p.precision == MDSEA_FP32,
+                                                        fixed_inv_h(c), s->pos4, c->d_sc);
     md_prof_end(c, &c->stats.ms_integrate);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
     return MDSEA_OK;
 }
 
-// after a drift: fetch the device-side trigger; rebuild before the next force evaluation if it fired
-static int check_trigger(mdsea_ctx *c) {
+// after a drift: fetch the (globally reduced) trigger; rebuild before the next force evaluation if it fired,
+// otherwise refresh the ghost positions
+static int after_drift(mdsea_ctx *c) {
     CellState *s = c->cells;
-    if (s->need_rebuild) return MDSEA_OK;  // no list yet: the trigger was computed against stale build positions
-    MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    MD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (s->h_flag[0]) {
-        s->need_rebuild = true;
-        MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
+    const int W = c->p.world;
+    if (!s->need_rebuild) {  // without a list the trigger would compare against stale build positions
+        if (W > 1) MD_TRY(md_comm_allreduce_max_i32(c, &c->d_sc->rebuild_flag, 1));
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (s->h_flag[0]) {
+            s->need_rebuild = true;
+            MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
+        }
     }
+    if (W > 1 && !s->need_rebuild) MD_TRY(halo_exchange(c));
     return MDSEA_OK;
 }
 
 int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
     CellState *s = c->cells;
+    const int  W = c->p.world;
     const bool verlet = c->p.algorithm == MDSEA_ALGO_VERLET;
     const bool reuse = verlet && c->p.force_evals_per_step == 1;
-    const size_t rowE = (size_t)3 * (size_t)c->n_global;
+    if (W > 1 && a->quench_targets) {
+        md_set_error(c, "run: quench / isothermal runs are not supported with world > 1 yet");
+        return MDSEA_ERR_UNSUPPORTED;
+    }
+    const size_t row_stride = W == 1 ? (size_t)c->n_global : (size_t)s->cap;
     for (int k = 0; k < a->nsteps; ++k) {
         if (verlet) {
             if (reuse && c->acc_valid) {
@@ -744,51 +1184,91 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
         } else {
             MD_TRY(cut_kick_drift(c, true, false, true));        // simulator.py:533
         }
-        MD_TRY(check_trigger(c));
+        MD_TRY(after_drift(c));
         MD_TRY(md_cutoff_force(c));                               // simulator.py:544
-        double *rr = a->record_coords ? c->d_r_rows + (size_t)k * rowE : nullptr;
-        double *vr = a->record_coords ? c->d_v_rows + (size_t)k * rowE : nullptr;
+        double *rr = a->record_coords ? c->d_r_rows + (size_t)k * 3 * row_stride : nullptr;
+        double *vr = a->record_coords ? c->d_v_rows + (size_t)k * 3 * row_stride : nullptr;
+        int *idr = (a->record_coords && W > 1) ? s->id_rows + (size_t)k * s->cap : nullptr;
+        if (W > 1) s->row_n_own[k] = c->n;
         md_prof_begin(c);
-        k_cut_kick_finish<<<md_div_up(c->n, 256), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap,
-                                                                       c->n_global, c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr);
+        c->n_ke_part = g256(c->n);
+        k_cut_kick_finish<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride,
+                                                            idr, c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr);
         md_prof_end(c, &c->stats.ms_integrate);
         MD_CUDA(c, cudaGetLastError());
         c->stats.kernel_launches += 1;
         c->acc_valid = true;
         MD_TRY(md_finalize_step(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k));
     }
+    if (W > 1) {  // global energies: one small allreduce per batch (the rows hold this rank's share of the means)
+        MD_TRY(md_comm_allreduce_sum_f64(c, c->d_pe_rows, a->nsteps));
+        MD_TRY(md_comm_allreduce_sum_f64(c, c->d_ke_rows, a->nsteps));
+    }
+    return MDSEA_OK;
+}
+
+// world > 1: compact rows (slot order) + ids -> caller's buffers [nsteps][3][cap] / [nsteps][cap]
+int md_cutoff_copy_rows(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows) {
+    CellState *s = c->cells;
+    if (!a->record_coords || !rows->r || !rows->v) return MDSEA_OK;
+    if (!rows->ids || !rows->n_owned || rows->row_stride < s->cap) {
+        md_set_error(c, "run: world > 1 needs rows.ids, rows.n_owned and rows.row_stride >= the rank capacity");
+        return MDSEA_ERR_BAD_ARG;
+    }
+    const size_t st = (size_t)rows->row_stride;
+    for (int k = 0; k < a->nsteps; ++k) {
+        const size_t n = (size_t)s->row_n_own[k];
+        rows->n_owned[k] = (int64_t)n;
+        for (int d = 0; d < 3; ++d) {
+            MD_CUDA(c, cudaMemcpyAsync(rows->r + ((size_t)k * 3 + d) * st, c->d_r_rows + ((size_t)k * 3 + d) * s->cap, sizeof(double) * n,
+                                       cudaMemcpyDeviceToHost, c->copy_stream));
+            MD_CUDA(c, cudaMemcpyAsync(rows->v + ((size_t)k * 3 + d) * st, c->d_v_rows + ((size_t)k * 3 + d) * s->cap, sizeof(double) * n,
+                                       cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        MD_CUDA(c, cudaMemcpyAsync(rows->ids + (size_t)k * st, s->id_rows + (size_t)k * s->cap, sizeof(int) * n, cudaMemcpyDeviceToHost,
+                                   c->copy_stream));
+    }
     return MDSEA_OK;
 }
 
 int md_cutoff_finish_rows(mdsea_ctx *c) { return MDSEA_OK; }
+long long md_cutoff_capacity(mdsea_ctx *c) { return c->cells ? c->cells->cap : 0; }
 
 int md_cutoff_get_state(mdsea_ctx *c, double *r, double *v, double *a, int64_t *ids, int64_t *n_owned) {
     CellState *s = c->cells;
     const long long n = c->n, N = c->n_global;
-    const int g = md_div_up(n, 256);
+    if (!s->scratch) MD_CUDA(c, cudaMalloc(&s->scratch, sizeof(double) * 3 * (size_t)N));
     const double *src[3] = {c->d_r, c->d_v, c->d_acc};
     double *dst[3] = {r, v, a};
+    std::vector<int> h(n > 0 ? n : 1);
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    MD_CUDA(c, cudaMemcpy(h.data(), s->id, sizeof(int) * n, cudaMemcpyDeviceToHost));
     for (int q = 0; q < 3; ++q) {
         if (!dst[q]) continue;
-        k_unsort<<<g, 256, 0, c->stream>>>(src[q], s->id, n, s->cap, N, s->scratch);
+        k_unsort<<<g256(n), 256, 0, c->stream>>>(src[q], s->id, n, s->cap, N, s->scratch);
         c->stats.kernel_launches += 1;
-        MD_CUDA(c, cudaMemcpyAsync(dst[q], s->scratch, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
-        MD_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
-    if (ids || n_owned) {
-        std::vector<int> h(n);
-        MD_CUDA(c, cudaMemcpy(h.data(), s->id, sizeof(int) * n, cudaMemcpyDeviceToHost));
-        if (ids) {
-            for (long long i = 0; i < n; ++i) ids[i] = h[i];
-            std::sort(ids, ids + n);
+        if (c->p.world == 1) {
+            MD_CUDA(c, cudaMemcpyAsync(dst[q], s->scratch, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
+            MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        } else {  // only the owned entries are defined: copy through a host bounce and scatter those
+            std::vector<double> tmp((size_t)3 * N);
+            MD_CUDA(c, cudaMemcpyAsync(tmp.data(), s->scratch, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
+            MD_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (long long k = 0; k < n; ++k)
+                for (int d = 0; d < 3; ++d) dst[q][(size_t)d * N + h[k]] = tmp[(size_t)d * N + h[k]];
         }
-        if (n_owned) *n_owned = n;
     }
+    if (ids) {
+        for (long long i = 0; i < n; ++i) ids[i] = h[i];
+        std::sort(ids, ids + n);
+    }
+    if (n_owned) *n_owned = n;
     return MDSEA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// test hooks (bit-exact contracts)
+// test hooks (bit-exact contracts).  With world > 1 each rank reports its OWNED particles: cell_of / offsets
+// entries of particles owned elsewhere are left at -1 / zero-length, `order` lists the owned ids in slot order.
 // ---------------------------------------------------------------------------------------------------
 extern "C" int mdsea_b200_get_cells(mdsea_ctx *c, int32_t *cell_of, int32_t *order, int32_t ncell_dim[3]) {
     if (!c || !cell_of || !order) return MDSEA_ERR_BAD_ARG;
@@ -797,10 +1277,11 @@ extern "C" int mdsea_b200_get_cells(mdsea_ctx *c, int32_t *cell_of, int32_t *ord
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
     const long long n = c->n;
-    std::vector<int> id(n), cell(n);
+    std::vector<int> id(n > 0 ? n : 1), cell(n > 0 ? n : 1);
     MD_CUDA(c, cudaStreamSynchronize(c->stream));
     MD_CUDA(c, cudaMemcpy(id.data(), s->id, sizeof(int) * n, cudaMemcpyDeviceToHost));
     MD_CUDA(c, cudaMemcpy(cell.data(), s->cell, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (long long g = 0; g < c->n_global; ++g) { cell_of[g] = -1; order[g] = -1; }
     for (long long k = 0; k < n; ++k) {
         order[k] = id[k];
         cell_of[id[k]] = cell[k];
@@ -815,19 +1296,19 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
     MD_CUDA(c, cudaSetDevice(c->p.device));
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
-    const long long n = c->n;
+    const long long n = c->n, nt = s->n_tot;
     MD_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::vector<int> id(n), cnt(n);
-    MD_CUDA(c, cudaMemcpy(id.data(), s->id, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    std::vector<int> id(nt > 0 ? nt : 1), cnt(n > 0 ? n : 1);
+    MD_CUDA(c, cudaMemcpy(id.data(), s->id, sizeof(int) * nt, cudaMemcpyDeviceToHost));
     MD_CUDA(c, cudaMemcpy(cnt.data(), s->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    // CSR over ORIGINAL ids
     std::vector<int64_t> count_by_id(c->n_global, 0);
     for (long long k = 0; k < n; ++k) count_by_id[id[k]] = cnt[k];
     offsets[0] = 0;
     for (long long g = 0; g < c->n_global; ++g) offsets[g + 1] = offsets[g] + count_by_id[g];
     *n_entries = offsets[c->n_global];
     if (!idx) return MDSEA_OK;
-    std::vector<int> nbr((size_t)s->max_nbr * (size_t)s->n_pad);
+    const size_t tiles = (size_t)((n + 31) / 32);
+    std::vector<int> nbr(tiles * (size_t)s->max_nbr * 32);
     MD_CUDA(c, cudaMemcpy(nbr.data(), s->nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost));
     for (long long k = 0; k < n; ++k) {
         int32_t *row = idx + offsets[id[k]];
@@ -835,10 +1316,4 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
         std::sort(row, row + cnt[k]);
     }
     return MDSEA_OK;
-}
-
-extern "C" int mdsea_b200_nccl_unique_id(void *) { return MDSEA_ERR_UNSUPPORTED; }
-extern "C" int mdsea_b200_comm_init(mdsea_ctx *c, const void *) {
-    md_set_error(c, "comm_init: multi-GPU domain decomposition is not built yet");
-    return MDSEA_ERR_UNSUPPORTED;
 }

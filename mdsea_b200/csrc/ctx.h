@@ -87,4 +87,5 @@ int md_pair_dists(mdsea_ctx *c, double *d_dists, double *d_units);
 int md_cells_setup(mdsea_ctx *c);
 void md_cells_free(mdsea_ctx *c);
 int md_cutoff_force(mdsea_ctx *c);            // rebuilds the list when flagged, then forces
-int md_cutoff_after_set_state(mdsea_ctx *c);
+int md_cutoff_copy_rows(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows);
+long long md_cutoff_capacity(mdsea_ctx *c);

@@ -1,0 +1,171 @@
+"""GPU: the spatial domain decomposition (K6) on ONE GPU through the in-process transport: `world` contexts, one
+host thread each, exchanging ghosts / migrants with device-to-device copies.  The NCCL transport shares every
+kernel and all of the routing logic; only the four primitives of csrc/comm.cu differ (exercised by bench.py under
+torchrun on real multi-GPU boxes).
+
+Contracts: the union of the ranks' owned particles is the full system at every step; per-rank neighbour lists are
+the canonical (global) lists of their owned particles, bit for bit; energies / trajectories equal the C oracle's
+(and hence the single-GPU path's) to the fp64 tolerances; all ranks rebuild on the same steps as the oracle.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle_c
+from test_gpu_cutoff import RC, SKIN, _liquid
+
+pytestmark = pytest.mark.gpu
+
+_KEY = [1000]
+
+
+def _run_ranks(world, grid, n, L, dt, r, v, steps, precision=0, evals=2, batch=None, want_lists=False):
+    from mdsea_b200 import _capi
+
+    _KEY[0] += 1
+    key = _KEY[0]
+    batch = batch or steps
+    out = [None] * world
+    errs = []
+
+    def worker(rank):
+        try:
+            ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1,
+                                precision=precision, epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=RC,
+                                skin=SKIN, force_evals_per_step=evals, ring_rows=batch, device=0, rank=rank, world=world,
+                                proc_grid=grid)
+            ctx.comm_init_local(key)
+            ctx.set_temperature(1.0)
+            ctx.set_state(r, v)
+            res = dict(pe=[], ke=[], rows=[])
+            for _ in range(steps // batch):
+                rows = ctx.run(batch, kb=1.0)
+                res["pe"].append(rows["pe"].copy()); res["ke"].append(rows["ke"].copy())
+                res["rows"].append({k: rows[k].copy() for k in ("r", "v", "ids", "n_owned")})
+            res["pe"] = np.concatenate(res["pe"]); res["ke"] = np.concatenate(res["ke"])
+            res["stats"] = ctx.stats()
+            if want_lists:
+                res["cells"] = ctx.get_cells()
+                res["nbrs"] = ctx.get_neighbors()
+            res["state"] = ctx.get_state()
+            out[rank] = res
+            ctx.close()
+        except Exception as e:  # pragma: no cover
+            errs.append((rank, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(world)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not errs, errs
+    assert all(o is not None for o in out)
+    return out
+
+
+def _assemble_rows(out, steps, n, batch):
+    """Scatter the ranks' compact rows by particle id -> (steps, 3, n); checks every particle is owned exactly once."""
+    r = np.full((steps, 3, n), np.nan)
+    v = np.full((steps, 3, n), np.nan)
+    owners = np.zeros((steps, n), dtype=int)
+    for o in out:
+        for b, rows in enumerate(o["rows"]):
+            for k in range(batch):
+                m = int(rows["n_owned"][k])
+                ids = rows["ids"][k, :m]
+                r[b * batch + k][:, ids] = rows["r"][k, :, :m]
+                v[b * batch + k][:, ids] = rows["v"][k, :, :m]
+                owners[b * batch + k, ids] += 1
+    assert np.all(owners == 1)
+    return r, v
+
+
+@pytest.mark.parametrize("world,grid", [(2, (2, 1, 1)), (2, (1, 1, 2)), (4, (2, 2, 1)), (8, (2, 2, 2))])
+def test_decomposed_run_matches_oracle(world, grid):
+    n, L, r, v, dt = _liquid(16)
+    steps, batch = 40, 20
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref = o.run(steps, record=True)
+    oc = o.counters()
+    out = _run_ranks(world, grid, n, L, dt, r, v, steps, precision=0, evals=2, batch=batch, want_lists=True)
+    for res in out:  # energies are global on every rank
+        np.testing.assert_allclose(res["pe"], ref["pe"], rtol=1e-10)
+        np.testing.assert_allclose(res["ke"], ref["ke"], rtol=1e-10)
+        assert res["stats"]["list_rebuilds"] == oc["rebuilds"]
+    rr, vv = _assemble_rows(out, steps, n, batch)
+    assert np.abs(rr - ref["r"]).max() <= 1e-9 * L
+    assert np.abs(vv - ref["v"]).max() <= 1e-9
+    assert sum(res["stats"]["pair_evals_unique"] for res in out) * 1.0 == pytest.approx(oc["pairs_unique"], rel=0, abs=world * steps)
+    assert sum(res["stats"]["n_local"] for res in out) == n
+    assert all(res["stats"]["n_ghost"] > 0 for res in out)
+    # the neighbour lists in force at the end: union over ranks == the oracle's list, entry for entry
+    ref_off, ref_idx = o.neighbor_list()
+    seen = np.zeros(n, dtype=int)
+    for res in out:
+        cell_of, order, nc = res["cells"]
+        off, idx = res["nbrs"]
+        owned = np.where(cell_of >= 0)[0]
+        seen[owned] += 1
+        for i in owned[:: max(1, len(owned) // 400)]:
+            np.testing.assert_array_equal(idx[off[i]:off[i + 1]], ref_idx[ref_off[i]:ref_off[i + 1]])
+        cnt = np.diff(off)
+        np.testing.assert_array_equal(cnt[owned], np.diff(ref_off)[owned])
+        assert cnt[np.setdiff1d(np.arange(n), owned)].sum() == 0
+    assert np.all(seen == 1)
+    # final state: each rank fills its owned entries
+    r_fin = np.full((3, n), np.nan)
+    for res in out:
+        rr_k, vv_k, aa_k, ids = res["state"]
+        r_fin[:, ids] = rr_k[:, ids]
+    assert np.abs(r_fin - ref["r"][-1]).max() <= 1e-9 * L
+    o.close()
+
+
+def test_decomposed_fp32_reuse_mode():
+    n, L, r, v, dt = _liquid(16)
+    steps = 40
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref = o.run(steps, record=True)
+    out = _run_ranks(4, (2, 1, 2), n, L, dt, r, v, steps, precision=1, evals=1, batch=steps)
+    for res in out:
+        np.testing.assert_allclose(res["pe"], ref["pe"], rtol=1e-5)
+        np.testing.assert_allclose(res["ke"], ref["ke"], rtol=1e-5)
+        assert res["stats"]["force_evals"] == steps + 1
+    rr, vv = _assemble_rows(out, steps, n, steps)
+    assert np.abs(rr[-1] - ref["r"][-1]).max() <= 1e-3
+    o.close()
+
+
+def test_uneven_blocks_and_lattice_start():
+    """nc not divisible by the process grid (blocks of different widths) and a perfect-lattice start."""
+    n, L, r, v, dt = _liquid(14, melt_steps=0)   # L = 16.86 -> nc = 6 with 2 ranks in x... and 3 along z: widths 2,2,2
+    steps = 30
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref = o.run(steps, record=True)
+    out = _run_ranks(6, (2, 1, 3), n, L, dt, r, v, steps, evals=2, batch=steps)
+    for res in out:
+        np.testing.assert_allclose(res["pe"], ref["pe"], rtol=1e-10)
+        np.testing.assert_allclose(res["ke"], ref["ke"], rtol=1e-10)
+    rr, vv = _assemble_rows(out, steps, n, steps)
+    assert np.abs(rr - ref["r"]).max() <= 1e-9 * L
+    n2, L2, r2, v2, dt2 = _liquid(15)            # L = 18.06 -> nc = 6; 4 ranks along x -> widths 1,2,1,2
+    o2 = oracle_c.CutoffSystem(r2, v2, L2, RC, SKIN, dt2)
+    ref2 = o2.run(20, record=True)
+    out2 = _run_ranks(4, (4, 1, 1), n2, L2, dt2, r2, v2, 20, evals=1, batch=20)
+    for res in out2:
+        np.testing.assert_allclose(res["pe"], ref2["pe"], rtol=1e-10)
+    o.close(); o2.close()
+
+
+def test_multirank_argument_errors():
+    from mdsea_b200 import _capi
+
+    kw = dict(ndim=3, num_particles=4096, boxlen=19.3, mass=1.0, radius=0.5, dt=0.005, pbc=1, algorithm=0, pot_kind=1, precision=0,
+              epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, force_evals_per_step=1, ring_rows=4, device=0)
+    with pytest.raises(_capi.MdseaError):   # all-pairs runs do not decompose
+        _capi.Context(r_cutoff=0.0, skin=0.0, rank=0, world=2, proc_grid=(2, 1, 1), **kw)
+    with pytest.raises(_capi.MdseaError):   # grid does not multiply to world
+        _capi.Context(r_cutoff=2.5, skin=0.3, rank=0, world=2, proc_grid=(2, 2, 1), **kw)
+    ctx = _capi.Context(r_cutoff=2.5, skin=0.3, rank=0, world=2, proc_grid=(2, 1, 1), **kw)
+    with pytest.raises(_capi.MdseaError):   # set_state before comm_init
+        ctx.set_state(np.zeros((3, 4096)), np.zeros((3, 4096)))
+    ctx.close()

@@ -160,7 +160,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib.mdsea_b200_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.mdsea_b200_version()
     # struct layout agreement between the header and the ctypes mirror
-    assert ctypes.sizeof(_capi.Params) == 200 and ctypes.sizeof(_capi.RunArgs) == 32 and ctypes.sizeof(_capi.Rows) == 40
+    assert ctypes.sizeof(_capi.Params) == 200 and ctypes.sizeof(_capi.RunArgs) == 32 and ctypes.sizeof(_capi.Rows) == 64
 
 
 def test_product_fails_loudly_without_gpu():
