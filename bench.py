@@ -34,9 +34,15 @@ WORKLOADS = {
     "c2": dict(name="3D LJ fluid N=4096 vf=0.3 all-pairs (BASELINE configs[1])", ndim=3, per_row=16, vf=0.3,
                r_cutoff=0.0, skin=0.0, md_steps=200, precision="fp64"),
     # configs[2]: 3-D LJ liquid, 1M particles, cell list + Verlet skin
+    # and, for N GPUs, configs[3] (weak scaling, ~1e6 particles per GPU on simple-cubic lattices: gen.py needs perfect cubes)
     "c3": dict(name="3D LJ liquid N=1e6 vf=0.3 rc=2.5 skin=0.3 cell+Verlet list (BASELINE configs[2])", ndim=3,
-               per_row=100, vf=0.3, r_cutoff=2.5, skin=0.3, md_steps=20, precision="fp32"),
+               per_row=100, vf=0.3, r_cutoff=2.5, skin=0.3, md_steps=20, precision="fp32",
+               per_row_by_world={1: 100, 2: 126, 4: 159, 8: 200},
+               name_multi="3D LJ liquid ~1e6 particles/GPU vf=0.3 rc=2.5 skin=0.3, spatial domain decomposition "
+                          "(BASELINE configs[3], weak scaling)"),
 }
+
+PROC_GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -176,16 +182,35 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     precision = args.precision or wl["precision"]
     md_steps = args.md_steps or wl["md_steps"]
-    n, L, r0, v0, dt = initial_state(wl["ndim"], wl["per_row"], wl["vf"], seed=rank)
     ndim = wl["ndim"]
-
-    ctx = make_ctx(wl, n, L, dt, local, precision, md_steps, evals=args.evals)
+    decomposed = world > 1 and wl["r_cutoff"] > 0
+    if decomposed:
+        # one system, spatially decomposed over the ranks (every rank generates the same gen.py state)
+        if world not in wl["per_row_by_world"]:
+            raise SystemExit(f"bench.py: no weak-scaling lattice defined for {world} GPUs (have {sorted(wl['per_row_by_world'])})")
+        n, L, r0, v0, dt = initial_state(ndim, wl["per_row_by_world"][world], wl["vf"], seed=0)
+        ctx = make_ctx(wl, n, L, dt, local, precision, md_steps, rank=rank, world=world, proc_grid=PROC_GRIDS[world],
+                       evals=args.evals)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        width = ctx.rank_capacity()
+    else:
+        # replicas: every rank runs its own independent system (all-pairs does not shard)
+        n, L, r0, v0, dt = initial_state(ndim, wl["per_row"], wl["vf"], seed=rank)
+        ctx = make_ctx(wl, n, L, dt, local, precision, md_steps, evals=args.evals)
+        width = n
     ctx.set_temperature(1.0)
-    pin = lambda shape: torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    pin = lambda shape, dt_=torch.float64: torch.empty(shape, dtype=dt_, pin_memory=True).numpy()
     r_pin, v_pin = pin((ndim, n)), pin((ndim, n))
     r_pin[:], v_pin[:] = r0, v0
-    rows = dict(r=pin((md_steps, ndim, n)), v=pin((md_steps, ndim, n)), pe=pin((md_steps,)), ke=pin((md_steps,)),
+    rows = dict(r=pin((md_steps, ndim, width)), v=pin((md_steps, ndim, width)), pe=pin((md_steps,)), ke=pin((md_steps,)),
                 temp=pin((md_steps,)))
+    if decomposed:
+        rows["ids"] = pin((md_steps, width), torch.int32)
+        rows["n_owned"] = pin((md_steps,), torch.int64)
     rows_dev = dict(r=None, v=None, pe=rows["pe"], ke=rows["ke"], temp=rows["temp"])
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -250,7 +275,8 @@ def run_ours(args, wl):
     e2e_pairs = ctx.stats()["pair_evals_unique"] - p0
     t_e2e = sum(e2e_times)
     h2d = 2 * ndim * n * 8
-    d2h = md_steps * (2 * ndim * n + 3) * 8
+    n_loc = ctx.stats()["n_local"] if decomposed else n
+    d2h = md_steps * ((2 * ndim * 8 + (4 if decomposed else 0)) * n_loc + 3 * 8)
 
     # ---------------- per-kernel roofline numbers (library's own CUDA-event timers) ----------------
     ctx.set_state(r_pin, v_pin)
@@ -274,8 +300,10 @@ def run_ours(args, wl):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     i_ms = (q1["ms_integrate"] - q0["ms_integrate"]) / max(md_steps, 1)
-    integ_bytes = (15 * 8 + 2 * 8) * ndim * n / ndim  # r,v,a read + r,v write + row r,v write, per particle-component group
-    integ_bytes = n * ndim * (5 * 8 + 2 * 8)          # per component: read r,v,a; write r,v; write row r,v
+    # per component and step: read r,v,a + write r,v (kick_drift) ; read v,a,r + write v (kick_finish) ; write row r,v
+    integ_bytes = n_loc * ndim * (5 * 8 + 4 * 8 + 2 * 8)
+    if wl["r_cutoff"] > 0:  # + build positions read (trigger) and the packed position copy written by the drift kernel
+        integ_bytes += n_loc * (ndim * 8 + (16 if precision == "fp32" else 32))
     roof_hbm = None
     if i_ms > 0:
         roof_hbm = {"bound": "hbm", "kernel": "fused integrator (kick_finish + kick_drift)", "achieved": integ_bytes / (i_ms * 1e-3) / 1e9,
@@ -309,13 +337,15 @@ def run_ours(args, wl):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if fp64 else "f32 pair math, f64 state", "data": "synthetic",
-            "timesteps_per_s": world * args.steps * md_steps / t_dev_max,
-            "config": {"workload": wl["name"], "particles_per_gpu": n, "md_steps_per_step": md_steps,
+            "timesteps_per_s": (1 if decomposed else world) * args.steps * md_steps / t_dev_max,
+            "config": {"workload": wl["name_multi"] if decomposed else wl["name"], "particles_total": n if decomposed else n * world,
+                       "particles_per_gpu": n // world if decomposed else n, "md_steps_per_step": md_steps,
                        "force_evals_per_md_step": fevals / (args.steps * md_steps), "precision": precision,
                        "k_boltzmann": 1.0, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": "replicas only (all-pairs does not shard)" if wl["r_cutoff"] <= 0 else f"dd{world}"},
+                       "parallelism": "replicas only (all-pairs does not shard)" if wl["r_cutoff"] <= 0 else
+                       f"dd{world} grid {PROC_GRIDS.get(world)}", "list_rebuilds_in_timed_region": int(s1["list_rebuilds"] - s0["list_rebuilds"])},
             "e2e": {"value": tot_e2e_pairs / t_e2e_max, "unit": "pair-interactions/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "timesteps_per_s": world * args.steps * md_steps / t_e2e_max,
+                    "d2h_bytes_per_step": d2h, "timesteps_per_s": (1 if decomposed else world) * args.steps * md_steps / t_e2e_max,
                     "ms_per_step": 1e3 * t_e2e_max / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64" if fp64 else "fp32", "kernel": "all-pairs force" if wl["r_cutoff"] <= 0 else "neighbour-list force",

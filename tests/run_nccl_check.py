@@ -1,0 +1,66 @@
+"""torchrun script (NOT collected by pytest): the NCCL transport of the domain decomposition on real GPUs.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_nccl_check.py
+
+Every rank steps its share of a 16^3 LJ liquid; rank 0 compares the global energies and the assembled trajectory
+with the C oracle (same contract as tests/test_gpu_multirank.py, which uses the in-process transport).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from mdsea_b200 import _capi  # noqa: E402
+from oracle import oracle_c  # noqa: E402
+from test_gpu_cutoff import RC, SKIN, _liquid  # noqa: E402
+
+GRIDS = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, L, r, v, dt = _liquid(16)
+    steps = 40
+    ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1, precision=0,
+                        epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=RC, skin=SKIN, force_evals_per_step=2,
+                        ring_rows=steps, device=local, rank=rank, world=world, proc_grid=GRIDS[world])
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0)
+    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    rows = ctx.run(steps, kb=1.0)
+    # gather the compact rows on rank 0 through torch.distributed (plumbing)
+    rr = np.zeros((steps, 3, n)); owners = np.zeros((steps, n))
+    for k in range(steps):
+        m = int(rows["n_owned"][k]); ids = rows["ids"][k, :m]
+        rr[k][:, ids] = rows["r"][k, :, :m]; owners[k, ids] = 1
+    t = torch.from_numpy(rr).cuda(); o = torch.from_numpy(owners).cuda()
+    dist.all_reduce(t); dist.all_reduce(o)
+    st = ctx.stats()
+    if rank == 0:
+        s = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+        ref = s.run(steps, record=True)
+        np.testing.assert_allclose(rows["pe"], ref["pe"], rtol=1e-10)
+        np.testing.assert_allclose(rows["ke"], ref["ke"], rtol=1e-10)
+        assert bool((o == 1).all()), "every particle must be owned by exactly one rank"
+        assert np.abs(t.cpu().numpy() - ref["r"]).max() <= 1e-9 * L
+        assert st["list_rebuilds"] == s.counters()["rebuilds"]
+        print(f"NCCL domain decomposition check OK: world={world} rebuilds={st['list_rebuilds']} n_local={st['n_local']} "
+              f"n_ghost={st['n_ghost']}")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
