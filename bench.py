@@ -320,13 +320,16 @@ def run_ours(args, wl):
         t_dev_max, t_e2e_max = tt.tolist()
         tot_pairs, tot_e2e_pairs = pp.tolist()
 
+    extra = None
+    if world == 1 and not args.no_extra and args.workload != "c2":
+        extra = allpairs_extra(local)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             if wl["r_cutoff"] > 0:
                 from oracle import oracle_c
 
-                res = oracle_c.bench_cutoff(wl, steps=2, warmup=0)
+                res = oracle_c.bench_cutoff(wl, steps=40, warmup=2)
             else:
                 res = cpu_allpairs_numpy(wl, 2, 0)
             cpu = {"value": res["pairs"] / res["seconds"], "unit": "pair-interactions/s", "cores": res["cores"],
@@ -357,6 +360,7 @@ def run_ours(args, wl):
                                         "(MEASURED_PEAKS.json has no CUDA-core FP peak)"},
             "roofline_hbm": roof_hbm,
             "cpu_baseline": cpu, "clocks": clocks, "energies_finite": energy_ok,
+            "allpairs_configs1": extra,
             "host_wall_s_timed_region": t_wall,
         }
         print(json.dumps(line), flush=True)
@@ -365,17 +369,62 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def allpairs_extra(local):
+    """configs[1] (N=4096 all-pairs, fp64 and fp32) measured beside the default workload at N=1."""
+    import torch
+
+    from mdsea_b200 import _capi
+
+    wl = WORKLOADS["c2"]
+    n, L, r0, v0, dt = initial_state(wl["ndim"], wl["per_row"], wl["vf"])
+    out = {"workload": wl["name"]}
+    for precision in ("fp64", "fp32"):
+        md = wl["md_steps"]
+        ctx = make_ctx(wl, n, L, dt, local, precision, md)
+        ctx.set_temperature(1.0)
+        ctx.set_state(r0, v0)
+        rows = dict(r=None, v=None, pe=np.empty(md), ke=np.empty(md), temp=np.empty(md))
+        stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+        for _ in range(3):
+            ctx.run(md, kb=1.0, record=True, rows=rows)
+        torch.cuda.synchronize()
+        s0 = ctx.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            ctx.run(md, kb=1.0, record=True, rows=rows)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3
+        s1 = ctx.stats()
+        ctx.set_profiling(True)
+        q0 = ctx.stats()
+        ctx.run(md, kb=1.0, record=True, rows=rows)
+        q1 = ctx.stats()
+        ctx.set_profiling(False)
+        fe = q1["force_evals"] - q0["force_evals"]
+        f_ms = (q1["ms_force"] - q0["ms_force"]) / max(fe, 1)
+        peak = _capi.measure_fma_peak(local, fp64=precision == "fp64")
+        ach = FLOP_PER_UNIQUE_PAIR[3] * (n * (n - 1) / 2) / (f_ms * 1e-3) / 1e12
+        out[precision] = {"pair_interactions_per_s": (s1["pair_evals_unique"] - s0["pair_evals_unique"]) / t,
+                          "timesteps_per_s": 5 * md / t, "force_ms_per_launch": f_ms,
+                          "roofline": {"bound": precision, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}}
+        ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=None, choices=["fp64", "fp32"])
     ap.add_argument("--md-steps", type=int, default=None, help="MD timesteps per bench step (one C-ABI run call)")
     ap.add_argument("--evals", type=int, default=1, choices=[1, 2], help="force evaluations per MD step (2 = reference-faithful)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional all-pairs (configs[1]) measurement at N=1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -28,7 +28,7 @@ from typing import Optional
 
 import numpy as np
 
-from mdsea_b200 import _capi, quicker
+from mdsea_b200 import _capi, parallel, quicker
 from mdsea_b200.config import Config
 from mdsea_b200.constants import DTYPE
 from mdsea_b200.core import SysManager
@@ -125,7 +125,15 @@ class _BaseSimulator:
         if fe == 1 and not sm.PBC:
             raise ValueError("force_evals_per_step=1 needs periodic boundaries (hard walls move particles between evaluations)")
         sigma = pp["sigma"]
+        # multi-GPU: one process per GPU (torchrun); only the cut-off path decomposes, all-pairs runs stay replicas
+        rank, world = parallel.dist_info()
+        self._rank, self._world = (rank, world) if (world > 1 and self.r_cutoff) else (0, 1)
+        grid = (1, 1, 1)
+        if self._world > 1:
+            rlist = float(self.r_cutoff) + (float(self.skin) if self.skin is not None else 0.3 * sigma)
+            grid = parallel.choose_proc_grid(self._world, int(sm.LEN_BOX // rlist))
         self._ctx = _capi.Context(
+            rank=self._rank, world=self._world, proc_grid=grid,
             ndim=nd, num_particles=n, boxlen=float(sm.LEN_BOX), mass=float(sm.MASS), radius=float(sm.RADIUS_PARTICLE),
             dt=float(self.dt), pbc=1 if sm.PBC else 0, algorithm=self._algorithm_code(),
             restitution=float(self.restitution_coeff), pot_kind=pp["kind"], precision=_PRECISIONS[self.precision],
@@ -134,9 +142,18 @@ class _BaseSimulator:
             skin=float(self.skin) if self.skin is not None else 0.3 * sigma,
             force_evals_per_step=int(fe), ring_rows=k, device=int(self.device), max_neighbors=int(self.max_neighbors),
         )
+        if self._world > 1:
+            self._ctx.comm_init(parallel.broadcast_unique_id(_capi.Context.nccl_unique_id))
+            parallel.barrier()
+            if self._rank != 0 and sm.dfile is None:  # rank 0 created the simfile tree; the others only open it
+                sm._open_datafile()
         self._ctx.set_temperature(self.temp, reset_ke=self.mean_ke is None)
-        self._rows = dict(r=_pinned_empty((k, nd, n)), v=_pinned_empty((k, nd, n)),
+        width = n if self._world == 1 else self._ctx.rank_capacity()
+        self._rows = dict(r=_pinned_empty((k, nd, width)), v=_pinned_empty((k, nd, width)),
                           pe=_pinned_empty((k,)), ke=_pinned_empty((k,)), temp=_pinned_empty((k,)))
+        if self._world > 1:
+            self._rows["ids"] = np.full((k, width), -1, dtype=np.int32)
+            self._rows["n_owned"] = np.zeros(k, dtype=np.int64)
         return self._ctx
 
     def _sync_to_device(self):
@@ -150,6 +167,8 @@ class _BaseSimulator:
     def _sync_to_host(self):
         if self._device_fresh and self._ctx is not None:
             self._r, self._v, self._acc, _ = self._ctx.get_state()
+            if self._world > 1:  # every rank holds its owned entries only
+                self._r, self._v, self._acc = (parallel.assemble_owned(a) for a in (self._r, self._v, self._acc))
             self._device_fresh = False
 
     # -- state attributes (host views of the device state) -----------------------------------------
@@ -313,11 +332,16 @@ class ContinuousPotentialSolver(_BaseSimulator):
             for i in range(s, s + n):
                 self.pbarr.log_progress(i)
             rows = self._run_batch(s, n, record=True)
-            sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], s)
-            sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], s)
-            sm.update_ds_block(sm.potenergy_dsname, rows["pe"][:n], s)
-            sm.update_ds_block(sm.kinenergy_dsname, rows["ke"][:n], s)
-            sm.update_ds_block(sm.temp_dsname, rows["temp"][:n], s)
+            if self._world > 1:
+                if not sm.dfile.id.valid:
+                    sm._open_datafile()
+                parallel.scatter_rows(sm, rows, n, s, self._rank)
+            else:
+                sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], s)
+                sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], s)
+                sm.update_ds_block(sm.potenergy_dsname, rows["pe"][:n], s)
+                sm.update_ds_block(sm.kinenergy_dsname, rows["ke"][:n], s)
+                sm.update_ds_block(sm.temp_dsname, rows["temp"][:n], s)
             s += n
             self.step = s - 1
         bad = self._ctx.first_nonfinite_step()
