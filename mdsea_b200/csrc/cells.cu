@@ -24,6 +24,7 @@
 #define SORT_ITEMS 8
 #define SORT_CHUNK (SORT_THREADS * SORT_ITEMS)
 #define NB_THREADS 128
+#define NBG 8  // list entries per gather group; rows are padded to a multiple of it
 
 // Spatial domain decomposition on the canonical cell grid: rank (bx, by, bz) of a px*py*pz process grid owns the
 // cells with bnd[d][b_d] <= c_d < bnd[d][b_d + 1]; its halo is the one-cell layer around that block (periodic).
@@ -381,8 +382,12 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
             nb_scan_range(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt);
         }
     }
-    nbr_cnt[i] = cnt < max_nbr ? cnt : max_nbr;
-    if (cnt > max_nbr) sc->overflow_flag = 1;
+    if (cnt > max_nbr) {
+        sc->overflow_flag = 1;
+        cnt = max_nbr;
+    }
+    nbr_cnt[i] = cnt;
+    for (int k = cnt; k < ((cnt + NBG - 1) / NBG) * NBG; ++k) row0[k * 32] = (int)i;  // padding, masked by j != i
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -453,22 +458,27 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, l
         const int   nn = nbr_cnt[i];
         const int *__restrict__ row0 = nbr + md_nbr_index(i, 0, max_nbr);
         const float cut_lo = rc2s * (1.0f - 2e-6f), cut_hi = rc2s * (1.0f + 2e-6f);
-        for (int k0 = 0; k0 < nn; k0 += 32) {
+        // Groups of NBG entries: all index loads, then all position gathers, then the arithmetic -- NBG independent
+        // gathers in flight per thread (the kernel is bound by the latency of these L1/L2 gathers, not by issue).
+        // Rows are padded by the build kernel to a multiple of NBG with the particle's own slot (masked by j != i).
+        for (int k0 = 0; k0 < nn; k0 += NBG) {
+            int   j[NBG];
+            uint4 qj[NBG];
+#pragma unroll
+            for (int u = 0; u < NBG; ++u) j[u] = row0[(k0 + u) * 32];
+#pragma unroll
+            for (int u = 0; u < NBG; ++u) qj[u] = pos[j[u]];
             float    fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
             unsigned flagged = 0u;
-            const int kn = min(32, nn - k0);
-#pragma unroll 8
-            for (int b = 0; b < kn; ++b) {
-                const int   j = row0[(k0 + b) * 32];
-                const uint4 qj = pos[j];
-                const int   ix = (int)(qj.x - qi.x), iy = (int)(qj.y - qi.y), iz = (int)(qj.z - qi.z);
-                const float dx = (float)ix, dy = (float)iy, dz = (float)iz;
+#pragma unroll
+            for (int u = 0; u < NBG; ++u) {
+                const float dx = (float)(int)(qj[u].x - qi.x), dy = (float)(int)(qj[u].y - qi.y), dz = (float)(int)(qj[u].z - qi.z);
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                 // an in-cutoff pair can only sit at the image tie if rc ~ L/2; rc + skin <= L/3 here, so only the
                 // cutoff band needs the exact redo
-                const bool slow = r2 > cut_lo && r2 < cut_hi;
-                flagged |= (slow ? 1u : 0u) << b;
-                const bool  ok = !slow && r2 < rc2s;
+                const bool inside = r2 < cut_lo, maybe = r2 < cut_hi;
+                flagged |= ((maybe && !inside) ? 1u : 0u) << u;
+                const bool  ok = inside && (j[u] != (int)i);
                 const float inv = ok ? md_rcpf(r2) : 0.0f;
                 const float t2 = P.sigma2 * inv;
                 const float t6 = t2 * t2 * t2;
@@ -480,12 +490,13 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, l
                 cnt += ok ? 1u : 0u;
             }
             while (flagged) {  // rare: decide and evaluate from the float64 positions
-                const int b = __ffs(flagged) - 1;
+                const int u = __ffs(flagged) - 1;
                 flagged &= flagged - 1;
-                const int    j = row0[(k0 + b) * 32];
-                const double ex = md_minimg_list(r64[j] - r64[i], L, halfL);
-                const double ey = md_minimg_list(r64[cap + j] - r64[cap + i], L, halfL);
-                const double ez = md_minimg_list(r64[2 * cap + j] - r64[2 * cap + i], L, halfL);
+                const int jj = row0[(k0 + u) * 32];
+                if (jj == (int)i) continue;
+                const double ex = md_minimg_list(r64[jj] - r64[i], L, halfL);
+                const double ey = md_minimg_list(r64[cap + jj] - r64[cap + i], L, halfL);
+                const double ez = md_minimg_list(r64[2 * cap + jj] - r64[2 * cap + i], L, halfL);
                 const double r2d = fma(ez, ez, fma(ey, ey, ex * ex));
                 if (r2d < rc2) {
                     const float dx = (float)(ex * inv_h), dy = (float)(ey * inv_h), dz = (float)(ez * inv_h);
@@ -812,6 +823,7 @@ int md_cells_setup(mdsea_ctx *c) {
         const double expect = 4.0 / 3.0 * 3.14159265358979 * s->rlist * s->rlist * s->rlist * rho;
         s->max_nbr = ((int)(expect * 1.6) + 32 + 7) / 8 * 8;
     }
+    s->max_nbr = (s->max_nbr + NBG - 1) / NBG * NBG;
     s->id_bits = bits_for((unsigned long long)(N - 1));
     s->cell_bits = bits_for((unsigned long long)(s->ncell - 1));
     s->sort_blocks = md_div_up(s->cap, SORT_CHUNK);
