@@ -97,6 +97,7 @@ struct CellState {
     int    *nbr = nullptr, *nbr_cnt = nullptr;
     double *scratch = nullptr;            // [3][N] for id-ordered downloads
     int    *h_flag = nullptr;             // pinned
+    cudaEvent_t ev_flag = nullptr;
     int     id_bits = 0, cell_bits = 0;
 };
 
@@ -319,43 +320,53 @@ __device__ __forceinline__ size_t md_nbr_index(long long i, int k, int max_nbr) 
 // K3: Verlet neighbour list.  One thread per particle; the 27-cell stencil of consecutive (cell-sorted)
 // particles overlaps almost completely, so the candidate loads are L1 broadcasts.
 // ---------------------------------------------------------------------------------------------------
+// One slot range of candidates against particle i.  EXACT = false is the hot path: 32-bit fixed-point separations
+// (exact integer differences, minimum image by wrap-around), r^2 in float, branch-free; a candidate whose float
+// r^2 lies within 1e-5 (relative) of the list radius -- far more than the ~5e-7 the float evaluation can be off --
+// only raises `band`.  EXACT = true evaluates the canonical float64 test for every candidate; the kernel re-runs
+// the (rare, ~0.2 % of the particles) banded particles that way, so the list is the canonical one bit for bit.
+template <bool EXACT>
 __device__ __forceinline__ void nb_scan_range(int j0, int j1, const uint4 qi, long long i, const double *__restrict__ r,
                                               const uint4 *__restrict__ q, long long cap, double L, double halfL, double rl2,
-                                              float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ row0, int &cnt) {
-#pragma unroll 2
-    for (int j = j0; j < j1; ++j) {
-        // prefilter in 32-bit fixed point: exact integer separations (minimum image by wrap-around), r^2 in
-        // float; only candidates within 1e-5 (relative) of the list radius -- far more than the ~5e-7 the float
-        // evaluation can be off -- go through the canonical float64 test
-        const uint4 qj = q[j];
-        const float fx = (float)(int)(qj.x - qi.x), fy = (float)(int)(qj.y - qi.y), fz = (float)(int)(qj.z - qi.z);
-        const float r2f = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
-        bool in = r2f < rl2s_lo;
-        if (__builtin_expect(!in && r2f < rl2s_hi, 0)) {
-            const double ddx = md_minimg_exact(__dsub_rn(r[j], r[i]), L, halfL);
-            const double ddy = md_minimg_exact(__dsub_rn(r[cap + j], r[cap + i]), L, halfL);
-            const double ddz = md_minimg_exact(__dsub_rn(r[2 * cap + j], r[2 * cap + i]), L, halfL);
-            in = md_r2_canonical(ddx, ddy, ddz) < rl2;
+                                              float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ row0, int &cnt,
+                                              bool &band) {
+    if (EXACT) {
+        const double xi = r[i], yi = r[cap + i], zi = r[2 * cap + i];
+        for (int j = j0; j < j1; ++j) {
+            const double ddx = md_minimg_exact(__dsub_rn(r[j], xi), L, halfL);
+            const double ddy = md_minimg_exact(__dsub_rn(r[cap + j], yi), L, halfL);
+            const double ddz = md_minimg_exact(__dsub_rn(r[2 * cap + j], zi), L, halfL);
+            if (md_r2_canonical(ddx, ddy, ddz) < rl2 && j != (int)i) {
+                if (cnt < max_nbr) row0[cnt * 32] = j;
+                ++cnt;
+            }
         }
-        if (in && j != (int)i) {
-            if (cnt < max_nbr) row0[cnt * 32] = j;
-            ++cnt;
+    } else {
+        // write cursor as a clamped 32-bit element offset: one predicated store per candidate, no bounds branch
+        // (an over-full row keeps overwriting its last slot; cnt still counts, the caller reports the overflow)
+        const unsigned off_max = (unsigned)(max_nbr - 1) * 32u;
+#pragma unroll 4
+        for (int j = j0; j < j1; ++j) {
+            const uint4 qj = q[j];
+            const float fx = (float)(int)(qj.x - qi.x), fy = (float)(int)(qj.y - qi.y), fz = (float)(int)(qj.z - qi.z);
+            const float r2f = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+            const bool in = r2f < rl2s_lo;
+            band = band || (!in && r2f < rl2s_hi);
+            const bool st = in && (j != (int)i);
+            const unsigned off = min((unsigned)cnt * 32u, off_max);
+            if (st) row0[off] = j;
+            cnt += st ? 1 : 0;
         }
     }
 }
 
-__global__ void __launch_bounds__(NB_THREADS)
-k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
-            const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
-            double L, double halfL, double rl2, float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ nbr,
-            int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_own) return;
-    const uint4 qi = q[i];
-    const int c = cell[i];
+template <bool EXACT>
+__device__ __forceinline__ int nb_particle(long long i, const uint4 qi, int c, const double *__restrict__ r,
+                                           const uint4 *__restrict__ q, long long cap, const int *__restrict__ cell_start,
+                                           const int *__restrict__ cell_end, int nc, double L, double halfL, double rl2,
+                                           float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ row0, bool &band) {
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
     const int xm = (cx + nc - 1) % nc, xp = (cx + 1) % nc;
-    int *row0 = nbr + md_nbr_index(i, 0, max_nbr);
     int cnt = 0;
     for (int dz = -1; dz <= 1; ++dz) {
         const int z = (cz + dz + nc) % nc;
@@ -374,14 +385,31 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
                 } else if (e1 != s1) {
                     if (ce == s1) ce = e1; // contiguous: extend
                     else {
-                        nb_scan_range(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt);
+                        nb_scan_range<EXACT>(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt, band);
                         cs = s1; ce = e1;
                     }
                 }
             }
-            nb_scan_range(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt);
+            nb_scan_range<EXACT>(cs, ce, qi, i, r, q, cap, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, cnt, band);
         }
     }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(NB_THREADS)
+k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
+            const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
+            double L, double halfL, double rl2, float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ nbr,
+            int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const uint4 qi = q[i];
+    const int c = cell[i];
+    int *row0 = nbr + md_nbr_index(i, 0, max_nbr);
+    bool band = false;
+    int cnt = nb_particle<false>(i, qi, c, r, q, cap, cell_start, cell_end, nc, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, band);
+    if (__builtin_expect(band, 0))
+        cnt = nb_particle<true>(i, qi, c, r, q, cap, cell_start, cell_end, nc, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, band);
     if (cnt > max_nbr) {
         sc->overflow_flag = 1;
         cnt = max_nbr;
@@ -402,9 +430,10 @@ struct LjF32 { float c6, sigma2; };    // in fixed-point units (see allpairs.cu)
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f64(const double4 *__restrict__ pos, long long n_own, long long cap, const int *__restrict__ nbr,
                 const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, LjF64 P,
-                double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc) {
+                double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
+    if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0;
     unsigned cnt = 0;
@@ -447,9 +476,10 @@ __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long n_own, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
                 double rc2, float rc2s, double inv_h, LjF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
-                StepScalars *__restrict__ sc) {
+                StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
+    if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   Fx = 0.0, Fy = 0.0, Fz = 0.0, PE = 0.0;
     unsigned cnt = 0;
@@ -562,8 +592,9 @@ __global__ void __launch_bounds__(256)
 k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
                   const int *__restrict__ id, long long n, long long cap, long long row_stride, int *__restrict__ id_row,
                   double dt, double g_dt, const StepScalars *__restrict__ sc, double *__restrict__ ke_part,
-                  double *__restrict__ r_row, double *__restrict__ v_row) {
+                  double *__restrict__ r_row, double *__restrict__ v_row, int guarded) {
     __shared__ double red[32];
+    if (guarded && sc->rebuild_flag) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double v2 = 0.0;
     if (i < n) {
@@ -852,6 +883,7 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->nbr_cnt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->d_cnt, sizeof(int) * (MD_MAXW + 8)));
     MD_CUDA(c, cudaMallocHost(&s->h_flag, sizeof(int) * 2));
+    MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_flag, cudaEventDisableTiming));
     MD_CUDA(c, cudaMallocHost(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8)));
     const size_t row_stride = W == 1 ? (size_t)N : (size_t)s->cap;
     MD_CUDA(c, cudaMalloc(&c->d_r_rows, sizeof(double) * 3 * row_stride * c->ring));
@@ -892,6 +924,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
     cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->id_rows);
     if (s->h_flag) cudaFreeHost(s->h_flag);
+    if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->h_cnt_all) cudaFreeHost(s->h_cnt_all);
     delete s;
     c->cells = nullptr;
@@ -1114,7 +1147,7 @@ static int rebuild(mdsea_ctx *c) {
     return MDSEA_OK;
 }
 
-int md_cutoff_force(mdsea_ctx *c) {
+static int cutoff_force(mdsea_ctx *c, int guarded) {
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
     const long long n = c->n;
@@ -1126,7 +1159,7 @@ int md_cutoff_force(mdsea_ctx *c) {
         P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
         P.sigma2 = c->pot.sigma2;
         k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, n, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
-                                                            c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part, c->d_sc);
+                                                            c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part, c->d_sc, guarded);
     } else {
         const double inv_h = fixed_inv_h(c);
         LjF32 P;
@@ -1135,7 +1168,7 @@ int md_cutoff_force(mdsea_ctx *c) {
         k_nbr_force_f32<<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, n, s->cap, s->nbr, s->nbr_cnt,
                                                             s->max_nbr, c->box.L, c->box.halfL, s->rc2,
                                                             (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc, c->d_pe_part,
-                                                            c->d_sc);
+                                                            c->d_sc, guarded);
     }
     md_prof_end(c, &c->stats.ms_force);
     MD_CUDA(c, cudaGetLastError());
@@ -1143,6 +1176,8 @@ int md_cutoff_force(mdsea_ctx *c) {
     c->stats.force_evals += 1;
     return MDSEA_OK;
 }
+
+int md_cutoff_force(mdsea_ctx *c) { return cutoff_force(c, 0); }
 
 static int cut_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, bool do_drift) {
     CellState *s = c->cells;
@@ -1156,26 +1191,54 @@ static int cut_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, bool do_drift)
     return MDSEA_OK;
 }
 
-// after a drift: fetch the (globally reduced) trigger; rebuild before the next force evaluation if it fired,
-// otherwise refresh the ghost positions
-static int after_drift(mdsea_ctx *c) {
+static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt, int guarded) {
     CellState *s = c->cells;
     const int W = c->p.world;
-    if (!s->need_rebuild) {  // without a list the trigger would compare against stale build positions
-        if (W > 1) MD_TRY(md_comm_allreduce_max_i32(c, &c->d_sc->rebuild_flag, 1));
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        MD_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (s->h_flag[0]) {
-            s->need_rebuild = true;
-            MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
-        }
+    const size_t row_stride = W == 1 ? (size_t)c->n_global : (size_t)s->cap;
+    double *rr = a->record_coords ? c->d_r_rows + (size_t)k * 3 * row_stride : nullptr;
+    double *vr = a->record_coords ? c->d_v_rows + (size_t)k * 3 * row_stride : nullptr;
+    int *idr = (a->record_coords && W > 1) ? s->id_rows + (size_t)k * s->cap : nullptr;
+    if (W > 1) s->row_n_own[k] = c->n;
+    md_prof_begin(c);
+    c->n_ke_part = g256(c->n);
+    k_cut_kick_finish<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride, idr,
+                                                        c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded);
+    md_prof_end(c, &c->stats.ms_integrate);
+    MD_CUDA(c, cudaGetLastError());
+    c->stats.kernel_launches += 1;
+    return md_finalize_step(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k, guarded);
+}
+
+// After a drift the skin trigger sits in a device flag.  To keep the GPU busy while the host learns its value,
+// the force / kick_finish / finalize kernels of the step are launched SPECULATIVELY, guarded by that flag (they
+// return at once when it is set); the host then reads the flag and, only if it fired (every ~6 steps at 1e6
+// particles), rebuilds and launches the three kernels again.  Multi-rank: the flag is first allreduced (MAX) so
+// that all ranks rebuild together, and the ghost refresh is issued unconditionally (harmless before a rebuild).
+static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt) {
+    CellState *s = c->cells;
+    const int W = c->p.world;
+    if (s->need_rebuild) {  // no list yet (first evaluation / new state): nothing to speculate on
+        MD_TRY(cutoff_force(c, 0));
+        return cut_finish_and_finalize(c, a, k, g_dt, 0);
     }
-    if (W > 1 && !s->need_rebuild) MD_TRY(halo_exchange(c));
+    if (W > 1) MD_TRY(md_comm_allreduce_max_i32(c, &c->d_sc->rebuild_flag, 1));
+    MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
+    if (W > 1) MD_TRY(halo_exchange(c));
+    const long long fe0 = c->stats.force_evals;
+    MD_TRY(cutoff_force(c, 1));
+    MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 1));
+    MD_CUDA(c, cudaEventSynchronize(s->ev_flag));
+    if (s->h_flag[0]) {  // the speculative kernels did nothing; rebuild (clears the flag) and do the step for real
+        c->stats.force_evals = fe0;
+        s->need_rebuild = true;
+        MD_TRY(cutoff_force(c, 0));
+        MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 0));
+    }
     return MDSEA_OK;
 }
 
 int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
-    CellState *s = c->cells;
     const int  W = c->p.world;
     const bool verlet = c->p.algorithm == MDSEA_ALGO_VERLET;
     const bool reuse = verlet && c->p.force_evals_per_step == 1;
@@ -1183,7 +1246,6 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
         md_set_error(c, "run: quench / isothermal runs are not supported with world > 1 yet");
         return MDSEA_ERR_UNSUPPORTED;
     }
-    const size_t row_stride = W == 1 ? (size_t)c->n_global : (size_t)s->cap;
     for (int k = 0; k < a->nsteps; ++k) {
         if (verlet) {
             if (reuse && c->acc_valid) {
@@ -1196,21 +1258,8 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
         } else {
             MD_TRY(cut_kick_drift(c, true, false, true));        // simulator.py:533
         }
-        MD_TRY(after_drift(c));
-        MD_TRY(md_cutoff_force(c));                               // simulator.py:544
-        double *rr = a->record_coords ? c->d_r_rows + (size_t)k * 3 * row_stride : nullptr;
-        double *vr = a->record_coords ? c->d_v_rows + (size_t)k * 3 * row_stride : nullptr;
-        int *idr = (a->record_coords && W > 1) ? s->id_rows + (size_t)k * s->cap : nullptr;
-        if (W > 1) s->row_n_own[k] = c->n;
-        md_prof_begin(c);
-        c->n_ke_part = g256(c->n);
-        k_cut_kick_finish<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride,
-                                                            idr, c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr);
-        md_prof_end(c, &c->stats.ms_integrate);
-        MD_CUDA(c, cudaGetLastError());
-        c->stats.kernel_launches += 1;
+        MD_TRY(force_after_drift(c, a, k, g_dt));                 // simulator.py:544 + kick + energies + row
         c->acc_valid = true;
-        MD_TRY(md_finalize_step(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k));
     }
     if (W > 1) {  // global energies: one small allreduce per batch (the rows hold this rank's share of the means)
         MD_TRY(md_comm_allreduce_sum_f64(c, c->d_pe_rows, a->nsteps));

@@ -99,8 +99,9 @@ k_finalize(const double *__restrict__ pe_part, int n_pe,
            const double *__restrict__ ke_part, int n_ke, double pe_factor /* lam_eps / 2 / N */,
            double ke_factor /* 0.5 m / N */, double kb, StepScalars *__restrict__ sc, double *__restrict__ pe_rows,
            double *__restrict__ ke_rows, double *__restrict__ temp_rows, int row, const double *__restrict__ quench_next,
-           long long step_index) {
+           long long step_index, int guarded) {
     __shared__ double red[32];
+    if (guarded && sc->rebuild_flag) return;  // speculative launch of the cut-off path (see cells.cu)
     double pe = 0.0, ke = 0.0;
     {   // four independent accumulators per thread: the loads are latency-, not bandwidth-bound
         double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
@@ -229,14 +230,14 @@ int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, 
     return MDSEA_OK;
 }
 
-int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index) {
+int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index, int guarded) {
     const double N = (double)c->n_global;
     const double pe_factor = (c->pot.fast == POTF_IDEAL) ? 0.0 : c->pot.lam_eps * 0.5 / N;
     const double ke_factor = 0.5 * c->p.mass / N;
     const double *qn = next_row_valid ? c->d_quench + (size_t)(row + 1) * 2 : nullptr;
     k_finalize<<<1, 1024, 0, c->stream>>>(c->d_pe_part, c->n_pe_part, c->d_ke_part, c->n_ke_part, pe_factor,
                                          ke_factor, kb, c->d_sc, c->d_pe_rows, c->d_ke_rows, c->d_temp_rows, row, qn,
-                                         step_index);
+                                         step_index, guarded);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;
