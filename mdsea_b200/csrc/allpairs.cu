@@ -238,7 +238,7 @@ k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF
         const int b = blockIdx.y * gridDim.x + blockIdx.x;
         pe_part[b] = bpe;
         cnt_part[b] = bc;
-        atomicAdd(&sc->pairs_directed, (unsigned long long)bc);  // integer: order-independent, stats only
+        atomicAdd(&sc->pairs_pending, (unsigned long long)bc);  // integer: order-independent, stats only
     }
 }
 
@@ -382,7 +382,7 @@ k_allpairs_f32(const uint32_t *__restrict__ q, const double *__restrict__ r64, i
         const int b = blockIdx.y * gridDim.x + blockIdx.x;
         pe_part[b] = bpe;
         cnt_part[b] = bc;
-        atomicAdd(&sc->pairs_directed, (unsigned long long)bc);  // integer: order-independent, stats only
+        atomicAdd(&sc->pairs_pending, (unsigned long long)bc);  // integer: order-independent, stats only
     }
 }
 

@@ -117,6 +117,11 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
     CK(cudaSetDevice(p->device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    {   // the halo refresh must not queue behind the thousands of CTAs of the force kernel it overlaps with
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CK(cudaEventCreateWithFlags(&c->ev_batch_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev_a));
@@ -163,6 +168,7 @@ extern "C" void mdsea_b200_destroy(mdsea_ctx *c) {
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     md_cells_free(c);
     cudaFree(c->d_r); cudaFree(c->d_v); cudaFree(c->d_acc); cudaFree(c->d_fpart);
     cudaFree(c->d_pe_part); cudaFree(c->d_cnt_part); cudaFree(c->d_ke_part);
@@ -178,6 +184,7 @@ extern "C" void mdsea_b200_destroy(mdsea_ctx *c) {
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     delete c;
 }
 
@@ -269,6 +276,7 @@ extern "C" int mdsea_b200_update_acc(mdsea_ctx *c, double *acc, double *mean_pe)
     ForceSrc s;
     MD_TRY(eval_forces(c, &s));
     if (s.f != c->d_acc) MD_TRY(md_reduce_acc(c, s.f, s.nparts, s.stride));
+    MD_TRY(md_commit_pairs(c));
     c->acc_valid = true;
     if (mean_pe) {
         // sum the per-block partials on the host (diagnostic path, not the step loop)

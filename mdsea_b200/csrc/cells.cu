@@ -57,6 +57,19 @@ __host__ __device__ inline bool dc_in_ext(const Decomp &D, int q, int cx, int cy
     return true;
 }
 
+// does the 27-cell stencil of this OWNED cell reach into the halo?  (cells on a face of the block in a decomposed
+// dimension)  Interior cells only have owned neighbours, so their forces do not wait for the halo refresh.
+__host__ __device__ inline bool dc_is_boundary(const Decomp &D, int cx, int cy, int cz) {
+    const int b[3] = {D.rank % D.p[0], (D.rank / D.p[0]) % D.p[1], D.rank / (D.p[0] * D.p[1])};
+    const int cc[3] = {cx, cy, cz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (D.p[d] == 1) continue;
+        if (cc[d] == D.bnd[d][b[d]] || cc[d] == D.bnd[d][b[d] + 1] - 1) return true;
+    }
+    return false;
+}
+
 struct PMsg {  // one particle in a rebuild-time message
     double    r[3], v[3];
     long long id;
@@ -65,6 +78,8 @@ struct PMsg {  // one particle in a rebuild-time message
 struct CellState {
     Decomp    D;
     long long n_tot = 0;                  // owned + ghost slots in use
+    long long n_int = 0;                  // owned slots [0, n_int) are interior (no ghost neighbours), [n_int, n) boundary
+    cudaEvent_t ev_drift = nullptr;       // main stream -> comm stream
     // multi-rank staging
     PMsg  *sendpool = nullptr, *recvpool = nullptr;
     long long sendpool_cap = 0;
@@ -135,8 +150,8 @@ __device__ __forceinline__ double md_r2_canonical(double dx, double dy, double d
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2a: keys.  key = ghost << 63 | cell id << 32 | particle id ; value = current (staging) slot.
-// Owned particles sort before ghosts; within each class the order is the canonical (cell id, particle id).
+// K2a: keys.  key = ghost << 63 | boundary << 62 | cell id << 32 | particle id ; value = current (staging) slot.
+// Slot order: owned interior, owned boundary, ghosts; within each class the canonical (cell id, particle id).
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_cell_keys(const double *__restrict__ r, const int *__restrict__ id, long long n, long long cap, double L,
                             double cl, int nc, Decomp D, unsigned long long *__restrict__ key, int *__restrict__ val,
@@ -147,12 +162,16 @@ __global__ void k_cell_keys(const double *__restrict__ r, const int *__restrict_
     const int cy = md_cell_coord(r[cap + i], L, cl, nc);
     const int cz = md_cell_coord(r[2 * cap + i], L, cl, nc);
     const unsigned long long c = (unsigned long long)((cz * nc + cy) * nc + cx);
-    unsigned long long ghost = 0ull;
+    unsigned long long ghost = 0ull, bnd = 0ull;
     if (D.world > 1) {
         ghost = dc_owner(D, cx, cy, cz) != D.rank ? 1ull : 0ull;
-        if (!ghost) atomicAdd(n_owned, 1);
+        if (!ghost) {
+            atomicAdd(n_owned, 1);
+            bnd = dc_is_boundary(D, cx, cy, cz) ? 1ull : 0ull;
+            if (!bnd) atomicAdd(n_owned + 1, 1);
+        }
     }
-    key[i] = (ghost << 63) | (c << 32) | (unsigned)id[i];
+    key[i] = (ghost << 63) | (bnd << 62) | (c << 32) | (unsigned)id[i];
     val[i] = (int)i;
 }
 
@@ -272,7 +291,7 @@ __global__ void k_reorder(const unsigned long long *__restrict__ key, const int 
     const unsigned long long k = key[s];
     const int o = val[s];
     id_out[s] = (int)(k & 0xffffffffull);
-    cell[s] = (int)((k >> 32) & 0x7fffffffull);
+    cell[s] = (int)((k >> 32) & 0x3fffffffull);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const double x = r_in[d * cap + o];
@@ -428,13 +447,13 @@ struct LjF64 { double c6, sigma2; };   // c6 = 6 lambda eps / m
 struct LjF32 { float c6, sigma2; };    // in fixed-point units (see allpairs.cu)
 
 __global__ void __launch_bounds__(NB_THREADS)
-k_nbr_force_f64(const double4 *__restrict__ pos, long long n_own, long long cap, const int *__restrict__ nbr,
+k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_own, long long cap, const int *__restrict__ nbr,
                 const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, LjF64 P,
                 double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0;
     unsigned cnt = 0;
     if (i < n_own) {
@@ -468,19 +487,19 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long n_own, long long cap,
     const unsigned bc = md_block_sum(cnt, redu);
     if (threadIdx.x == 0) {
         pe_part[blockIdx.x] = bpe;
-        atomicAdd(&sc->pairs_directed, (unsigned long long)bc);
+        atomicAdd(&sc->pairs_pending, (unsigned long long)bc);
     }
 }
 
 __global__ void __launch_bounds__(NB_THREADS)
-k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long n_own, long long cap,
+k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long i_begin, long long n_own, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
                 double rc2, float rc2s, double inv_h, LjF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
                 StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   Fx = 0.0, Fy = 0.0, Fz = 0.0, PE = 0.0;
     unsigned cnt = 0;
     if (i < n_own) {
@@ -552,7 +571,7 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, l
     const unsigned bc = md_block_sum(cnt, redu);
     if (threadIdx.x == 0) {
         pe_part[blockIdx.x] = bpe;
-        atomicAdd(&sc->pairs_directed, (unsigned long long)bc);
+        atomicAdd(&sc->pairs_pending, (unsigned long long)bc);
     }
 }
 
@@ -776,24 +795,54 @@ __global__ void k_halo_lists(const int *__restrict__ flag, const int *__restrict
     const long long q = t / n_tot, s = t - q * n_tot;
     idx[q * n_tot + (scan[t] - scan[q * n_tot])] = (int)s;
 }
-__global__ void k_halo_pack(const double *__restrict__ r, long long cap, const int *__restrict__ idx, long long n,
-                            double *__restrict__ buf) {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int s = idx[k];
-    buf[3 * k] = r[s];
-    buf[3 * k + 1] = r[cap + s];
-    buf[3 * k + 2] = r[2 * cap + s];
+// One message per peer and step: [3 * n positions][1 double: this rank's skin-trigger flag].  Every rank sends to
+// every other rank every step (an empty halo still carries the flag), so after the unpack each rank holds the
+// MAX of all flags -- the collective rebuild decision rides on the halo traffic instead of a separate allreduce.
+struct HaloTab {
+    int       world, rank;
+    long long ent0[MD_MAXW + 1];  // prefix sum of the per-peer entry counts (self: 0 entries)
+    long long idx0[MD_MAXW];      // start of the peer's index list inside halo_idx
+};
+__device__ __forceinline__ int halo_peer_of(const HaloTab &T, long long k) {
+    int q = 0;
+    while (q + 1 < T.world && k >= T.ent0[q + 1]) ++q;
+    return q;
 }
-__global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restrict__ idx, long long n, long long cap,
-                              double *__restrict__ r, int fp32, double inv_h, void *__restrict__ pos4) {
+__global__ void k_halo_pack(const double *__restrict__ r, long long cap, const int *__restrict__ idx, HaloTab T,
+                            const StepScalars *__restrict__ sc, double *__restrict__ buf) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int s = idx[k];
-    const double x = buf[3 * k], y = buf[3 * k + 1], z = buf[3 * k + 2];
-    r[s] = x; r[cap + s] = y; r[2 * cap + s] = z;
-    if (fp32) ((uint4 *)pos4)[s] = make_uint4(md_to_fixed(x, inv_h), md_to_fixed(y, inv_h), md_to_fixed(z, inv_h), 0u);
-    else ((double4 *)pos4)[s] = make_double4(x, y, z, 0.0);
+    const long long total = T.ent0[T.world];
+    if (k < total) {
+        const int q = halo_peer_of(T, k);
+        const long long l = k - T.ent0[q];
+        const int s = idx[T.idx0[q] + l];
+        double *m = buf + 3 * T.ent0[q] + q;  // q flag slots precede this peer's segment
+        m[3 * l] = r[s];
+        m[3 * l + 1] = r[cap + s];
+        m[3 * l + 2] = r[2 * cap + s];
+    } else if (k < total + T.world) {
+        const int q = (int)(k - total);
+        if (q != T.rank) buf[3 * T.ent0[q + 1] + q] = (double)sc->rebuild_flag;
+    }
+}
+__global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restrict__ idx, HaloTab T, long long cap,
+                              double *__restrict__ r, int fp32, double inv_h, void *__restrict__ pos4,
+                              StepScalars *__restrict__ sc) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = T.ent0[T.world];
+    if (k < total) {
+        const int q = halo_peer_of(T, k);
+        const long long l = k - T.ent0[q];
+        const int s = idx[T.idx0[q] + l];
+        const double *m = buf + 3 * T.ent0[q] + q;
+        const double x = m[3 * l], y = m[3 * l + 1], z = m[3 * l + 2];
+        r[s] = x; r[cap + s] = y; r[2 * cap + s] = z;
+        if (fp32) ((uint4 *)pos4)[s] = make_uint4(md_to_fixed(x, inv_h), md_to_fixed(y, inv_h), md_to_fixed(z, inv_h), 0u);
+        else ((double4 *)pos4)[s] = make_double4(x, y, z, 0.0);
+    } else if (k < total + T.world) {
+        const int q = (int)(k - total);
+        if (q != T.rank && buf[3 * T.ent0[q + 1] + q] != 0.0) sc->rebuild_flag = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -882,7 +931,8 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
     MD_CUDA(c, cudaMalloc(&s->nbr_cnt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->d_cnt, sizeof(int) * (MD_MAXW + 8)));
-    MD_CUDA(c, cudaMallocHost(&s->h_flag, sizeof(int) * 2));
+    MD_CUDA(c, cudaMallocHost(&s->h_flag, sizeof(int) * 4));
+    MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_drift, cudaEventDisableTiming));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_flag, cudaEventDisableTiming));
     MD_CUDA(c, cudaMallocHost(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8)));
     const size_t row_stride = W == 1 ? (size_t)N : (size_t)s->cap;
@@ -904,8 +954,8 @@ int md_cells_setup(mdsea_ctx *c) {
         MD_CUDA(c, cudaMalloc(&s->halo_scan, sizeof(int) * ((size_t)W * s->cap + 1)));
         MD_CUDA(c, cudaMalloc(&s->halo_idx, sizeof(int) * (size_t)W * s->cap));
         MD_CUDA(c, cudaMalloc(&s->scan_tmp, sizeof(int) * (md_div_up((long long)W * s->cap + 1, SCAN_THREADS * SCAN_ITEMS) + 1)));
-        MD_CUDA(c, cudaMalloc(&s->halo_send, sizeof(double) * 3 * (size_t)s->cap * std::min(W - 1, 3)));
-        MD_CUDA(c, cudaMalloc(&s->halo_recv, sizeof(double) * 3 * (size_t)s->cap));
+        MD_CUDA(c, cudaMalloc(&s->halo_send, sizeof(double) * (3 * (size_t)s->cap * std::min(W - 1, 3) + MD_MAXW)));
+        MD_CUDA(c, cudaMalloc(&s->halo_recv, sizeof(double) * (3 * (size_t)s->cap + MD_MAXW)));
         MD_CUDA(c, cudaMalloc(&s->id_rows, sizeof(int) * (size_t)s->cap * c->ring));
         s->row_n_own.assign(c->ring, 0);
     }
@@ -925,6 +975,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->id_rows);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
+    if (s->ev_drift) cudaEventDestroy(s->ev_drift);
     if (s->h_cnt_all) cudaFreeHost(s->h_cnt_all);
     delete s;
     c->cells = nullptr;
@@ -1041,42 +1092,35 @@ static int build_halo_lists(mdsea_ctx *c) {
     return MDSEA_OK;
 }
 
-// per step: owned boundary positions -> the ranks that hold them as ghosts
-static int halo_exchange(mdsea_ctx *c) {
+// per step: owned boundary positions (+ the trigger flag) -> the ranks that hold them as ghosts
+static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
     CellState *s = c->cells;
     const int W = c->p.world, me = c->p.rank;
-    md_prof_begin(c);
+    if (st == c->stream) md_prof_begin(c);
+    HaloTab ts, tr;
+    ts.world = tr.world = W;
+    ts.rank = tr.rank = me;
+    ts.ent0[0] = tr.ent0[0] = 0;
+    for (int q = 0; q < W; ++q) {
+        ts.ent0[q + 1] = ts.ent0[q] + (q == me ? 0 : s->halo_nsend[q]);
+        tr.ent0[q + 1] = tr.ent0[q] + (q == me ? 0 : s->halo_nrecv[q]);
+        ts.idx0[q] = s->halo_base[q];
+        tr.idx0[q] = s->halo_base[q] + s->halo_nsend[q];
+    }
     void  *sp[MD_MAXW], *rp[MD_MAXW];
     size_t sb[MD_MAXW], rbytes[MD_MAXW];
-    long long so = 0, ro = 0;
     for (int q = 0; q < W; ++q) {
-        sp[q] = s->halo_send + 3 * so;
-        rp[q] = s->halo_recv + 3 * ro;
-        sb[q] = rbytes[q] = 0;
-        if (q == me) continue;
-        const long long ns = s->halo_nsend[q], nr = s->halo_nrecv[q];
-        if (ns) {
-            k_halo_pack<<<g256(ns), 256, 0, c->stream>>>(c->d_r, s->cap, s->halo_idx + s->halo_base[q], ns, s->halo_send + 3 * so);
-            c->stats.kernel_launches += 1;
-        }
-        sb[q] = sizeof(double) * 3 * (size_t)ns;
-        rbytes[q] = sizeof(double) * 3 * (size_t)nr;
-        so += ns;
-        ro += nr;
+        sp[q] = s->halo_send + 3 * ts.ent0[q] + q;
+        rp[q] = s->halo_recv + 3 * tr.ent0[q] + q;
+        sb[q] = q == me ? 0 : sizeof(double) * (3 * (size_t)s->halo_nsend[q] + 1);
+        rbytes[q] = q == me ? 0 : sizeof(double) * (3 * (size_t)s->halo_nrecv[q] + 1);
     }
-    MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes));
-    ro = 0;
-    for (int q = 0; q < W; ++q) {
-        if (q == me) continue;
-        const long long nr = s->halo_nrecv[q];
-        if (nr) {
-            k_halo_unpack<<<g256(nr), 256, 0, c->stream>>>(s->halo_recv + 3 * ro, s->halo_idx + s->halo_base[q] + s->halo_nsend[q], nr,
-                                                           s->cap, c->d_r, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4);
-            c->stats.kernel_launches += 1;
-        }
-        ro += nr;
-    }
-    md_prof_end(c, &c->stats.ms_comm);
+    k_halo_pack<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, s->halo_send);
+    MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes, st));
+    k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->halo_recv, s->halo_idx, tr, s->cap, c->d_r,
+                                                        c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc);
+    c->stats.kernel_launches += 2;
+    if (st == c->stream) md_prof_end(c, &c->stats.ms_comm);
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;
 }
@@ -1086,13 +1130,13 @@ static int rebuild(mdsea_ctx *c) {
     const int W = c->p.world;
     md_prof_begin(c);
     if (W > 1) MD_TRY(mr_assemble(c));
-    else s->n_tot = c->n;
+    else s->n_tot = s->n_int = c->n;
     const long long nt = s->n_tot;
     const double *src_r = W > 1 ? s->r_alt : c->d_r, *src_v = W > 1 ? s->v_alt : c->d_v;
     const int    *src_id = W > 1 ? s->id_alt : s->id;
     double *dst_r = W > 1 ? c->d_r : s->r_alt, *dst_v = W > 1 ? c->d_v : s->v_alt;
     int    *dst_id = W > 1 ? s->id : s->id_alt;
-    MD_CUDA(c, cudaMemsetAsync(s->d_cnt + MD_MAXW, 0, sizeof(int), c->stream));
+    MD_CUDA(c, cudaMemsetAsync(s->d_cnt + MD_MAXW, 0, 2 * sizeof(int), c->stream));
     k_cell_keys<<<g256(nt), 256, 0, c->stream>>>(src_r, src_id, nt, s->cap, c->box.L, s->cell_len, s->nc, s->D, s->key, s->val,
                                                  s->d_cnt + MD_MAXW);
     int launches = 1;
@@ -1118,9 +1162,10 @@ static int rebuild(mdsea_ctx *c) {
         std::swap(c->d_v, s->v_alt);
         std::swap(s->id, s->id_alt);
     } else {
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt + MD_MAXW, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt + MD_MAXW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MD_CUDA(c, cudaStreamSynchronize(c->stream));
         c->n = s->h_flag[0];
+        s->n_int = s->h_flag[1];
         c->stats.n_local = c->n;
         c->stats.n_ghost = nt - c->n;
     }
@@ -1147,32 +1192,40 @@ static int rebuild(mdsea_ctx *c) {
     return MDSEA_OK;
 }
 
-static int cutoff_force(mdsea_ctx *c, int guarded) {
+// force kernel over the owned slots [i0, i1); its per-block PE partials go to pe_part[pe_off ...]
+static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded) {
     CellState *s = c->cells;
-    if (s->need_rebuild) MD_TRY(rebuild(c));
-    const long long n = c->n;
-    md_prof_begin(c);
-    const int grid = md_div_up(n > 0 ? n : 1, NB_THREADS);
-    c->n_pe_part = grid;
+    if (i1 <= i0) return MDSEA_OK;
+    const int grid = md_div_up(i1 - i0, NB_THREADS);
     if (c->p.precision == MDSEA_FP64) {
         LjF64 P;
         P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
         P.sigma2 = c->pot.sigma2;
-        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, n, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
-                                                            c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part, c->d_sc, guarded);
+        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
+                                                            c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off, c->d_sc,
+                                                            guarded);
     } else {
         const double inv_h = fixed_inv_h(c);
         LjF32 P;
         P.c6 = (float)(6.0 * c->pot.lam_eps * c->pot.inv_mass * inv_h);
         P.sigma2 = (float)(c->pot.sigma2 * inv_h * inv_h);
-        k_nbr_force_f32<<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, n, s->cap, s->nbr, s->nbr_cnt,
+        k_nbr_force_f32<<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, i0, i1, s->cap, s->nbr, s->nbr_cnt,
                                                             s->max_nbr, c->box.L, c->box.halfL, s->rc2,
-                                                            (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc, c->d_pe_part,
-                                                            c->d_sc, guarded);
+                                                            (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
+                                                            c->d_pe_part + pe_off, c->d_sc, guarded);
     }
-    md_prof_end(c, &c->stats.ms_force);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
+    return MDSEA_OK;
+}
+
+static int cutoff_force(mdsea_ctx *c, int guarded) {
+    CellState *s = c->cells;
+    if (s->need_rebuild) MD_TRY(rebuild(c));
+    md_prof_begin(c);
+    c->n_pe_part = md_div_up(c->n > 0 ? c->n : 1, NB_THREADS);
+    MD_TRY(launch_force(c, 0, c->n, 0, guarded));
+    md_prof_end(c, &c->stats.ms_force);
     c->stats.force_evals += 1;
     return MDSEA_OK;
 }
@@ -1212,8 +1265,8 @@ static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k,
 // After a drift the skin trigger sits in a device flag.  To keep the GPU busy while the host learns its value,
 // the force / kick_finish / finalize kernels of the step are launched SPECULATIVELY, guarded by that flag (they
 // return at once when it is set); the host then reads the flag and, only if it fired (every ~6 steps at 1e6
-// particles), rebuilds and launches the three kernels again.  Multi-rank: the flag is first allreduced (MAX) so
-// that all ranks rebuild together, and the ghost refresh is issued unconditionally (harmless before a rebuild).
+// particles), rebuilds and launches the three kernels again.  Multi-rank: the per-step halo messages carry every
+// rank's flag, so after the (unconditional) ghost refresh all ranks hold the same MAX and rebuild together.
 static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt) {
     CellState *s = c->cells;
     const int W = c->p.world;
@@ -1221,17 +1274,38 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
         MD_TRY(cutoff_force(c, 0));
         return cut_finish_and_finalize(c, a, k, g_dt, 0);
     }
-    if (W > 1) MD_TRY(md_comm_allreduce_max_i32(c, &c->d_sc->rebuild_flag, 1));
-    MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
-    if (W > 1) MD_TRY(halo_exchange(c));
     const long long fe0 = c->stats.force_evals;
-    MD_TRY(cutoff_force(c, 1));
+    if (W == 1) {
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
+        MD_TRY(cutoff_force(c, 1));
+    } else if (c->profiling) {  // per-family timers need everything on one stream: no overlap
+        MD_TRY(halo_exchange(c, c->stream));
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
+        MD_TRY(cutoff_force(c, 1));
+    } else {
+        // comm stream: ghost refresh (+ flags) while the main stream computes the INTERIOR forces, which need no ghosts
+        MD_CUDA(c, cudaEventRecord(s->ev_drift, c->stream));
+        MD_CUDA(c, cudaStreamWaitEvent(c->comm_stream, s->ev_drift, 0));
+        MD_TRY(halo_exchange(c, c->comm_stream));
+        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->comm_stream));
+        MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
+        const int gi = md_div_up(s->n_int > 0 ? s->n_int : 1, NB_THREADS);
+        c->n_pe_part = gi + md_div_up(c->n - s->n_int > 0 ? c->n - s->n_int : 1, NB_THREADS);
+        MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
+        MD_TRY(launch_force(c, 0, s->n_int, 0, 1));                       // guarded by the LOCAL flag only (the global one
+                                                                          // is not known yet): redone if any rank fired
+        MD_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_flag, 0));
+        MD_TRY(launch_force(c, s->n_int, c->n, gi, 1));                   // boundary particles: ghosts are fresh now
+        c->stats.force_evals += 1;
+    }
     MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 1));
     MD_CUDA(c, cudaEventSynchronize(s->ev_flag));
-    if (s->h_flag[0]) {  // the speculative kernels did nothing; rebuild (clears the flag) and do the step for real
+    if (s->h_flag[0]) {  // the guarded kernels did nothing; rebuild (clears the flag) and do the step for real
         c->stats.force_evals = fe0;
         s->need_rebuild = true;
+        MD_CUDA(c, cudaMemsetAsync(&c->d_sc->pairs_pending, 0, sizeof(unsigned long long), c->stream));
         MD_TRY(cutoff_force(c, 0));
         MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 0));
     }
@@ -1253,6 +1327,7 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
             } else {
                 MD_TRY(cut_kick_drift(c, true, false, false));   // apply_bc
                 MD_TRY(md_cutoff_force(c));                       // simulator.py:540
+                MD_TRY(md_commit_pairs(c));                       // counted for good: not part of the speculation below
                 MD_TRY(cut_kick_drift(c, false, true, true));
             }
         } else {

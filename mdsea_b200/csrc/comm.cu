@@ -240,14 +240,15 @@ int md_comm_allreduce_sum_f64(mdsea_ctx *c, double *d_buf, int count) {
 // personalised exchange: send[q] (send_bytes[q]) goes to rank q, recv[p] (recv_bytes[p]) comes from rank p.
 // Entries for q == rank are ignored (the caller handles its own data in place).
 int md_comm_exchange(mdsea_ctx *c, void *const *d_send, const size_t *send_bytes, void *const *d_recv,
-                     const size_t *recv_bytes) {
+                     const size_t *recv_bytes, cudaStream_t stream) {
     CommState *s = c->comm;
+    if (!stream) stream = c->stream;
     if (s->backend == 1) {
         MD_NCCL(c, g_nccl.GroupStart());
         for (int q = 0; q < s->world; ++q) {
             if (q == s->rank) continue;
-            if (send_bytes[q]) MD_NCCL(c, g_nccl.Send(d_send[q], send_bytes[q], ncclUint8, q, s->nccl, c->stream));
-            if (recv_bytes[q]) MD_NCCL(c, g_nccl.Recv(d_recv[q], recv_bytes[q], ncclUint8, q, s->nccl, c->stream));
+            if (send_bytes[q]) MD_NCCL(c, g_nccl.Send(d_send[q], send_bytes[q], ncclUint8, q, s->nccl, stream));
+            if (recv_bytes[q]) MD_NCCL(c, g_nccl.Recv(d_recv[q], recv_bytes[q], ncclUint8, q, s->nccl, stream));
         }
         MD_NCCL(c, g_nccl.GroupEnd());
         return MDSEA_OK;
@@ -257,7 +258,7 @@ int md_comm_exchange(mdsea_ctx *c, void *const *d_send, const size_t *send_bytes
         g->ptr[s->rank][q] = d_send[q];
         g->bytes[s->rank][q] = send_bytes[q];
     }
-    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    MD_CUDA(c, cudaStreamSynchronize(stream));
     pthread_barrier_wait(&g->bar);
     for (int p = 0; p < s->world; ++p) {
         if (p == s->rank || !recv_bytes[p]) continue;
@@ -266,9 +267,9 @@ int md_comm_exchange(mdsea_ctx *c, void *const *d_send, const size_t *send_bytes
             pthread_barrier_wait(&g->bar);
             return MDSEA_ERR_STATE;
         }
-        MD_CUDA(c, cudaMemcpyAsync(d_recv[p], g->ptr[p][s->rank], recv_bytes[p], cudaMemcpyDefault, c->stream));
+        MD_CUDA(c, cudaMemcpyAsync(d_recv[p], g->ptr[p][s->rank], recv_bytes[p], cudaMemcpyDefault, stream));
     }
-    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    MD_CUDA(c, cudaStreamSynchronize(stream));
     pthread_barrier_wait(&g->bar);
     return MDSEA_OK;
 }

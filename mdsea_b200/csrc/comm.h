@@ -10,5 +10,6 @@ int  md_comm_world(const mdsea_ctx *c);
 int  md_comm_allgather_i32(mdsea_ctx *c, const int *d_send, int count, int *d_recv);
 int  md_comm_allreduce_max_i32(mdsea_ctx *c, int *d_buf, int count);
 int  md_comm_allreduce_sum_f64(mdsea_ctx *c, double *d_buf, int count);
+#include <cuda_runtime.h>
 int  md_comm_exchange(mdsea_ctx *c, void *const *d_send, const size_t *send_bytes, void *const *d_recv,
-                      const size_t *recv_bytes);
+                      const size_t *recv_bytes, cudaStream_t stream = nullptr);

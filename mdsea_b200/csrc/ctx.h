@@ -21,6 +21,7 @@ struct mdsea_ctx {
 
     cudaStream_t stream = nullptr;       // compute stream
     cudaStream_t copy_stream = nullptr;  // D2H of buffered rows
+    cudaStream_t comm_stream = nullptr;  // halo refresh, overlapped with the interior force kernel
     cudaEvent_t  ev_batch_done = nullptr, ev_copy_done = nullptr;
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
 
@@ -82,6 +83,7 @@ int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, 
 int md_reduce_acc(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride);
 int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index, int guarded = 0);
 int md_prepare_first(mdsea_ctx *c, double kb);
+int md_commit_pairs(mdsea_ctx *c);
 int md_pair_dists(mdsea_ctx *c, double *d_dists, double *d_units);
 // cells.cu / nbr.cu (cutoff path)
 int md_cells_setup(mdsea_ctx *c);

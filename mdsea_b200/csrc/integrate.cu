@@ -128,6 +128,8 @@ k_finalize(const double *__restrict__ pe_part, int n_pe,
         sc->ke_prev = mean_ke;
         sc->ke_valid = 1;
         sc->steps_done += 1;
+        sc->pairs_directed += sc->pairs_pending;
+        sc->pairs_pending = 0ull;
         // quench bookkeeping for the NEXT step (simulator.py:185-195, 233-239)
         double scale = 1.0, temp = sc->temp;
         if (quench_next) {
@@ -142,6 +144,11 @@ k_finalize(const double *__restrict__ pe_part, int n_pe,
         sc->temp = temp;
         sc->scale = scale;
     }
+}
+
+__global__ void k_commit_pairs(StepScalars *sc) {
+    sc->pairs_directed += sc->pairs_pending;
+    sc->pairs_pending = 0ull;
 }
 
 // quench bookkeeping for the first step of a batch (uses the scalars left by the previous batch)
@@ -238,6 +245,13 @@ int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long 
     k_finalize<<<1, 1024, 0, c->stream>>>(c->d_pe_part, c->n_pe_part, c->d_ke_part, c->n_ke_part, pe_factor,
                                          ke_factor, kb, c->d_sc, c->d_pe_rows, c->d_ke_rows, c->d_temp_rows, row, qn,
                                          step_index, guarded);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+int md_commit_pairs(mdsea_ctx *c) {
+    k_commit_pairs<<<1, 1, 0, c->stream>>>(c->d_sc);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;
