@@ -15,6 +15,8 @@
 // positions that the drift kernel refreshes every step (double4 in fp64 mode; uint4 32-bit fixed point in
 // fp32 mode, where integer subtraction gives the minimum image for free).  The neighbour list is a sliced
 // ELLPACK (tiles of 32 particles x max_nbr rows) so that a warp of consecutive particles reads it coalesced.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ctx.h"
@@ -1125,12 +1127,29 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
     return MDSEA_OK;
 }
 
+#include <chrono>
+static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
+struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronises the stream; off by default)
+    mdsea_ctx *c;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(mdsea_ctx *cc) : c(cc) { if (g_trace_rebuild) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); } }
+    void lap(const char *name) {
+        if (!g_trace_rebuild) return;
+        cudaStreamSynchronize(c->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rebuild rank %d] %-12s %8.1f us\n", c->p.rank, name, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int rebuild(mdsea_ctx *c) {
     CellState *s = c->cells;
     const int W = c->p.world;
     md_prof_begin(c);
+    PhaseTimer pt(c);
     if (W > 1) MD_TRY(mr_assemble(c));
     else s->n_tot = s->n_int = c->n;
+    pt.lap("assemble");
     const long long nt = s->n_tot;
     const double *src_r = W > 1 ? s->r_alt : c->d_r, *src_v = W > 1 ? s->v_alt : c->d_v;
     const int    *src_id = W > 1 ? s->id_alt : s->id;
@@ -1156,6 +1175,7 @@ static int rebuild(mdsea_ctx *c) {
         std::swap(s->val, s->val_alt);
         launches += 3;
     }
+    pt.lap("keys+sort");
     k_reorder<<<g256(nt), 256, 0, c->stream>>>(s->key, s->val, nt, s->cap, src_r, src_v, dst_r, dst_v, s->rb, dst_id, s->cell);
     if (W == 1) {
         std::swap(c->d_r, s->r_alt);
@@ -1174,7 +1194,9 @@ static int rebuild(mdsea_ctx *c) {
     k_cell_bounds<<<g256(nt), 256, 0, c->stream>>>(s->cell, nt, s->cell_start, s->cell_end);
     k_pack_positions<<<g256(nt), 256, 0, c->stream>>>(c->d_r, nt, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4,
                                                       s->qfix);
+    pt.lap("reorder+pack");
     if (W > 1) MD_TRY(build_halo_lists(c));
+    pt.lap("halo lists");
     {
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
@@ -1183,6 +1205,7 @@ static int rebuild(mdsea_ctx *c) {
             (float)(rl2s * (1.0 - 1e-5)), (float)(rl2s * (1.0 + 1e-5)), s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
     }
     launches += 4;
+    pt.lap("nbr build");
     MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
     md_prof_end(c, &c->stats.ms_rebuild);
     MD_CUDA(c, cudaGetLastError());
