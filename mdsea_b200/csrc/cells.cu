@@ -16,6 +16,7 @@
 // fp32 mode, where integer subtraction gives the minimum image for free).  The neighbour list is a sliced
 // ELLPACK (tiles of 32 particles x max_nbr rows) so that a warp of consecutive particles reads it coalesced.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -25,8 +26,8 @@
 #define SORT_THREADS 256
 #define SORT_ITEMS 8
 #define SORT_CHUNK (SORT_THREADS * SORT_ITEMS)
-#define NB_THREADS 128
-#define NBG 8  // list entries per gather group; rows are padded to a multiple of it
+#define NB_THREADS 128       // thread-per-particle list build
+#define FORCE_THREADS 256    // list force kernels: FG lanes per particle -> FORCE_THREADS / FG particles per block
 
 // Spatial domain decomposition on the canonical cell grid: rank (bx, by, bz) of a px*py*pz process grid owns the
 // cells with bnd[d][b_d] <= c_d < bnd[d][b_d + 1]; its halo is the one-cell layer around that block (periodic).
@@ -329,23 +330,33 @@ __global__ void k_pack_positions(const double *__restrict__ r, long long n, long
     else ((double4 *)pos4)[i] = make_double4(x, y, z, 0.0);
 }
 
-// Neighbour-list layout: sliced ELLPACK.  Particles are grouped in tiles of 32 consecutive slots (= one warp of
-// the force kernel); tile t owns max_nbr rows of 32 ints, entry (k, lane) at t*max_nbr*32 + k*32 + lane.  The
-// force kernel reads one 128-byte row per k (coalesced); the build kernel's stores of one warp all land in the
-// same ~15 KB tile, so partially written sectors merge in L2 instead of being evicted half empty.
-__device__ __forceinline__ size_t md_nbr_index(long long i, int k, int max_nbr) {
-    return ((size_t)(i >> 5) * (size_t)max_nbr + (size_t)k) * 32u + (size_t)(i & 31);
+// Neighbour-list layout: sliced ELLPACK for FG-lane groups.  The force kernels give every particle a group of
+// FG = 8 lanes that walk its row 8 entries at a time, so a warp serves the 4 consecutive particles of one "quad".
+// Quad t = i >> 2 owns max_nbr / 8 chunks of 32 ints; chunk m holds entries 8m .. 8m+7 of its four particles,
+// particle p = i & 3 at ints [8p, 8p+8): entry (i, k) sits at ((i>>2) * max_nbr + (k & ~7)) * 4 + (i&3) * 8 + (k&7).
+// One warp-wide load of a chunk is a single coalesced 128-byte line, and the 8 lanes of a group then gather 8
+// CONSECUTIVE list entries -- neighbours that the build found next to each other in slot order -- so the
+// position gather of a warp touches a handful of lines instead of one line per lane.
+#define FG 8
+__host__ __device__ __forceinline__ size_t md_nbr_row_base(long long i, int max_nbr) {
+    return ((size_t)(i >> 2) * (size_t)max_nbr) * 4u + (size_t)(i & 3) * 8u;
 }
+__host__ __device__ __forceinline__ unsigned md_nbr_off(unsigned k) { return ((k >> 3) << 5) + (k & 7u); }
 
 // ---------------------------------------------------------------------------------------------------
-// K3: Verlet neighbour list.  One thread per particle; the 27-cell stencil of consecutive (cell-sorted)
-// particles overlaps almost completely, so the candidate loads are L1 broadcasts.
+// K3: Verlet neighbour list.
+//
+// Two kernels produce the SAME canonical list (j != i with canonical float64 r^2 < (rc+skin)^2):
+//   k_nbr_build_warp  (default)  one warp per tile of 32 consecutive slots.  The warp walks the UNION of the 27-cell
+//                     stencils of its particles (they share an x-row of cells, so the union is 9 short slot ranges),
+//                     stages 32 candidates at a time in shared memory as floats relative to a common origin (the
+//                     fixed-point subtraction is exact and wraps to the minimum image for free) and every lane tests
+//                     the broadcast candidates against its own particle: no divergence, no per-lane gathers.  In-range
+//                     candidates are collected in a 32-bit mask per lane and appended after each chunk.
+//   k_nbr_build       one thread per particle over its own 27 cells (MDSEA_NBR_BUILD=thread; kept as the A/B baseline).
+// Both decide in float with a guard band around the list radius; a particle that saw a candidate inside the band is
+// redone with the canonical float64 test for every candidate, so the list is the canonical one bit for bit.
 // ---------------------------------------------------------------------------------------------------
-// One slot range of candidates against particle i.  EXACT = false is the hot path: 32-bit fixed-point separations
-// (exact integer differences, minimum image by wrap-around), r^2 in float, branch-free; a candidate whose float
-// r^2 lies within 1e-5 (relative) of the list radius -- far more than the ~5e-7 the float evaluation can be off --
-// only raises `band`.  EXACT = true evaluates the canonical float64 test for every candidate; the kernel re-runs
-// the (rare, ~0.2 % of the particles) banded particles that way, so the list is the canonical one bit for bit.
 template <bool EXACT>
 __device__ __forceinline__ void nb_scan_range(int j0, int j1, const uint4 qi, long long i, const double *__restrict__ r,
                                               const uint4 *__restrict__ q, long long cap, double L, double halfL, double rl2,
@@ -358,14 +369,14 @@ __device__ __forceinline__ void nb_scan_range(int j0, int j1, const uint4 qi, lo
             const double ddy = md_minimg_exact(__dsub_rn(r[cap + j], yi), L, halfL);
             const double ddz = md_minimg_exact(__dsub_rn(r[2 * cap + j], zi), L, halfL);
             if (md_r2_canonical(ddx, ddy, ddz) < rl2 && j != (int)i) {
-                if (cnt < max_nbr) row0[cnt * 32] = j;
+                if (cnt < max_nbr) row0[md_nbr_off((unsigned)cnt)] = j;
                 ++cnt;
             }
         }
     } else {
-        // write cursor as a clamped 32-bit element offset: one predicated store per candidate, no bounds branch
-        // (an over-full row keeps overwriting its last slot; cnt still counts, the caller reports the overflow)
-        const unsigned off_max = (unsigned)(max_nbr - 1) * 32u;
+        // clamped write cursor: one predicated store per candidate, no bounds branch (an over-full row keeps
+        // overwriting its last slot; cnt still counts, the caller reports the overflow)
+        const unsigned k_max = (unsigned)(max_nbr - 1);
 #pragma unroll 4
         for (int j = j0; j < j1; ++j) {
             const uint4 qj = q[j];
@@ -374,7 +385,7 @@ __device__ __forceinline__ void nb_scan_range(int j0, int j1, const uint4 qi, lo
             const bool in = r2f < rl2s_lo;
             band = band || (!in && r2f < rl2s_hi);
             const bool st = in && (j != (int)i);
-            const unsigned off = min((unsigned)cnt * 32u, off_max);
+            const unsigned off = md_nbr_off(min((unsigned)cnt, k_max));
             if (st) row0[off] = j;
             cnt += st ? 1 : 0;
         }
@@ -426,7 +437,7 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
     if (i >= n_own) return;
     const uint4 qi = q[i];
     const int c = cell[i];
-    int *row0 = nbr + md_nbr_index(i, 0, max_nbr);
+    int *row0 = nbr + md_nbr_row_base(i, max_nbr);
     bool band = false;
     int cnt = nb_particle<false>(i, qi, c, r, q, cap, cell_start, cell_end, nc, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, band);
     if (__builtin_expect(band, 0))
@@ -436,51 +447,192 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
         cnt = max_nbr;
     }
     nbr_cnt[i] = cnt;
-    for (int k = cnt; k < ((cnt + NBG - 1) / NBG) * NBG; ++k) row0[k * 32] = (int)i;  // padding, masked by j != i
+}
+
+// ---- warp-cooperative build ------------------------------------------------------------------------
+#define NBW_WARPS 4      // warps (= tiles of 32 slots) per block
+#define NBW_RUN   6      // at most this many x-consecutive cells of i-particles per pass (bounds the float error)
+
+// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle
+__device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
+                                                   float neg_rl2s, float neg_bw, float &bandmin) {
+    unsigned m = 0u;
+    for (int t0 = 0; t0 < ncand; t0 += 8) {
+        unsigned m8 = 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 cj = cand[t0 + u];   // broadcast LDS.128
+            const float dx = cj.x - xi, dy = cj.y - yi, dz = cj.z - zi;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, neg_rl2s)));   // r^2 - rl^2
+            if (d < neg_bw) m8 |= 1u << u;
+            bandmin = fminf(bandmin, fabsf(d));
+        }
+        m |= m8 << t0;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(NBW_WARPS * 32)
+k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
+                 const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
+                 double L, double halfL, double cell_len, double inv_h, double rl2, float rl2s, float bw, float rl2s_lo,
+                 float rl2s_hi, int max_nbr, int *__restrict__ nbr, int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
+    __shared__ float4 s_cand[NBW_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
+    if (i0 >= n_own) return;   // whole warp out of range (only __syncwarp below)
+    const long long i = i0 + lane;
+    const bool valid = i < n_own;
+    const long long il = valid ? i : n_own - 1;
+    const uint4 qi = q[il];
+    const int c = cell[il];
+    const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
+    float4 *cand = s_cand[w];
+    int *row0 = nbr + md_nbr_row_base(il, max_nbr);
+    const unsigned k_max = (unsigned)max_nbr;
+    const float neg_rl2s = -rl2s, neg_bw = -bw;
+    float bandmin = 3.0e38f;
+    int cnt = 0;
+    unsigned todo = __ballot_sync(0xffffffffu, valid);
+    while (todo) {
+        // ---- pick the particles of this pass: same (cy, cz) row as the first pending lane, cx within NBW_RUN cells
+        const int leader = __ffs(todo) - 1;
+        const int cl = __shfl_sync(0xffffffffu, c, leader);
+        const int cxl = cl % nc, cyl = (cl / nc) % nc, czl = cl / (nc * nc);
+        const bool mine = ((todo >> lane) & 1u) && cy == cyl && cz == czl && cx >= cxl && cx < cxl + NBW_RUN;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+        const int cxb = __reduce_max_sync(0xffffffffu, mine ? cx : cxl);
+        const int ncx = min(cxb - cxl + 3, nc);   // candidate cells cxl-1 .. cxb+1 (periodic), each at most once
+        // common origin = centre of the i-cells of the pass, in fixed point
+        const uint32_t ox = md_to_fixed((cxl + 0.5 * (double)(cxb - cxl + 1)) * cell_len, inv_h);
+        const uint32_t oy = md_to_fixed((cyl + 0.5) * cell_len, inv_h), oz = md_to_fixed((czl + 0.5) * cell_len, inv_h);
+        const float xi = (float)(int)(qi.x - ox), yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = (czl + dz + nc) % nc;
+            // lanes 0..23 fetch the slot ranges of the 3 x ncx candidate cells of this z layer
+            int cs_l = 0, ce_l = 0;
+            {
+                const int dyi = lane >> 3, t = lane & 7;
+                if (dyi < 3 && t < ncx) {
+                    const int y = (cyl + dyi - 1 + nc) % nc;
+                    const int x = (cxl - 1 + t + nc) % nc;
+                    const int cc = (z * nc + y) * nc + x;
+                    cs_l = cell_start[cc];
+                    ce_l = cell_end[cc];
+                }
+            }
+            for (int dyi = 0; dyi < 3; ++dyi) {
+                int rs = 0, re = 0;   // pending (merged) slot range
+                for (int t = 0; t <= ncx; ++t) {
+                    int s1 = 0, e1 = 0;
+                    if (t < ncx) {
+                        s1 = __shfl_sync(0xffffffffu, cs_l, dyi * 8 + t);
+                        e1 = __shfl_sync(0xffffffffu, ce_l, dyi * 8 + t);
+                        if (e1 == s1) continue;
+                        if (re > rs && s1 == re) { re = e1; continue; }   // contiguous with the pending range
+                    }
+                    // flush the pending range, 32 candidates at a time
+                    for (int base = rs; base < re; base += 32) {
+                        const int jj = base + lane;
+                        float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
+                        if (jj < re) {
+                            const uint4 qj = q[jj];
+                            cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), 0.0f);
+                        }
+                        __syncwarp();
+                        cand[lane] = cd;
+                        __syncwarp();
+                        float bm = 3.0e38f;
+                        unsigned m = nbw_test_chunk(cand, min(32, re - base), xi, yi, zi, neg_rl2s, neg_bw, bm);
+                        if (mine) bandmin = fminf(bandmin, bm);
+                        else m = 0u;
+                        const long long self = i - base;
+                        if (self >= 0 && self < 32) m &= ~(1u << self);
+                        while (m) {
+                            const int t1 = __ffs(m) - 1;
+                            m &= m - 1;
+                            if ((unsigned)cnt < k_max) row0[md_nbr_off((unsigned)cnt)] = base + t1;
+                            ++cnt;
+                        }
+                    }
+                    rs = s1; re = e1;
+                }
+            }
+        }
+    }
+    if (valid) {
+        if (__builtin_expect(bandmin <= bw, 0)) {   // a candidate sat in the guard band: canonical float64 redo of this particle
+            bool band = false;
+            cnt = nb_particle<true>(i, qi, c, r, q, cap, cell_start, cell_end, nc, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, band);
+        }
+        if (cnt > max_nbr) {
+            sc->overflow_flag = 1;
+            cnt = max_nbr;
+        }
+        nbr_cnt[i] = cnt;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4: neighbour-list forces.  One thread per particle, no atomics on forces; the list is read coalesced,
-// neighbour positions are 16 B (fp32 mode) or 32 B (fp64 mode) gathers that mostly hit L1/L2 because
-// slots are cell-sorted.  Borderline decisions (image tie, |r2 - rc2| within the fp32 guard band) are
-// masked out of the hot loop and redone from the float64 positions, like in the all-pairs kernels.
+// K4: neighbour-list forces.  A group of FG = 8 lanes per particle, 4 particles per warp: the lanes of a group take
+// 8 consecutive list entries per iteration (one coalesced 128-byte list line per warp), gather those neighbours'
+// packed positions (16 B fixed point in fp32 mode, 32 B double4 in fp64 mode), and the group's partial forces are
+// combined with warp shuffles in a fixed order -- no atomics on forces.  Borderline in/out-of-cutoff decisions of
+// the fp32 kernel (|r2 - rc2| inside the float guard band) are redone from the float64 positions, so every pair
+// is in or out exactly as in the fp64 kernel.
 // ---------------------------------------------------------------------------------------------------
 struct LjF64 { double c6, sigma2; };   // c6 = 6 lambda eps / m
 struct LjF32 { float c6, sigma2; };    // in fixed-point units (see allpairs.cu)
 
-__global__ void __launch_bounds__(NB_THREADS)
-k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_own, long long cap, const int *__restrict__ nbr,
+__device__ __forceinline__ double md_group_sum(double v) {   // sum over the 8 lanes of a group (fixed xor tree)
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+__global__ void __launch_bounds__(FORCE_THREADS)
+k_nbr_force_f64(const double4 *__restrict__ pos, long long i_lo, long long i_hi, long long cap, const int *__restrict__ nbr,
                 const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, LjF64 P,
                 double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
-    const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, l = lane & (FG - 1);
+    const long long i = (i_lo & ~3LL) + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / FG;
+    const bool valid = i >= i_lo && i < i_hi;
+    const long long ic = valid ? i : i_lo;
+    const double4 pi = pos[ic];
+    const int nn = valid ? nbr_cnt[ic] : 0;
+    int nmax = max(nn, __shfl_xor_sync(0xffffffffu, nn, 8));
+    nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+    const int *__restrict__ row = nbr + md_nbr_row_base(ic, max_nbr) + l;
     double   fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0;
     unsigned cnt = 0;
-    if (i < n_own) {
-        const double4 pi = pos[i];
-        const int nn = nbr_cnt[i];
-        const int *__restrict__ row0 = nbr + md_nbr_index(i, 0, max_nbr);
-#pragma unroll 4
-        for (int k = 0; k < nn; ++k) {
-            const int j = row0[k * 32];
-            const double4 pj = pos[j];
-            const double dx = md_minimg_list(pj.x - pi.x, L, halfL);
-            const double dy = md_minimg_list(pj.y - pi.y, L, halfL);
-            const double dz = md_minimg_list(pj.z - pi.z, L, halfL);
-            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            const bool ok = r2 < rc2;
-            const double inv = ok ? md_rcp(r2) : 0.0;
-            const double t2 = P.sigma2 * inv;
-            const double t6 = t2 * t2 * t2;
-            const double s = (P.c6 * inv) * (t6 * fma(-2.0, t6, 1.0));
-            fx = fma(dx, s, fx);
-            fy = fma(dy, s, fy);
-            fz = fma(dz, s, fz);
-            pe += fma(t6, t6, -t6);
-            cnt += ok ? 1u : 0u;
-        }
+#pragma unroll 2
+    for (int k0 = 0; k0 < nmax; k0 += FG) {
+        const bool have = k0 + l < nn;
+        const int j = have ? row[k0 * 4] : (int)ic;
+        const double4 pj = pos[j];
+        const double dx = md_minimg_list(pj.x - pi.x, L, halfL);
+        const double dy = md_minimg_list(pj.y - pi.y, L, halfL);
+        const double dz = md_minimg_list(pj.z - pi.z, L, halfL);
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        const bool ok = have && r2 < rc2;
+        const double inv = ok ? md_rcp(r2) : 0.0;
+        const double t2 = P.sigma2 * inv;
+        const double t6 = t2 * t2 * t2;
+        const double s = (P.c6 * inv) * (t6 * fma(-2.0, t6, 1.0));
+        fx = fma(dx, s, fx);
+        fy = fma(dy, s, fy);
+        fz = fma(dz, s, fz);
+        pe += fma(t6, t6, -t6);
+        cnt += ok ? 1u : 0u;
+    }
+    fx = md_group_sum(fx);
+    fy = md_group_sum(fy);
+    fz = md_group_sum(fz);
+    if (valid && l == 0) {
         acc[i] = fx;
         acc[cap + i] = fy;
         acc[2 * cap + i] = fz;
@@ -493,83 +645,100 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_
     }
 }
 
-__global__ void __launch_bounds__(NB_THREADS)
-k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long i_begin, long long n_own, long long cap,
+// one list entry in fp32 (fixed-point separations); MASKED: the entry may be absent (tail of a row)
+template <bool MASKED>
+__device__ __forceinline__ void lj32_entry(const uint4 qi, const uint4 qj, bool have, float rc2s, float neg_bw, LjF32 P,
+                                           float &fx, float &fy, float &fz, float &s6, float &s12, unsigned &cnt,
+                                           float &bandmin) {
+    const float dx = (float)(int)(qj.x - qi.x), dy = (float)(int)(qj.y - qi.y), dz = (float)(int)(qj.z - qi.z);
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float d = r2 - rc2s;
+    bool ok = d < neg_bw;
+    if (MASKED) ok = ok && have;
+    bandmin = fminf(bandmin, fabsf(d));
+    const float inv = ok ? md_rcpf(r2) : 0.0f;
+    const float t2 = P.sigma2 * inv;
+    const float t6 = t2 * t2 * t2;
+    const float u = t6 * inv;
+    const float s = u * fmaf(-2.0f * P.c6, t6, P.c6);   // c6/r^2 * t6 * (1 - 2 t6)
+    fx = fmaf(dx, s, fx);
+    fy = fmaf(dy, s, fy);
+    fz = fmaf(dz, s, fz);
+    s6 += t6;
+    s12 = fmaf(t6, t6, s12);
+    cnt += ok ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(FORCE_THREADS)
+k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long i_lo, long long i_hi, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
                 double rc2, float rc2s, double inv_h, LjF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
                 StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
-    const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    double   Fx = 0.0, Fy = 0.0, Fz = 0.0, PE = 0.0;
+    const int lane = threadIdx.x & 31, l = lane & (FG - 1);
+    const long long i = (i_lo & ~3LL) + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / FG;
+    const bool valid = i >= i_lo && i < i_hi;
+    const long long ic = valid ? i : i_lo;
+    const uint4 qi = pos[ic];
+    const int nn = valid ? nbr_cnt[ic] : 0;
+    int nmax = max(nn, __shfl_xor_sync(0xffffffffu, nn, 8));
+    nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+    int nmin = min(nn, __shfl_xor_sync(0xffffffffu, nn, 8));
+    nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, 16));
+    const int nfull = nmin & ~(FG - 1);   // every group of the warp has at least this many entries
+    const int *__restrict__ row = nbr + md_nbr_row_base(ic, max_nbr) + l;
+    // guard band of the float cutoff decision: the float r^2 is off by < 1e-6 relative (I2F rounding of the exact
+    // integer separations + 3 fma roundings), anything within 2e-6 is re-decided in float64
+    const float bw = rc2s * 2e-6f, neg_bw = -bw;
+    float    fx = 0.f, fy = 0.f, fz = 0.f, s6 = 0.f, s12 = 0.f, bandmin = 3.0e38f;
     unsigned cnt = 0;
-    if (i < n_own) {
-        const uint4 qi = pos[i];
-        const int   nn = nbr_cnt[i];
-        const int *__restrict__ row0 = nbr + md_nbr_index(i, 0, max_nbr);
-        const float cut_lo = rc2s * (1.0f - 2e-6f), cut_hi = rc2s * (1.0f + 2e-6f);
-        // Groups of NBG entries: all index loads, then all position gathers, then the arithmetic -- NBG independent
-        // gathers in flight per thread (the kernel is bound by the latency of these L1/L2 gathers, not by issue).
-        // Rows are padded by the build kernel to a multiple of NBG with the particle's own slot (masked by j != i).
-        for (int k0 = 0; k0 < nn; k0 += NBG) {
-            int   j[NBG];
-            uint4 qj[NBG];
-#pragma unroll
-            for (int u = 0; u < NBG; ++u) j[u] = row0[(k0 + u) * 32];
-#pragma unroll
-            for (int u = 0; u < NBG; ++u) qj[u] = pos[j[u]];
-            float    fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
-            unsigned flagged = 0u;
-#pragma unroll
-            for (int u = 0; u < NBG; ++u) {
-                const float dx = (float)(int)(qj[u].x - qi.x), dy = (float)(int)(qj[u].y - qi.y), dz = (float)(int)(qj[u].z - qi.z);
-                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                // an in-cutoff pair can only sit at the image tie if rc ~ L/2; rc + skin <= L/3 here, so only the
-                // cutoff band needs the exact redo
-                const bool inside = r2 < cut_lo, maybe = r2 < cut_hi;
-                flagged |= ((maybe && !inside) ? 1u : 0u) << u;
-                const bool  ok = inside && (j[u] != (int)i);
-                const float inv = ok ? md_rcpf(r2) : 0.0f;
+    int k0 = 0;
+#pragma unroll 2
+    for (; k0 < nfull; k0 += FG) {
+        const int j = row[k0 * 4];
+        lj32_entry<false>(qi, pos[j], true, rc2s, neg_bw, P, fx, fy, fz, s6, s12, cnt, bandmin);
+    }
+    for (; k0 < nmax; k0 += FG) {
+        const bool have = k0 + l < nn;
+        const int j = have ? row[k0 * 4] : (int)ic;
+        lj32_entry<true>(qi, pos[j], have, rc2s, neg_bw, P, fx, fy, fz, s6, s12, cnt, bandmin);
+    }
+    if (__builtin_expect(bandmin <= bw, 0)) {
+        // rare: one of this lane's pairs sits in the guard band.  Redo the lane's entries with the float64 in/out
+        // decision (the separations are then taken from the float64 positions as well).
+        fx = fy = fz = s6 = s12 = 0.f;
+        cnt = 0;
+        const double xi = r64[ic], yi = r64[cap + ic], zi = r64[2 * cap + ic];
+        for (int k = l; k < nn; k += FG) {
+            const int jj = row[(k - l) * 4];
+            const double ex = md_minimg_list(r64[jj] - xi, L, halfL);
+            const double ey = md_minimg_list(r64[cap + jj] - yi, L, halfL);
+            const double ez = md_minimg_list(r64[2 * cap + jj] - zi, L, halfL);
+            const double r2d = fma(ez, ez, fma(ey, ey, ex * ex));
+            if (r2d < rc2) {
+                const float dx = (float)(ex * inv_h), dy = (float)(ey * inv_h), dz = (float)(ez * inv_h);
+                const float inv = md_rcpf((float)(r2d * inv_h * inv_h));
                 const float t2 = P.sigma2 * inv;
                 const float t6 = t2 * t2 * t2;
-                const float s = (P.c6 * inv) * (t6 * fmaf(-2.0f, t6, 1.0f));
+                const float s = (t6 * inv) * fmaf(-2.0f * P.c6, t6, P.c6);
                 fx = fmaf(dx, s, fx);
                 fy = fmaf(dy, s, fy);
                 fz = fmaf(dz, s, fz);
-                pe += fmaf(t6, t6, -t6);
-                cnt += ok ? 1u : 0u;
+                s6 += t6;
+                s12 = fmaf(t6, t6, s12);
+                cnt += 1u;
             }
-            while (flagged) {  // rare: decide and evaluate from the float64 positions
-                const int u = __ffs(flagged) - 1;
-                flagged &= flagged - 1;
-                const int jj = row0[(k0 + u) * 32];
-                if (jj == (int)i) continue;
-                const double ex = md_minimg_list(r64[jj] - r64[i], L, halfL);
-                const double ey = md_minimg_list(r64[cap + jj] - r64[cap + i], L, halfL);
-                const double ez = md_minimg_list(r64[2 * cap + jj] - r64[2 * cap + i], L, halfL);
-                const double r2d = fma(ez, ez, fma(ey, ey, ex * ex));
-                if (r2d < rc2) {
-                    const float dx = (float)(ex * inv_h), dy = (float)(ey * inv_h), dz = (float)(ez * inv_h);
-                    const float r2 = (float)(r2d * inv_h * inv_h);
-                    const float inv = md_rcpf(r2);
-                    const float t2 = P.sigma2 * inv;
-                    const float t6 = t2 * t2 * t2;
-                    const float s = (P.c6 * inv) * (t6 * fmaf(-2.0f, t6, 1.0f));
-                    fx = fmaf(dx, s, fx);
-                    fy = fmaf(dy, s, fy);
-                    fz = fmaf(dz, s, fz);
-                    pe += fmaf(t6, t6, -t6);
-                    cnt += 1u;
-                }
-            }
-            Fx += (double)fx; Fy += (double)fy; Fz += (double)fz; PE += (double)pe;
         }
+    }
+    const double Fx = md_group_sum((double)fx), Fy = md_group_sum((double)fy), Fz = md_group_sum((double)fz);
+    if (valid && l == 0) {
         acc[i] = Fx;
         acc[cap + i] = Fy;
         acc[2 * cap + i] = Fz;
     }
-    const double   bpe = md_block_sum(PE, red);
+    const double   bpe = md_block_sum((double)s12 - (double)s6, red);
     const unsigned bc = md_block_sum(cnt, redu);
     if (threadIdx.x == 0) {
         pe_part[blockIdx.x] = bpe;
@@ -857,6 +1026,8 @@ static int bits_for(unsigned long long maxval) {
 }
 static inline double fixed_inv_h(const mdsea_ctx *c) { return 4294967296.0 / c->box.L; }
 static inline int g256(long long n) { return md_div_up(n > 0 ? n : 1, 256); }
+// blocks of a list force launch over the owned slots [i0, i1): the launch starts at the quad boundary below i0
+static inline int force_grid(long long i0, long long i1) { return md_div_up(i1 - (i0 & ~3LL), FORCE_THREADS / FG); }
 
 static int scan_exclusive(mdsea_ctx *c, const int *in, int *out, long long n) {
     CellState *s = c->cells;
@@ -905,7 +1076,7 @@ int md_cells_setup(mdsea_ctx *c) {
         const double expect = 4.0 / 3.0 * 3.14159265358979 * s->rlist * s->rlist * s->rlist * rho;
         s->max_nbr = ((int)(expect * 1.6) + 32 + 7) / 8 * 8;
     }
-    s->max_nbr = (s->max_nbr + NBG - 1) / NBG * NBG;
+    s->max_nbr = (s->max_nbr + FG - 1) / FG * FG;
     s->id_bits = bits_for((unsigned long long)(N - 1));
     s->cell_bits = bits_for((unsigned long long)(s->ncell - 1));
     s->sort_blocks = md_div_up(s->cap, SORT_CHUNK);
@@ -943,7 +1114,7 @@ int md_cells_setup(mdsea_ctx *c) {
     c->n_ke_part = md_div_up(s->cap, 256);
     MD_CUDA(c, cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
     MD_CUDA(c, cudaMemset(c->d_ke_part, 0, sizeof(double) * c->n_ke_part));
-    c->n_pe_part = md_div_up(s->cap, NB_THREADS);
+    c->n_pe_part = force_grid(0, s->cap) + 2;
     MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
     MD_CUDA(c, cudaMemset(c->d_pe_part, 0, sizeof(double) * c->n_pe_part));
     if (W > 1) {
@@ -1129,6 +1300,7 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
 
 #include <chrono>
 static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
+static bool g_build_thread = getenv("MDSEA_NBR_BUILD") && !strcmp(getenv("MDSEA_NBR_BUILD"), "thread");  // A/B switch
 struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronises the stream; off by default)
     mdsea_ctx *c;
     std::chrono::steady_clock::time_point t0;
@@ -1200,9 +1372,16 @@ static int rebuild(mdsea_ctx *c) {
     {
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
-        k_nbr_build<<<md_div_up(c->n > 0 ? c->n : 1, NB_THREADS), NB_THREADS, 0, c->stream>>>(
-            c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2,
-            (float)(rl2s * (1.0 - 1e-5)), (float)(rl2s * (1.0 + 1e-5)), s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
+        const float lo = (float)(rl2s * (1.0 - 1e-5)), hi = (float)(rl2s * (1.0 + 1e-5));
+        const long long no = c->n > 0 ? c->n : 1;
+        if (g_build_thread)
+            k_nbr_build<<<md_div_up(no, NB_THREADS), NB_THREADS, 0, c->stream>>>(
+                c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
+                s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
+        else
+            k_nbr_build_warp<<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(
+                c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih,
+                s->rl2, (float)rl2s, (float)(rl2s * 1e-5), lo, hi, s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
     }
     launches += 4;
     pt.lap("nbr build");
@@ -1219,12 +1398,12 @@ static int rebuild(mdsea_ctx *c) {
 static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded) {
     CellState *s = c->cells;
     if (i1 <= i0) return MDSEA_OK;
-    const int grid = md_div_up(i1 - i0, NB_THREADS);
+    const int grid = force_grid(i0, i1);
     if (c->p.precision == MDSEA_FP64) {
         LjF64 P;
         P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
         P.sigma2 = c->pot.sigma2;
-        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
+        k_nbr_force_f64<<<grid, FORCE_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
                                                             c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off, c->d_sc,
                                                             guarded);
     } else {
@@ -1232,7 +1411,7 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
         LjF32 P;
         P.c6 = (float)(6.0 * c->pot.lam_eps * c->pot.inv_mass * inv_h);
         P.sigma2 = (float)(c->pot.sigma2 * inv_h * inv_h);
-        k_nbr_force_f32<<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, i0, i1, s->cap, s->nbr, s->nbr_cnt,
+        k_nbr_force_f32<<<grid, FORCE_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, i0, i1, s->cap, s->nbr, s->nbr_cnt,
                                                             s->max_nbr, c->box.L, c->box.halfL, s->rc2,
                                                             (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
                                                             c->d_pe_part + pe_off, c->d_sc, guarded);
@@ -1246,7 +1425,7 @@ static int cutoff_force(mdsea_ctx *c, int guarded) {
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
     md_prof_begin(c);
-    c->n_pe_part = md_div_up(c->n > 0 ? c->n : 1, NB_THREADS);
+    c->n_pe_part = force_grid(0, c->n > 0 ? c->n : 1);
     MD_TRY(launch_force(c, 0, c->n, 0, guarded));
     md_prof_end(c, &c->stats.ms_force);
     c->stats.force_evals += 1;
@@ -1314,8 +1493,8 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
         MD_TRY(halo_exchange(c, c->comm_stream));
         MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->comm_stream));
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
-        const int gi = md_div_up(s->n_int > 0 ? s->n_int : 1, NB_THREADS);
-        c->n_pe_part = gi + md_div_up(c->n - s->n_int > 0 ? c->n - s->n_int : 1, NB_THREADS);
+        const int gi = force_grid(0, s->n_int > 0 ? s->n_int : 1);
+        c->n_pe_part = gi + force_grid(s->n_int, c->n > s->n_int ? c->n : s->n_int + 1);
         MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
         MD_TRY(launch_force(c, 0, s->n_int, 0, 1));                       // guarded by the LOCAL flag only (the global one
                                                                           // is not known yet): redone if any rank fired
@@ -1466,12 +1645,13 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
     for (long long g = 0; g < c->n_global; ++g) offsets[g + 1] = offsets[g] + count_by_id[g];
     *n_entries = offsets[c->n_global];
     if (!idx) return MDSEA_OK;
-    const size_t tiles = (size_t)((n + 31) / 32);
-    std::vector<int> nbr(tiles * (size_t)s->max_nbr * 32);
+    const size_t quads = (size_t)((n + 3) / 4);
+    std::vector<int> nbr(quads * (size_t)s->max_nbr * 4);
     MD_CUDA(c, cudaMemcpy(nbr.data(), s->nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost));
     for (long long k = 0; k < n; ++k) {
         int32_t *row = idx + offsets[id[k]];
-        for (int m = 0; m < cnt[k]; ++m) row[m] = id[nbr[((size_t)(k >> 5) * s->max_nbr + m) * 32 + (k & 31)]];
+        const size_t base = md_nbr_row_base(k, s->max_nbr);
+        for (int m = 0; m < cnt[k]; ++m) row[m] = id[nbr[base + md_nbr_off((unsigned)m)]];
         std::sort(row, row + cnt[k]);
     }
     return MDSEA_OK;
