@@ -27,7 +27,7 @@
 #define SORT_ITEMS 8
 #define SORT_CHUNK (SORT_THREADS * SORT_ITEMS)
 #define NB_THREADS 128       // thread-per-particle list build
-#define FORCE_THREADS 256    // list force kernels: FG lanes per particle -> FORCE_THREADS / FG particles per block
+#define NBG 8                // list entries per gather group of the force kernels
 
 // Spatial domain decomposition on the canonical cell grid: rank (bx, by, bz) of a px*py*pz process grid owns the
 // cells with bnd[d][b_d] <= c_d < bnd[d][b_d + 1]; its halo is the one-cell layer around that block (periodic).
@@ -105,6 +105,7 @@ struct CellState {
     int    *id = nullptr, *id_alt = nullptr;
     double *rb = nullptr;                 // positions at the last build, slot order
     void   *pos4 = nullptr;               // double4[cap] (fp64) or uint4[cap] (fp32)
+    cudaTextureObject_t tex_pos = 0;      // experiment (MDSEA_FORCE_TEX=1): gather the fp32 positions through the texture path
     unsigned long long *key = nullptr, *key_alt = nullptr;
     int    *val = nullptr, *val_alt = nullptr;
     int    *hist = nullptr, *hist_tot = nullptr;
@@ -330,18 +331,16 @@ __global__ void k_pack_positions(const double *__restrict__ r, long long n, long
     else ((double4 *)pos4)[i] = make_double4(x, y, z, 0.0);
 }
 
-// Neighbour-list layout: sliced ELLPACK for FG-lane groups.  The force kernels give every particle a group of
-// FG = 8 lanes that walk its row 8 entries at a time, so a warp serves the 4 consecutive particles of one "quad".
-// Quad t = i >> 2 owns max_nbr / 8 chunks of 32 ints; chunk m holds entries 8m .. 8m+7 of its four particles,
-// particle p = i & 3 at ints [8p, 8p+8): entry (i, k) sits at ((i>>2) * max_nbr + (k & ~7)) * 4 + (i&3) * 8 + (k&7).
-// One warp-wide load of a chunk is a single coalesced 128-byte line, and the 8 lanes of a group then gather 8
-// CONSECUTIVE list entries -- neighbours that the build found next to each other in slot order -- so the
-// position gather of a warp touches a handful of lines instead of one line per lane.
-#define FG 8
+// Neighbour-list layout: sliced ELLPACK.  Particles are grouped in tiles of 32 consecutive slots (= one warp of
+// the force kernel); tile t owns max_nbr rows of 32 ints, entry (k, lane) at t*max_nbr*32 + k*32 + lane.  The
+// force kernel reads one 128-byte row per k (coalesced); the build kernels' stores of one warp all land in the
+// same ~15 KB tile, so partially written sectors merge in L2 instead of being evicted half empty.
+// (A quad-sliced layout with 8 lanes per particle was measured in r01: 1.6x fewer L1 wavefronts per gather, but
+// 1.7x more instructions per pair -- 208 us against 136 us for this one; see profiles/README.md.)
 __host__ __device__ __forceinline__ size_t md_nbr_row_base(long long i, int max_nbr) {
-    return ((size_t)(i >> 2) * (size_t)max_nbr) * 4u + (size_t)(i & 3) * 8u;
+    return (size_t)(i >> 5) * (size_t)max_nbr * 32u + (size_t)(i & 31);
 }
-__host__ __device__ __forceinline__ unsigned md_nbr_off(unsigned k) { return ((k >> 3) << 5) + (k & 7u); }
+__host__ __device__ __forceinline__ unsigned md_nbr_off(unsigned k) { return k * 32u; }
 
 // ---------------------------------------------------------------------------------------------------
 // K3: Verlet neighbour list.
@@ -447,11 +446,15 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
         cnt = max_nbr;
     }
     nbr_cnt[i] = cnt;
+    for (int k = cnt; k < ((cnt + NBG - 1) / NBG) * NBG; ++k) row0[k * 32] = (int)i;  // padding, masked by j != i
 }
 
 // ---- warp-cooperative build ------------------------------------------------------------------------
 #define NBW_WARPS 4      // warps (= tiles of 32 slots) per block
 #define NBW_RUN   6      // at most this many x-consecutive cells of i-particles per pass (bounds the float error)
+// Offsets from the common origin are plain floats (no wrap), so they only reproduce the minimum image while the
+// candidate window stays inside half a period: (run + 2) cells < nc in x, 3 cells < nc in y and z.  The host
+// therefore passes run_max = min(NBW_RUN, nc - 3) and uses the thread-per-particle kernel when nc == 3.
 
 // test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle
 __device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
@@ -476,7 +479,8 @@ __global__ void __launch_bounds__(NBW_WARPS * 32)
 k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
                  double L, double halfL, double cell_len, double inv_h, double rl2, float rl2s, float bw, float rl2s_lo,
-                 float rl2s_hi, int max_nbr, int *__restrict__ nbr, int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
+                 float rl2s_hi, int max_nbr, int run_max, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
+                 StepScalars *__restrict__ sc) {
     __shared__ float4 s_cand[NBW_WARPS][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
@@ -489,7 +493,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
     float4 *cand = s_cand[w];
     int *row0 = nbr + md_nbr_row_base(il, max_nbr);
-    const unsigned k_max = (unsigned)max_nbr;
+    int *wp = row0;   // write cursor inside the row
     const float neg_rl2s = -rl2s, neg_bw = -bw;
     float bandmin = 3.0e38f;
     int cnt = 0;
@@ -499,10 +503,10 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
         const int leader = __ffs(todo) - 1;
         const int cl = __shfl_sync(0xffffffffu, c, leader);
         const int cxl = cl % nc, cyl = (cl / nc) % nc, czl = cl / (nc * nc);
-        const bool mine = ((todo >> lane) & 1u) && cy == cyl && cz == czl && cx >= cxl && cx < cxl + NBW_RUN;
+        const bool mine = ((todo >> lane) & 1u) && cy == cyl && cz == czl && cx >= cxl && cx < cxl + run_max;
         todo &= ~__ballot_sync(0xffffffffu, mine);
         const int cxb = __reduce_max_sync(0xffffffffu, mine ? cx : cxl);
-        const int ncx = min(cxb - cxl + 3, nc);   // candidate cells cxl-1 .. cxb+1 (periodic), each at most once
+        const int ncx = cxb - cxl + 3;   // candidate cells cxl-1 .. cxb+1 (periodic); run_max <= nc - 3 keeps them distinct
         // common origin = centre of the i-cells of the pass, in fixed point
         const uint32_t ox = md_to_fixed((cxl + 0.5 * (double)(cxb - cxl + 1)) * cell_len, inv_h);
         const uint32_t oy = md_to_fixed((cyl + 0.5) * cell_len, inv_h), oz = md_to_fixed((czl + 0.5) * cell_len, inv_h);
@@ -548,11 +552,16 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
+                        if (cnt + __popc(m) > max_nbr) {   // row full: keep counting, the overflow is reported below
+                            cnt += __popc(m);
+                            m = 0u;
+                        }
                         while (m) {
                             const int t1 = __ffs(m) - 1;
                             m &= m - 1;
-                            if ((unsigned)cnt < k_max) row0[md_nbr_off((unsigned)cnt)] = base + t1;
+                            *wp = base + t1;
                             ++cnt;
+                            wp += 32;   // next entry of the tile-sliced row (md_nbr_off)
                         }
                     }
                     rs = s1; re = e1;
@@ -570,69 +579,52 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
             cnt = max_nbr;
         }
         nbr_cnt[i] = cnt;
+        for (int k = cnt; k < ((cnt + NBG - 1) / NBG) * NBG; ++k) row0[k * 32] = (int)i;  // padding, masked by j != i
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4: neighbour-list forces.  A group of FG = 8 lanes per particle, 4 particles per warp: the lanes of a group take
-// 8 consecutive list entries per iteration (one coalesced 128-byte list line per warp), gather those neighbours'
-// packed positions (16 B fixed point in fp32 mode, 32 B double4 in fp64 mode), and the group's partial forces are
-// combined with warp shuffles in a fixed order -- no atomics on forces.  Borderline in/out-of-cutoff decisions of
-// the fp32 kernel (|r2 - rc2| inside the float guard band) are redone from the float64 positions, so every pair
-// is in or out exactly as in the fp64 kernel.
+// K4: neighbour-list forces.  One thread per particle, no atomics on forces; the list is read coalesced,
+// neighbour positions are 16 B (fp32 mode) or 32 B (fp64 mode) gathers that mostly hit L1/L2 because
+// slots are cell-sorted.  Borderline decisions (image tie, |r2 - rc2| within the fp32 guard band) are
+// masked out of the hot loop and redone from the float64 positions, like in the all-pairs kernels.
 // ---------------------------------------------------------------------------------------------------
 struct LjF64 { double c6, sigma2; };   // c6 = 6 lambda eps / m
 struct LjF32 { float c6, sigma2; };    // in fixed-point units (see allpairs.cu)
 
-__device__ __forceinline__ double md_group_sum(double v) {   // sum over the 8 lanes of a group (fixed xor tree)
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    return v;
-}
-
-__global__ void __launch_bounds__(FORCE_THREADS)
-k_nbr_force_f64(const double4 *__restrict__ pos, long long i_lo, long long i_hi, long long cap, const int *__restrict__ nbr,
+__global__ void __launch_bounds__(NB_THREADS)
+k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_own, long long cap, const int *__restrict__ nbr,
                 const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, LjF64 P,
                 double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
-    const int lane = threadIdx.x & 31, l = lane & (FG - 1);
-    const long long i = (i_lo & ~3LL) + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / FG;
-    const bool valid = i >= i_lo && i < i_hi;
-    const long long ic = valid ? i : i_lo;
-    const double4 pi = pos[ic];
-    const int nn = valid ? nbr_cnt[ic] : 0;
-    int nmax = max(nn, __shfl_xor_sync(0xffffffffu, nn, 8));
-    nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-    const int *__restrict__ row = nbr + md_nbr_row_base(ic, max_nbr) + l;
+    const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0;
     unsigned cnt = 0;
-#pragma unroll 2
-    for (int k0 = 0; k0 < nmax; k0 += FG) {
-        const bool have = k0 + l < nn;
-        const int j = have ? row[k0 * 4] : (int)ic;
-        const double4 pj = pos[j];
-        const double dx = md_minimg_list(pj.x - pi.x, L, halfL);
-        const double dy = md_minimg_list(pj.y - pi.y, L, halfL);
-        const double dz = md_minimg_list(pj.z - pi.z, L, halfL);
-        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        const bool ok = have && r2 < rc2;
-        const double inv = ok ? md_rcp(r2) : 0.0;
-        const double t2 = P.sigma2 * inv;
-        const double t6 = t2 * t2 * t2;
-        const double s = (P.c6 * inv) * (t6 * fma(-2.0, t6, 1.0));
-        fx = fma(dx, s, fx);
-        fy = fma(dy, s, fy);
-        fz = fma(dz, s, fz);
-        pe += fma(t6, t6, -t6);
-        cnt += ok ? 1u : 0u;
-    }
-    fx = md_group_sum(fx);
-    fy = md_group_sum(fy);
-    fz = md_group_sum(fz);
-    if (valid && l == 0) {
+    if (i < n_own) {
+        const double4 pi = pos[i];
+        const int nn = nbr_cnt[i];
+        const int *__restrict__ row0 = nbr + md_nbr_row_base(i, max_nbr);
+#pragma unroll 4
+        for (int k = 0; k < nn; ++k) {
+            const int j = row0[k * 32];
+            const double4 pj = pos[j];
+            const double dx = md_minimg_list(pj.x - pi.x, L, halfL);
+            const double dy = md_minimg_list(pj.y - pi.y, L, halfL);
+            const double dz = md_minimg_list(pj.z - pi.z, L, halfL);
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const bool ok = r2 < rc2;
+            const double inv = ok ? md_rcp(r2) : 0.0;
+            const double t2 = P.sigma2 * inv;
+            const double t6 = t2 * t2 * t2;
+            const double s = (P.c6 * inv) * (t6 * fma(-2.0, t6, 1.0));
+            fx = fma(dx, s, fx);
+            fy = fma(dy, s, fy);
+            fz = fma(dz, s, fz);
+            pe += fma(t6, t6, -t6);
+            cnt += ok ? 1u : 0u;
+        }
         acc[i] = fx;
         acc[cap + i] = fy;
         acc[2 * cap + i] = fz;
@@ -645,100 +637,84 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long i_lo, long long i_hi,
     }
 }
 
-// one list entry in fp32 (fixed-point separations); MASKED: the entry may be absent (tail of a row)
-template <bool MASKED>
-__device__ __forceinline__ void lj32_entry(const uint4 qi, const uint4 qj, bool have, float rc2s, float neg_bw, LjF32 P,
-                                           float &fx, float &fy, float &fz, float &s6, float &s12, unsigned &cnt,
-                                           float &bandmin) {
-    const float dx = (float)(int)(qj.x - qi.x), dy = (float)(int)(qj.y - qi.y), dz = (float)(int)(qj.z - qi.z);
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const float d = r2 - rc2s;
-    bool ok = d < neg_bw;
-    if (MASKED) ok = ok && have;
-    bandmin = fminf(bandmin, fabsf(d));
-    const float inv = ok ? md_rcpf(r2) : 0.0f;
-    const float t2 = P.sigma2 * inv;
-    const float t6 = t2 * t2 * t2;
-    const float u = t6 * inv;
-    const float s = u * fmaf(-2.0f * P.c6, t6, P.c6);   // c6/r^2 * t6 * (1 - 2 t6)
-    fx = fmaf(dx, s, fx);
-    fy = fmaf(dy, s, fy);
-    fz = fmaf(dz, s, fz);
-    s6 += t6;
-    s12 = fmaf(t6, t6, s12);
-    cnt += ok ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(FORCE_THREADS)
-k_nbr_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, long long i_lo, long long i_hi, long long cap,
+template <bool TEX>
+__global__ void __launch_bounds__(NB_THREADS)
+k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const double *__restrict__ r64, long long i_begin, long long n_own, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
                 double rc2, float rc2s, double inv_h, LjF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
                 StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
-    const int lane = threadIdx.x & 31, l = lane & (FG - 1);
-    const long long i = (i_lo & ~3LL) + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / FG;
-    const bool valid = i >= i_lo && i < i_hi;
-    const long long ic = valid ? i : i_lo;
-    const uint4 qi = pos[ic];
-    const int nn = valid ? nbr_cnt[ic] : 0;
-    int nmax = max(nn, __shfl_xor_sync(0xffffffffu, nn, 8));
-    nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-    int nmin = min(nn, __shfl_xor_sync(0xffffffffu, nn, 8));
-    nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, 16));
-    const int nfull = nmin & ~(FG - 1);   // every group of the warp has at least this many entries
-    const int *__restrict__ row = nbr + md_nbr_row_base(ic, max_nbr) + l;
-    // guard band of the float cutoff decision: the float r^2 is off by < 1e-6 relative (I2F rounding of the exact
-    // integer separations + 3 fma roundings), anything within 2e-6 is re-decided in float64
-    const float bw = rc2s * 2e-6f, neg_bw = -bw;
-    float    fx = 0.f, fy = 0.f, fz = 0.f, s6 = 0.f, s12 = 0.f, bandmin = 3.0e38f;
+    const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double   Fx = 0.0, Fy = 0.0, Fz = 0.0, PE = 0.0;
     unsigned cnt = 0;
-    int k0 = 0;
-#pragma unroll 2
-    for (; k0 < nfull; k0 += FG) {
-        const int j = row[k0 * 4];
-        lj32_entry<false>(qi, pos[j], true, rc2s, neg_bw, P, fx, fy, fz, s6, s12, cnt, bandmin);
-    }
-    for (; k0 < nmax; k0 += FG) {
-        const bool have = k0 + l < nn;
-        const int j = have ? row[k0 * 4] : (int)ic;
-        lj32_entry<true>(qi, pos[j], have, rc2s, neg_bw, P, fx, fy, fz, s6, s12, cnt, bandmin);
-    }
-    if (__builtin_expect(bandmin <= bw, 0)) {
-        // rare: one of this lane's pairs sits in the guard band.  Redo the lane's entries with the float64 in/out
-        // decision (the separations are then taken from the float64 positions as well).
-        fx = fy = fz = s6 = s12 = 0.f;
-        cnt = 0;
-        const double xi = r64[ic], yi = r64[cap + ic], zi = r64[2 * cap + ic];
-        for (int k = l; k < nn; k += FG) {
-            const int jj = row[(k - l) * 4];
-            const double ex = md_minimg_list(r64[jj] - xi, L, halfL);
-            const double ey = md_minimg_list(r64[cap + jj] - yi, L, halfL);
-            const double ez = md_minimg_list(r64[2 * cap + jj] - zi, L, halfL);
-            const double r2d = fma(ez, ez, fma(ey, ey, ex * ex));
-            if (r2d < rc2) {
-                const float dx = (float)(ex * inv_h), dy = (float)(ey * inv_h), dz = (float)(ez * inv_h);
-                const float inv = md_rcpf((float)(r2d * inv_h * inv_h));
+    if (i < n_own) {
+        const uint4 qi = pos[i];
+        const int   nn = nbr_cnt[i];
+        const int *__restrict__ row0 = nbr + md_nbr_row_base(i, max_nbr);
+        const float cut_lo = rc2s * (1.0f - 2e-6f), cut_hi = rc2s * (1.0f + 2e-6f);
+        // Groups of NBG entries: all index loads, then all position gathers, then the arithmetic -- NBG independent
+        // gathers in flight per thread (the kernel is bound by the latency of these L1/L2 gathers, not by issue).
+        // Rows are padded by the build kernel to a multiple of NBG with the particle's own slot (masked by j != i).
+        for (int k0 = 0; k0 < nn; k0 += NBG) {
+            int   j[NBG];
+            uint4 qj[NBG];
+#pragma unroll
+            for (int u = 0; u < NBG; ++u) j[u] = row0[(k0 + u) * 32];
+#pragma unroll
+            for (int u = 0; u < NBG; ++u) qj[u] = TEX ? tex1Dfetch<uint4>(tex, j[u]) : pos[j[u]];
+            float    fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+            unsigned flagged = 0u;
+#pragma unroll
+            for (int u = 0; u < NBG; ++u) {
+                const float dx = (float)(int)(qj[u].x - qi.x), dy = (float)(int)(qj[u].y - qi.y), dz = (float)(int)(qj[u].z - qi.z);
+                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                // an in-cutoff pair can only sit at the image tie if rc ~ L/2; rc + skin <= L/3 here, so only the
+                // cutoff band needs the exact redo
+                const bool inside = r2 < cut_lo, maybe = r2 < cut_hi;
+                flagged |= ((maybe && !inside) ? 1u : 0u) << u;
+                const bool  ok = inside && (j[u] != (int)i);
+                const float inv = ok ? md_rcpf(r2) : 0.0f;
                 const float t2 = P.sigma2 * inv;
                 const float t6 = t2 * t2 * t2;
-                const float s = (t6 * inv) * fmaf(-2.0f * P.c6, t6, P.c6);
+                const float s = (P.c6 * inv) * (t6 * fmaf(-2.0f, t6, 1.0f));
                 fx = fmaf(dx, s, fx);
                 fy = fmaf(dy, s, fy);
                 fz = fmaf(dz, s, fz);
-                s6 += t6;
-                s12 = fmaf(t6, t6, s12);
-                cnt += 1u;
+                pe += fmaf(t6, t6, -t6);
+                cnt += ok ? 1u : 0u;
             }
+            while (flagged) {  // rare: decide and evaluate from the float64 positions
+                const int u = __ffs(flagged) - 1;
+                flagged &= flagged - 1;
+                const int jj = row0[(k0 + u) * 32];
+                if (jj == (int)i) continue;
+                const double ex = md_minimg_list(r64[jj] - r64[i], L, halfL);
+                const double ey = md_minimg_list(r64[cap + jj] - r64[cap + i], L, halfL);
+                const double ez = md_minimg_list(r64[2 * cap + jj] - r64[2 * cap + i], L, halfL);
+                const double r2d = fma(ez, ez, fma(ey, ey, ex * ex));
+                if (r2d < rc2) {
+                    const float dx = (float)(ex * inv_h), dy = (float)(ey * inv_h), dz = (float)(ez * inv_h);
+                    const float r2 = (float)(r2d * inv_h * inv_h);
+                    const float inv = md_rcpf(r2);
+                    const float t2 = P.sigma2 * inv;
+                    const float t6 = t2 * t2 * t2;
+                    const float s = (P.c6 * inv) * (t6 * fmaf(-2.0f, t6, 1.0f));
+                    fx = fmaf(dx, s, fx);
+                    fy = fmaf(dy, s, fy);
+                    fz = fmaf(dz, s, fz);
+                    pe += fmaf(t6, t6, -t6);
+                    cnt += 1u;
+                }
+            }
+            Fx += (double)fx; Fy += (double)fy; Fz += (double)fz; PE += (double)pe;
         }
-    }
-    const double Fx = md_group_sum((double)fx), Fy = md_group_sum((double)fy), Fz = md_group_sum((double)fz);
-    if (valid && l == 0) {
         acc[i] = Fx;
         acc[cap + i] = Fy;
         acc[2 * cap + i] = Fz;
     }
-    const double   bpe = md_block_sum((double)s12 - (double)s6, red);
+    const double   bpe = md_block_sum(PE, red);
     const unsigned bc = md_block_sum(cnt, redu);
     if (threadIdx.x == 0) {
         pe_part[blockIdx.x] = bpe;
@@ -1026,8 +1002,8 @@ static int bits_for(unsigned long long maxval) {
 }
 static inline double fixed_inv_h(const mdsea_ctx *c) { return 4294967296.0 / c->box.L; }
 static inline int g256(long long n) { return md_div_up(n > 0 ? n : 1, 256); }
-// blocks of a list force launch over the owned slots [i0, i1): the launch starts at the quad boundary below i0
-static inline int force_grid(long long i0, long long i1) { return md_div_up(i1 - (i0 & ~3LL), FORCE_THREADS / FG); }
+// blocks of a list force launch over the owned slots [i0, i1)
+static inline int force_grid(long long i0, long long i1) { return md_div_up(i1 - i0, NB_THREADS); }
 
 static int scan_exclusive(mdsea_ctx *c, const int *in, int *out, long long n) {
     CellState *s = c->cells;
@@ -1076,7 +1052,7 @@ int md_cells_setup(mdsea_ctx *c) {
         const double expect = 4.0 / 3.0 * 3.14159265358979 * s->rlist * s->rlist * s->rlist * rho;
         s->max_nbr = ((int)(expect * 1.6) + 32 + 7) / 8 * 8;
     }
-    s->max_nbr = (s->max_nbr + FG - 1) / FG * FG;
+    s->max_nbr = (s->max_nbr + NBG - 1) / NBG * NBG;
     s->id_bits = bits_for((unsigned long long)(N - 1));
     s->cell_bits = bits_for((unsigned long long)(s->ncell - 1));
     s->sort_blocks = md_div_up(s->cap, SORT_CHUNK);
@@ -1092,6 +1068,18 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->id_alt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->pos4, (p.precision == MDSEA_FP32 ? sizeof(uint4) : sizeof(double4)) * (size_t)s->cap));
     MD_CUDA(c, cudaMalloc(&s->qfix, sizeof(uint4) * (size_t)s->cap));
+    if (p.precision == MDSEA_FP32 && getenv("MDSEA_FORCE_TEX") && s->cap <= (1LL << 27)) {
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = s->pos4;
+        rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+        rd.res.linear.sizeInBytes = sizeof(uint4) * (size_t)s->cap;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.readMode = cudaReadModeElementType;
+        MD_CUDA(c, cudaCreateTextureObject(&s->tex_pos, &rd, &td, nullptr));
+    }
     MD_CUDA(c, cudaMalloc(&s->key, sizeof(unsigned long long) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->key_alt, sizeof(unsigned long long) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->val, sizeof(int) * s->cap));
@@ -1140,6 +1128,7 @@ void md_cells_free(mdsea_ctx *c) {
     CellState *s = c->cells;
     if (!s) return;
     md_comm_free(c);
+    if (s->tex_pos) cudaDestroyTextureObject(s->tex_pos);
     cudaFree(s->r_alt); cudaFree(s->v_alt); cudaFree(s->rb); cudaFree(s->id); cudaFree(s->id_alt); cudaFree(s->pos4);
     cudaFree(s->key); cudaFree(s->key_alt); cudaFree(s->val); cudaFree(s->val_alt); cudaFree(s->hist); cudaFree(s->hist_tot);
     cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
@@ -1374,14 +1363,14 @@ static int rebuild(mdsea_ctx *c) {
         const double rl2s = s->rl2 * ih * ih;
         const float lo = (float)(rl2s * (1.0 - 1e-5)), hi = (float)(rl2s * (1.0 + 1e-5));
         const long long no = c->n > 0 ? c->n : 1;
-        if (g_build_thread)
+        if (g_build_thread || s->nc < 4)
             k_nbr_build<<<md_div_up(no, NB_THREADS), NB_THREADS, 0, c->stream>>>(
                 c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
                 s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
         else
             k_nbr_build_warp<<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(
                 c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih,
-                s->rl2, (float)rl2s, (float)(rl2s * 1e-5), lo, hi, s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
+                s->rl2, (float)rl2s, (float)(rl2s * 1e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc);
     }
     launches += 4;
     pt.lap("nbr build");
@@ -1403,7 +1392,7 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
         LjF64 P;
         P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
         P.sigma2 = c->pot.sigma2;
-        k_nbr_force_f64<<<grid, FORCE_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
+        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
                                                             c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off, c->d_sc,
                                                             guarded);
     } else {
@@ -1411,10 +1400,16 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
         LjF32 P;
         P.c6 = (float)(6.0 * c->pot.lam_eps * c->pot.inv_mass * inv_h);
         P.sigma2 = (float)(c->pot.sigma2 * inv_h * inv_h);
-        k_nbr_force_f32<<<grid, FORCE_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, c->d_r, i0, i1, s->cap, s->nbr, s->nbr_cnt,
-                                                            s->max_nbr, c->box.L, c->box.halfL, s->rc2,
-                                                            (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
-                                                            c->d_pe_part + pe_off, c->d_sc, guarded);
+        if (s->tex_pos)
+            k_nbr_force_f32<true><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr,
+                                                                     s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,
+                                                                     (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
+                                                                     c->d_pe_part + pe_off, c->d_sc, guarded);
+        else
+            k_nbr_force_f32<false><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, 0, c->d_r, i0, i1, s->cap, s->nbr,
+                                                                      s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,
+                                                                      (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
+                                                                      c->d_pe_part + pe_off, c->d_sc, guarded);
     }
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
@@ -1645,8 +1640,8 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
     for (long long g = 0; g < c->n_global; ++g) offsets[g + 1] = offsets[g] + count_by_id[g];
     *n_entries = offsets[c->n_global];
     if (!idx) return MDSEA_OK;
-    const size_t quads = (size_t)((n + 3) / 4);
-    std::vector<int> nbr(quads * (size_t)s->max_nbr * 4);
+    const size_t tiles = (size_t)((n + 31) / 32);
+    std::vector<int> nbr(tiles * (size_t)s->max_nbr * 32);
     MD_CUDA(c, cudaMemcpy(nbr.data(), s->nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost));
     for (long long k = 0; k < n; ++k) {
         int32_t *row = idx + offsets[id[k]];
