@@ -109,6 +109,10 @@ struct CellState {
     unsigned long long *key = nullptr, *key_alt = nullptr;
     int    *val = nullptr, *val_alt = nullptr;
     int    *hist = nullptr, *hist_tot = nullptr;
+    int    *bkt = nullptr, *arrival = nullptr, *bcount = nullptr, *bstart = nullptr;   // counting-sort binning
+    int    *tmp_id = nullptr, *tmp_src = nullptr, *tmp_bkt = nullptr;
+    long long nbucket = 0;
+    bool    radix_binning = false;
     uint4  *qfix = nullptr;               // 32-bit fixed-point positions, refreshed at every rebuild (list prefilter)
     int     sort_blocks = 0;
     int    *cell = nullptr;               // cell id per slot (sorted)
@@ -153,6 +157,11 @@ __device__ __forceinline__ double md_r2_canonical(double dx, double dy, double d
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// 32-bit fixed point (unit L / 2^32): wraps like the periodic box
+__device__ __forceinline__ uint32_t md_to_fixed(double x, double inv_h) {
+    return (uint32_t)(unsigned long long)__double2ll_rn(x * inv_h);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2a: keys.  key = ghost << 63 | boundary << 62 | cell id << 32 | particle id ; value = current (staging) slot.
 // Slot order: owned interior, owned boundary, ghosts; within each class the canonical (cell id, particle id).
@@ -177,6 +186,78 @@ __global__ void k_cell_keys(const double *__restrict__ r, const int *__restrict_
     }
     key[i] = (ghost << 63) | (bnd << 62) | (c << 32) | (unsigned)id[i];
     val[i] = (int)i;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 (default): binning as ONE counting pass over the cells -- a radix sort whose single digit is the bucket
+// (class, cell) -- followed by a rank-by-id inside each bucket.  Buckets: class 0 = owned interior, 1 = owned
+// boundary, 2 = ghost (single GPU: class 0 only); bucket = class * ncell + cell id.  The arrival order inside a
+// bucket (atomicAdd) is not deterministic, so the final slot of a particle is bucket start + the number of bucket
+// members with a smaller particle id: the result is the canonical stable order by (class, cell id, particle id),
+// identical to what the LSD radix passes below produce (kept as MDSEA_BINNING=radix for A/B).
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_bin_count(const double *__restrict__ r, long long n, long long cap, double L, double cl, int nc, int ncell,
+                            Decomp D, int *__restrict__ bkt, int *__restrict__ arrival, int *__restrict__ bcount) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = md_cell_coord(r[i], L, cl, nc);
+    const int cy = md_cell_coord(r[cap + i], L, cl, nc);
+    const int cz = md_cell_coord(r[2 * cap + i], L, cl, nc);
+    int b = (cz * nc + cy) * nc + cx;
+    if (D.world > 1) {
+        const int cls = dc_owner(D, cx, cy, cz) != D.rank ? 2 : (dc_is_boundary(D, cx, cy, cz) ? 1 : 0);
+        b += cls * ncell;
+    }
+    bkt[i] = b;
+    arrival[i] = atomicAdd(&bcount[b], 1);
+}
+
+__global__ void k_bin_scatter(long long n, const int *__restrict__ bkt, const int *__restrict__ arrival,
+                              const int *__restrict__ bstart, const int *__restrict__ id, int *__restrict__ tmp_id,
+                              int *__restrict__ tmp_src, int *__restrict__ tmp_bkt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = bkt[i];
+    const int u = bstart[b] + arrival[i];
+    tmp_id[u] = id[i];
+    tmp_src[u] = (int)i;
+    tmp_bkt[u] = b;
+}
+
+// rank inside the bucket -> final slot; gather the state into it (+ build positions, ids, cell ids, cell bounds
+// and the packed position copies: everything the rest of the rebuild reads)
+__global__ void __launch_bounds__(256)
+k_bin_place(long long n, long long cap, int ncell, const int *__restrict__ bstart, const int *__restrict__ tmp_id,
+            const int *__restrict__ tmp_src, const int *__restrict__ tmp_bkt, const double *__restrict__ r_in,
+            const double *__restrict__ v_in, double *__restrict__ r_out, double *__restrict__ v_out, double *__restrict__ rb,
+            int *__restrict__ id_out, int *__restrict__ cell, int *__restrict__ cell_start, int *__restrict__ cell_end, int fp32,
+            double inv_h, void *__restrict__ pos4, uint4 *__restrict__ qfix) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int b = tmp_bkt[u], lo = bstart[b], hi = bstart[b + 1];
+    const int my = tmp_id[u];
+    int rank = 0;
+    for (int t = lo; t < hi; ++t) rank += tmp_id[t] < my ? 1 : 0;
+    const int s = lo + rank, o = tmp_src[u];
+    const int cc = b % ncell;
+    id_out[s] = my;
+    cell[s] = cc;
+    if (rank == 0) {
+        cell_start[cc] = lo;
+        cell_end[cc] = hi;
+    }
+    double x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        x[d] = r_in[d * cap + o];
+        r_out[d * cap + s] = x[d];
+        rb[d * cap + s] = x[d];
+        v_out[d * cap + s] = v_in[d * cap + o];
+    }
+    const uint4 q = make_uint4(md_to_fixed(x[0], inv_h), md_to_fixed(x[1], inv_h), md_to_fixed(x[2], inv_h), 0u);
+    qfix[s] = q;
+    if (fp32) ((uint4 *)pos4)[s] = q;
+    else ((double4 *)pos4)[s] = make_double4(x[0], x[1], x[2], 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -317,9 +398,6 @@ __global__ void k_cell_bounds(const int *__restrict__ cell, long long n, int *__
 }
 
 // packed position copies for the force gathers
-__device__ __forceinline__ uint32_t md_to_fixed(double x, double inv_h) {
-    return (uint32_t)(unsigned long long)__double2ll_rn(x * inv_h);
-}
 __global__ void k_pack_positions(const double *__restrict__ r, long long n, long long cap, int fp32, double inv_h,
                                  void *__restrict__ pos4, uint4 *__restrict__ qfix) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1080,12 +1158,28 @@ int md_cells_setup(mdsea_ctx *c) {
         td.readMode = cudaReadModeElementType;
         MD_CUDA(c, cudaCreateTextureObject(&s->tex_pos, &rd, &td, nullptr));
     }
-    MD_CUDA(c, cudaMalloc(&s->key, sizeof(unsigned long long) * s->cap));
-    MD_CUDA(c, cudaMalloc(&s->key_alt, sizeof(unsigned long long) * s->cap));
-    MD_CUDA(c, cudaMalloc(&s->val, sizeof(int) * s->cap));
-    MD_CUDA(c, cudaMalloc(&s->val_alt, sizeof(int) * s->cap));
-    MD_CUDA(c, cudaMalloc(&s->hist, sizeof(int) * 256 * (size_t)s->sort_blocks));
-    MD_CUDA(c, cudaMalloc(&s->hist_tot, sizeof(int) * 256));
+    s->radix_binning = getenv("MDSEA_BINNING") && !strcmp(getenv("MDSEA_BINNING"), "radix");   // A/B switch
+    s->nbucket = (long long)(W > 1 ? 3 : 1) * s->ncell;
+    if (s->radix_binning) {
+        MD_CUDA(c, cudaMalloc(&s->key, sizeof(unsigned long long) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->key_alt, sizeof(unsigned long long) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->val, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->val_alt, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->hist, sizeof(int) * 256 * (size_t)s->sort_blocks));
+        MD_CUDA(c, cudaMalloc(&s->hist_tot, sizeof(int) * 256));
+    } else {
+        MD_CUDA(c, cudaMalloc(&s->bkt, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->arrival, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->tmp_id, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->tmp_src, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->tmp_bkt, sizeof(int) * s->cap));
+        MD_CUDA(c, cudaMalloc(&s->bcount, sizeof(int) * ((size_t)s->nbucket + 1)));
+        MD_CUDA(c, cudaMalloc(&s->bstart, sizeof(int) * ((size_t)s->nbucket + 1)));
+    }
+    {
+        const long long scan_max = std::max<long long>(s->nbucket + 1, (long long)W * s->cap + 1);
+        MD_CUDA(c, cudaMalloc(&s->scan_tmp, sizeof(int) * (md_div_up(scan_max, SCAN_THREADS * SCAN_ITEMS) + 1)));
+    }
     MD_CUDA(c, cudaMalloc(&s->cell, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->cell_start, sizeof(int) * ((size_t)s->ncell + 1)));
     MD_CUDA(c, cudaMalloc(&s->cell_end, sizeof(int) * ((size_t)s->ncell + 1)));
@@ -1114,7 +1208,6 @@ int md_cells_setup(mdsea_ctx *c) {
         MD_CUDA(c, cudaMalloc(&s->halo_flag, sizeof(int) * ((size_t)W * s->cap + 1)));
         MD_CUDA(c, cudaMalloc(&s->halo_scan, sizeof(int) * ((size_t)W * s->cap + 1)));
         MD_CUDA(c, cudaMalloc(&s->halo_idx, sizeof(int) * (size_t)W * s->cap));
-        MD_CUDA(c, cudaMalloc(&s->scan_tmp, sizeof(int) * (md_div_up((long long)W * s->cap + 1, SCAN_THREADS * SCAN_ITEMS) + 1)));
         MD_CUDA(c, cudaMalloc(&s->halo_send, sizeof(double) * (3 * (size_t)s->cap * std::min(W - 1, 3) + MD_MAXW)));
         MD_CUDA(c, cudaMalloc(&s->halo_recv, sizeof(double) * (3 * (size_t)s->cap + MD_MAXW)));
         MD_CUDA(c, cudaMalloc(&s->id_rows, sizeof(int) * (size_t)s->cap * c->ring));
@@ -1131,6 +1224,7 @@ void md_cells_free(mdsea_ctx *c) {
     if (s->tex_pos) cudaDestroyTextureObject(s->tex_pos);
     cudaFree(s->r_alt); cudaFree(s->v_alt); cudaFree(s->rb); cudaFree(s->id); cudaFree(s->id_alt); cudaFree(s->pos4);
     cudaFree(s->key); cudaFree(s->key_alt); cudaFree(s->val); cudaFree(s->val_alt); cudaFree(s->hist); cudaFree(s->hist_tot);
+    cudaFree(s->bkt); cudaFree(s->arrival); cudaFree(s->tmp_id); cudaFree(s->tmp_src); cudaFree(s->tmp_bkt); cudaFree(s->bcount); cudaFree(s->bstart);
     cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
     cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
@@ -1316,46 +1410,65 @@ static int rebuild(mdsea_ctx *c) {
     const int    *src_id = W > 1 ? s->id_alt : s->id;
     double *dst_r = W > 1 ? c->d_r : s->r_alt, *dst_v = W > 1 ? c->d_v : s->v_alt;
     int    *dst_id = W > 1 ? s->id : s->id_alt;
-    MD_CUDA(c, cudaMemsetAsync(s->d_cnt + MD_MAXW, 0, 2 * sizeof(int), c->stream));
-    k_cell_keys<<<g256(nt), 256, 0, c->stream>>>(src_r, src_id, nt, s->cap, c->box.L, s->cell_len, s->nc, s->D, s->key, s->val,
-                                                 s->d_cnt + MD_MAXW);
-    int launches = 1;
-    // LSD passes over the id bits, then the cell bits, then (multi-rank) the ghost bit:
-    // = stable sort by (ghost, cell id, particle id)
-    std::vector<int> shifts;
-    for (int b = 0; b < s->id_bits; b += 8) shifts.push_back(b);
-    for (int b = 0; b < s->cell_bits; b += 8) shifts.push_back(32 + b);
-    if (W > 1) shifts.push_back(56);
-    const int nblk = md_div_up(nt, SORT_CHUNK);
-    for (int sh : shifts) {
-        k_sort_hist<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, nt, sh, s->hist, nblk);
-        k_sort_rowscan<<<256, 256, 0, c->stream>>>(s->hist, nblk, s->hist_tot);
-        k_sort_scatter<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, s->val, s->key_alt, s->val_alt, nt, sh, s->hist, nblk,
-                                                             s->hist_tot);
-        std::swap(s->key, s->key_alt);
-        std::swap(s->val, s->val_alt);
+    int launches = 0;
+    MD_CUDA(c, cudaMemsetAsync(s->cell_start, 0, sizeof(int) * ((size_t)s->ncell + 1), c->stream));
+    MD_CUDA(c, cudaMemsetAsync(s->cell_end, 0, sizeof(int) * ((size_t)s->ncell + 1), c->stream));
+    if (!s->radix_binning) {
+        // counting pass over (class, cell) buckets -> bucket starts -> rank by id inside the bucket, gather into place
+        MD_CUDA(c, cudaMemsetAsync(s->bcount, 0, sizeof(int) * ((size_t)s->nbucket + 1), c->stream));
+        k_bin_count<<<g256(nt), 256, 0, c->stream>>>(src_r, nt, s->cap, c->box.L, s->cell_len, s->nc, s->ncell, s->D, s->bkt, s->arrival,
+                                                     s->bcount);
+        MD_TRY(scan_exclusive(c, s->bcount, s->bstart, s->nbucket + 1));
+        k_bin_scatter<<<g256(nt), 256, 0, c->stream>>>(nt, s->bkt, s->arrival, s->bstart, src_id, s->tmp_id, s->tmp_src, s->tmp_bkt);
+        pt.lap("count+scan");
+        k_bin_place<<<g256(nt), 256, 0, c->stream>>>(nt, s->cap, s->ncell, s->bstart, s->tmp_id, s->tmp_src, s->tmp_bkt, src_r, src_v, dst_r,
+                                                     dst_v, s->rb, dst_id, s->cell, s->cell_start, s->cell_end,
+                                                     c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, s->qfix);
         launches += 3;
+        if (W > 1)   // owned interior | owned boundary | ghost: the class boundaries are bucket starts
+            MD_CUDA(c, cudaMemcpy2DAsync(s->h_flag, sizeof(int), s->bstart + s->ncell, sizeof(int) * (size_t)s->ncell, sizeof(int), 2,
+                                         cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        MD_CUDA(c, cudaMemsetAsync(s->d_cnt + MD_MAXW, 0, 2 * sizeof(int), c->stream));
+        k_cell_keys<<<g256(nt), 256, 0, c->stream>>>(src_r, src_id, nt, s->cap, c->box.L, s->cell_len, s->nc, s->D, s->key, s->val,
+                                                     s->d_cnt + MD_MAXW);
+        // LSD passes over the id bits, then the cell bits, then (multi-rank) the boundary / ghost bits:
+        // = stable sort by (ghost, boundary, cell id, particle id)
+        std::vector<int> shifts;
+        for (int b = 0; b < s->id_bits; b += 8) shifts.push_back(b);
+        for (int b = 0; b < s->cell_bits; b += 8) shifts.push_back(32 + b);
+        if (W > 1) shifts.push_back(56);
+        const int nblk = md_div_up(nt, SORT_CHUNK);
+        for (int sh : shifts) {
+            k_sort_hist<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, nt, sh, s->hist, nblk);
+            k_sort_rowscan<<<256, 256, 0, c->stream>>>(s->hist, nblk, s->hist_tot);
+            k_sort_scatter<<<nblk, SORT_THREADS, 0, c->stream>>>(s->key, s->val, s->key_alt, s->val_alt, nt, sh, s->hist, nblk,
+                                                                 s->hist_tot);
+            std::swap(s->key, s->key_alt);
+            std::swap(s->val, s->val_alt);
+            launches += 3;
+        }
+        pt.lap("keys+sort");
+        k_reorder<<<g256(nt), 256, 0, c->stream>>>(s->key, s->val, nt, s->cap, src_r, src_v, dst_r, dst_v, s->rb, dst_id, s->cell);
+        k_cell_bounds<<<g256(nt), 256, 0, c->stream>>>(s->cell, nt, s->cell_start, s->cell_end);
+        k_pack_positions<<<g256(nt), 256, 0, c->stream>>>(dst_r, nt, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4,
+                                                          s->qfix);
+        launches += 4;
+        if (W > 1)   // {owned, owned interior}
+            MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt + MD_MAXW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
-    pt.lap("keys+sort");
-    k_reorder<<<g256(nt), 256, 0, c->stream>>>(s->key, s->val, nt, s->cap, src_r, src_v, dst_r, dst_v, s->rb, dst_id, s->cell);
     if (W == 1) {
         std::swap(c->d_r, s->r_alt);
         std::swap(c->d_v, s->v_alt);
         std::swap(s->id, s->id_alt);
     } else {
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt + MD_MAXW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MD_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->n = s->h_flag[0];
-        s->n_int = s->h_flag[1];
+        if (s->radix_binning) { c->n = s->h_flag[0]; s->n_int = s->h_flag[1]; }
+        else { s->n_int = s->h_flag[0]; c->n = s->h_flag[1]; }
         c->stats.n_local = c->n;
         c->stats.n_ghost = nt - c->n;
     }
-    MD_CUDA(c, cudaMemsetAsync(s->cell_start, 0, sizeof(int) * ((size_t)s->ncell + 1), c->stream));
-    MD_CUDA(c, cudaMemsetAsync(s->cell_end, 0, sizeof(int) * ((size_t)s->ncell + 1), c->stream));
-    k_cell_bounds<<<g256(nt), 256, 0, c->stream>>>(s->cell, nt, s->cell_start, s->cell_end);
-    k_pack_positions<<<g256(nt), 256, 0, c->stream>>>(c->d_r, nt, s->cap, c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4,
-                                                      s->qfix);
-    pt.lap("reorder+pack");
+    pt.lap("place");
     if (W > 1) MD_TRY(build_halo_lists(c));
     pt.lap("halo lists");
     {
@@ -1372,7 +1485,7 @@ static int rebuild(mdsea_ctx *c) {
                 c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih,
                 s->rl2, (float)rl2s, (float)(rl2s * 1e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc);
     }
-    launches += 4;
+    launches += 1;
     pt.lap("nbr build");
     MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
     md_prof_end(c, &c->stats.ms_rebuild);
