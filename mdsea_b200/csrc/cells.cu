@@ -530,11 +530,18 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
 // ---- warp-cooperative build ------------------------------------------------------------------------
 #define NBW_WARPS 4      // warps (= tiles of 32 slots) per block
 #define NBW_RUN   6      // at most this many x-consecutive cells of i-particles per pass (bounds the float error)
+#define NBW_SCAP  64     // staged list entries per lane in shared memory before they are flushed to the global rows
 // Offsets from the common origin are plain floats (no wrap), so they only reproduce the minimum image while the
 // candidate window stays inside half a period: (run + 2) cells < nc in x, 3 cells < nc in y and z.  The host
 // therefore passes run_max = min(NBW_RUN, nc - 3) and uses the thread-per-particle kernel when nc == 3.
+//
+// Why the entries are staged in shared memory: in the tile-sliced list, entry e of lane l lives in line (tile, e).
+// Lanes fill their rows at different rates, so appending straight to global memory scatters every store over as
+// many lines as there are distinct fill levels in the warp -- measured, that store traffic (not the distance tests)
+// bounded all earlier variants at ~610-670 us.  Here a lane appends to its own shared-memory column (one bank per
+// lane, conflict free) and the warp flushes entry level by entry level: one coalesced line per level.
 
-// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle
+// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle -> bit mask
 __device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
                                                    float neg_rl2s, float neg_bw, float &bandmin) {
     unsigned m = 0u;
@@ -553,6 +560,30 @@ __device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ ca
     return m;
 }
 
+// fast path of a chunk (it does not contain the lane's own slot): every in-range candidate is appended with one
+// predicated shared-memory store at the lane's cursor; the candidate's slot index rides in cand.w
+__device__ __forceinline__ void nbw_chunk_append(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
+                                                 float neg_rl2s, float neg_bw, float &bandmin, unsigned &saddr) {
+    for (int t0 = 0; t0 < ncand; t0 += 8) {
+        float d[8], jw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // 8 independent load + distance chains ...
+            const float4 cj = cand[t0 + u];   // broadcast LDS.128
+            const float dx = cj.x - xi, dy = cj.y - yi, dz = cj.z - zi;
+            d[u] = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, neg_rl2s)));   // r^2 - rl^2
+            jw[u] = cj.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // ... then the (serial) cursor updates
+            bandmin = fminf(bandmin, fabsf(d[u]));
+            if (d[u] < neg_bw) {
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "f"(jw[u]));
+                saddr += 128u;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NBW_WARPS * 32)
 k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
@@ -560,6 +591,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                  float rl2s_hi, int max_nbr, int run_max, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
                  StepScalars *__restrict__ sc) {
     __shared__ float4 s_cand[NBW_WARPS][32];
+    __shared__ int    s_rows[NBW_WARPS][NBW_SCAP][32];   // entry k of lane l at [k][l]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
     if (i0 >= n_own) return;   // whole warp out of range (only __syncwarp below)
@@ -571,13 +603,27 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
     float4 *cand = s_cand[w];
     int *row0 = nbr + md_nbr_row_base(il, max_nbr);
-    int *wp = row0;   // write cursor inside the row
+    const int *srow = &s_rows[w][0][lane];
+    const unsigned saddr0 = (unsigned)__cvta_generic_to_shared(srow);
+    unsigned saddr = saddr0;   // the lane's cursor in its shared-memory column: +128 bytes per staged entry
+    int flushed = 0;           // entries of this lane already in (or dropped from) its global row
     const float neg_rl2s = -rl2s, neg_bw = -bw;
     float bandmin = 3.0e38f;
-    int cnt = 0;
+
+    // flush the staged entries to the global rows, one entry level (= one line of the tile) per iteration
+    auto flush = [&]() {
+        asm volatile("" ::: "memory");   // the staged entries were written by asm stores
+        const int lo = flushed, hi = flushed + (int)((saddr - saddr0) >> 7);
+        const int emin = __reduce_min_sync(0xffffffffu, lo), emax = min(__reduce_max_sync(0xffffffffu, hi), max_nbr);
+        for (int e = emin; e < emax; ++e)
+            if (e >= lo && e < hi) row0[e * 32] = srow[(e - lo) * 32];
+        flushed = hi;
+        saddr = saddr0;
+    };
+
     unsigned todo = __ballot_sync(0xffffffffu, valid);
     while (todo) {
-        // ---- pick the particles of this pass: same (cy, cz) row as the first pending lane, cx within NBW_RUN cells
+        // ---- pick the particles of this pass: same (cy, cz) row as the first pending lane, cx within run_max cells
         const int leader = __ffs(todo) - 1;
         const int cl = __shfl_sync(0xffffffffu, c, leader);
         const int cxl = cl % nc, cyl = (cl / nc) % nc, czl = cl / (nc * nc);
@@ -588,7 +634,8 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
         // common origin = centre of the i-cells of the pass, in fixed point
         const uint32_t ox = md_to_fixed((cxl + 0.5 * (double)(cxb - cxl + 1)) * cell_len, inv_h);
         const uint32_t oy = md_to_fixed((cyl + 0.5) * cell_len, inv_h), oz = md_to_fixed((czl + 0.5) * cell_len, inv_h);
-        const float xi = (float)(int)(qi.x - ox), yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
+        // lanes that are not part of this pass sit far away: they fail every test and never touch bandmin
+        const float xi = mine ? (float)(int)(qi.x - ox) : 3.0e30f, yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
         for (int dz = -1; dz <= 1; ++dz) {
             const int z = (czl + dz + nc) % nc;
             // lanes 0..23 fetch the slot ranges of the 3 x ncx candidate cells of this z layer
@@ -603,51 +650,64 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                     ce_l = cell_end[cc];
                 }
             }
+            // merge slot-contiguous cells into ranges (warp-uniform); lane k keeps range k
+            int my_s = 0, my_e = 0, nr = 0;
             for (int dyi = 0; dyi < 3; ++dyi) {
-                int rs = 0, re = 0;   // pending (merged) slot range
-                for (int t = 0; t <= ncx; ++t) {
-                    int s1 = 0, e1 = 0;
-                    if (t < ncx) {
-                        s1 = __shfl_sync(0xffffffffu, cs_l, dyi * 8 + t);
-                        e1 = __shfl_sync(0xffffffffu, ce_l, dyi * 8 + t);
-                        if (e1 == s1) continue;
-                        if (re > rs && s1 == re) { re = e1; continue; }   // contiguous with the pending range
-                    }
-                    // flush the pending range, 32 candidates at a time
-                    for (int base = rs; base < re; base += 32) {
-                        const int jj = base + lane;
-                        float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
-                        if (jj < re) {
-                            const uint4 qj = q[jj];
-                            cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), 0.0f);
-                        }
-                        __syncwarp();
-                        cand[lane] = cd;
-                        __syncwarp();
-                        float bm = 3.0e38f;
-                        unsigned m = nbw_test_chunk(cand, min(32, re - base), xi, yi, zi, neg_rl2s, neg_bw, bm);
-                        if (mine) bandmin = fminf(bandmin, bm);
-                        else m = 0u;
-                        const long long self = i - base;
-                        if (self >= 0 && self < 32) m &= ~(1u << self);
-                        if (cnt + __popc(m) > max_nbr) {   // row full: keep counting, the overflow is reported below
-                            cnt += __popc(m);
-                            m = 0u;
-                        }
-                        while (m) {
-                            const int t1 = __ffs(m) - 1;
-                            m &= m - 1;
-                            *wp = base + t1;
-                            ++cnt;
-                            wp += 32;   // next entry of the tile-sliced row (md_nbr_off)
-                        }
-                    }
+                int rs = 0, re = 0;
+                for (int t = 0; t < ncx; ++t) {
+                    const int s1 = __shfl_sync(0xffffffffu, cs_l, dyi * 8 + t), e1 = __shfl_sync(0xffffffffu, ce_l, dyi * 8 + t);
+                    if (e1 == s1) continue;
+                    if (re > rs && s1 == re) { re = e1; continue; }
+                    if (re > rs) { if (lane == nr) { my_s = rs; my_e = re; } ++nr; }
                     rs = s1; re = e1;
                 }
+                if (re > rs) { if (lane == nr) { my_s = rs; my_e = re; } ++nr; }
+            }
+            if (nr == 0) continue;
+            // walk the chunks of all ranges; the candidates of the NEXT chunk are fetched while this one is tested
+            int ri = 0, rs = __shfl_sync(0xffffffffu, my_s, 0), re = __shfl_sync(0xffffffffu, my_e, 0), base = rs;
+            uint4 qj = make_uint4(0u, 0u, 0u, 0u);
+            if (base + lane < re) qj = q[base + lane];
+            while (true) {
+                int nri = ri, nrs = rs, nre = re, nbase = base + 32;
+                if (nbase >= re) {
+                    nri = ri + 1;
+                    if (nri < nr) { nrs = __shfl_sync(0xffffffffu, my_s, nri); nre = __shfl_sync(0xffffffffu, my_e, nri); nbase = nrs; }
+                }
+                const bool has_next = nri < nr;
+                const int jj = base + lane;
+                float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
+                if (jj < re)
+                    cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), __int_as_float(jj));
+                __syncwarp();
+                cand[lane] = cd;
+                __syncwarp();
+                uint4 qn = make_uint4(0u, 0u, 0u, 0u);
+                if (has_next && nbase + lane < nre) qn = q[nbase + lane];
+                const int ncand = min(32, re - base);
+                // room for 32 more entries in every lane's column?  (warp-uniform)
+                if (__any_sync(0xffffffffu, (int)((saddr - saddr0) >> 7) > NBW_SCAP - 32)) flush();
+                if (!(base < i0 + 32 && base + 32 > i0)) {
+                    nbw_chunk_append(cand, ncand, xi, yi, zi, neg_rl2s, neg_bw, bandmin, saddr);
+                } else {   // the chunk overlaps the tile's own slots: mask path with self exclusion
+                    unsigned m = nbw_test_chunk(cand, ncand, xi, yi, zi, neg_rl2s, neg_bw, bandmin);
+                    const long long self = i - base;
+                    if (self >= 0 && self < 32) m &= ~(1u << self);
+                    while (m) {
+                        const int t1 = __ffs(m) - 1;
+                        m &= m - 1;
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(base + t1));
+                        saddr += 128u;
+                    }
+                }
+                if (!has_next) break;
+                ri = nri; rs = nrs; re = nre; base = nbase; qj = qn;
             }
         }
     }
+    flush();
     if (valid) {
+        int cnt = flushed;
         if (__builtin_expect(bandmin <= bw, 0)) {   // a candidate sat in the guard band: canonical float64 redo of this particle
             bool band = false;
             cnt = nb_particle<true>(i, qi, c, r, q, cap, cell_start, cell_end, nc, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, band);
