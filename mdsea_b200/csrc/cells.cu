@@ -22,6 +22,7 @@
 
 #include "ctx.h"
 #include "comm.h"
+#include "finalize.cuh"
 
 #define SORT_THREADS 256
 #define SORT_ITEMS 8
@@ -530,18 +531,11 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
 // ---- warp-cooperative build ------------------------------------------------------------------------
 #define NBW_WARPS 4      // warps (= tiles of 32 slots) per block
 #define NBW_RUN   6      // at most this many x-consecutive cells of i-particles per pass (bounds the float error)
-#define NBW_SCAP  64     // staged list entries per lane in shared memory before they are flushed to the global rows
 // Offsets from the common origin are plain floats (no wrap), so they only reproduce the minimum image while the
 // candidate window stays inside half a period: (run + 2) cells < nc in x, 3 cells < nc in y and z.  The host
 // therefore passes run_max = min(NBW_RUN, nc - 3) and uses the thread-per-particle kernel when nc == 3.
-//
-// Why the entries are staged in shared memory: in the tile-sliced list, entry e of lane l lives in line (tile, e).
-// Lanes fill their rows at different rates, so appending straight to global memory scatters every store over as
-// many lines as there are distinct fill levels in the warp -- measured, that store traffic (not the distance tests)
-// bounded all earlier variants at ~610-670 us.  Here a lane appends to its own shared-memory column (one bank per
-// lane, conflict free) and the warp flushes entry level by entry level: one coalesced line per level.
 
-// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle -> bit mask
+// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle
 __device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
                                                    float neg_rl2s, float neg_bw, float &bandmin) {
     unsigned m = 0u;
@@ -560,30 +554,6 @@ __device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ ca
     return m;
 }
 
-// fast path of a chunk (it does not contain the lane's own slot): every in-range candidate is appended with one
-// predicated shared-memory store at the lane's cursor; the candidate's slot index rides in cand.w
-__device__ __forceinline__ void nbw_chunk_append(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
-                                                 float neg_rl2s, float neg_bw, float &bandmin, unsigned &saddr) {
-    for (int t0 = 0; t0 < ncand; t0 += 8) {
-        float d[8], jw[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {   // 8 independent load + distance chains ...
-            const float4 cj = cand[t0 + u];   // broadcast LDS.128
-            const float dx = cj.x - xi, dy = cj.y - yi, dz = cj.z - zi;
-            d[u] = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, neg_rl2s)));   // r^2 - rl^2
-            jw[u] = cj.w;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {   // ... then the (serial) cursor updates
-            bandmin = fminf(bandmin, fabsf(d[u]));
-            if (d[u] < neg_bw) {
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "f"(jw[u]));
-                saddr += 128u;
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(NBW_WARPS * 32)
 k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
@@ -591,7 +561,6 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                  float rl2s_hi, int max_nbr, int run_max, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
                  StepScalars *__restrict__ sc) {
     __shared__ float4 s_cand[NBW_WARPS][32];
-    __shared__ int    s_rows[NBW_WARPS][NBW_SCAP][32];   // entry k of lane l at [k][l]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
     if (i0 >= n_own) return;   // whole warp out of range (only __syncwarp below)
@@ -603,27 +572,13 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
     float4 *cand = s_cand[w];
     int *row0 = nbr + md_nbr_row_base(il, max_nbr);
-    const int *srow = &s_rows[w][0][lane];
-    const unsigned saddr0 = (unsigned)__cvta_generic_to_shared(srow);
-    unsigned saddr = saddr0;   // the lane's cursor in its shared-memory column: +128 bytes per staged entry
-    int flushed = 0;           // entries of this lane already in (or dropped from) its global row
+    int *wp = row0;   // write cursor inside the row
     const float neg_rl2s = -rl2s, neg_bw = -bw;
     float bandmin = 3.0e38f;
-
-    // flush the staged entries to the global rows, one entry level (= one line of the tile) per iteration
-    auto flush = [&]() {
-        asm volatile("" ::: "memory");   // the staged entries were written by asm stores
-        const int lo = flushed, hi = flushed + (int)((saddr - saddr0) >> 7);
-        const int emin = __reduce_min_sync(0xffffffffu, lo), emax = min(__reduce_max_sync(0xffffffffu, hi), max_nbr);
-        for (int e = emin; e < emax; ++e)
-            if (e >= lo && e < hi) row0[e * 32] = srow[(e - lo) * 32];
-        flushed = hi;
-        saddr = saddr0;
-    };
-
+    int cnt = 0;
     unsigned todo = __ballot_sync(0xffffffffu, valid);
     while (todo) {
-        // ---- pick the particles of this pass: same (cy, cz) row as the first pending lane, cx within run_max cells
+        // ---- pick the particles of this pass: same (cy, cz) row as the first pending lane, cx within NBW_RUN cells
         const int leader = __ffs(todo) - 1;
         const int cl = __shfl_sync(0xffffffffu, c, leader);
         const int cxl = cl % nc, cyl = (cl / nc) % nc, czl = cl / (nc * nc);
@@ -634,8 +589,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
         // common origin = centre of the i-cells of the pass, in fixed point
         const uint32_t ox = md_to_fixed((cxl + 0.5 * (double)(cxb - cxl + 1)) * cell_len, inv_h);
         const uint32_t oy = md_to_fixed((cyl + 0.5) * cell_len, inv_h), oz = md_to_fixed((czl + 0.5) * cell_len, inv_h);
-        // lanes that are not part of this pass sit far away: they fail every test and never touch bandmin
-        const float xi = mine ? (float)(int)(qi.x - ox) : 3.0e30f, yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
+        const float xi = (float)(int)(qi.x - ox), yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
         for (int dz = -1; dz <= 1; ++dz) {
             const int z = (czl + dz + nc) % nc;
             // lanes 0..23 fetch the slot ranges of the 3 x ncx candidate cells of this z layer
@@ -650,64 +604,51 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                     ce_l = cell_end[cc];
                 }
             }
-            // merge slot-contiguous cells into ranges (warp-uniform); lane k keeps range k
-            int my_s = 0, my_e = 0, nr = 0;
             for (int dyi = 0; dyi < 3; ++dyi) {
-                int rs = 0, re = 0;
-                for (int t = 0; t < ncx; ++t) {
-                    const int s1 = __shfl_sync(0xffffffffu, cs_l, dyi * 8 + t), e1 = __shfl_sync(0xffffffffu, ce_l, dyi * 8 + t);
-                    if (e1 == s1) continue;
-                    if (re > rs && s1 == re) { re = e1; continue; }
-                    if (re > rs) { if (lane == nr) { my_s = rs; my_e = re; } ++nr; }
+                int rs = 0, re = 0;   // pending (merged) slot range
+                for (int t = 0; t <= ncx; ++t) {
+                    int s1 = 0, e1 = 0;
+                    if (t < ncx) {
+                        s1 = __shfl_sync(0xffffffffu, cs_l, dyi * 8 + t);
+                        e1 = __shfl_sync(0xffffffffu, ce_l, dyi * 8 + t);
+                        if (e1 == s1) continue;
+                        if (re > rs && s1 == re) { re = e1; continue; }   // contiguous with the pending range
+                    }
+                    // flush the pending range, 32 candidates at a time
+                    for (int base = rs; base < re; base += 32) {
+                        const int jj = base + lane;
+                        float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
+                        if (jj < re) {
+                            const uint4 qj = q[jj];
+                            cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), 0.0f);
+                        }
+                        __syncwarp();
+                        cand[lane] = cd;
+                        __syncwarp();
+                        float bm = 3.0e38f;
+                        unsigned m = nbw_test_chunk(cand, min(32, re - base), xi, yi, zi, neg_rl2s, neg_bw, bm);
+                        if (mine) bandmin = fminf(bandmin, bm);
+                        else m = 0u;
+                        const long long self = i - base;
+                        if (self >= 0 && self < 32) m &= ~(1u << self);
+                        if (cnt + __popc(m) > max_nbr) {   // row full: keep counting, the overflow is reported below
+                            cnt += __popc(m);
+                            m = 0u;
+                        }
+                        while (m) {
+                            const int t1 = __ffs(m) - 1;
+                            m &= m - 1;
+                            *wp = base + t1;
+                            ++cnt;
+                            wp += 32;   // next entry of the tile-sliced row (md_nbr_off)
+                        }
+                    }
                     rs = s1; re = e1;
                 }
-                if (re > rs) { if (lane == nr) { my_s = rs; my_e = re; } ++nr; }
-            }
-            if (nr == 0) continue;
-            // walk the chunks of all ranges; the candidates of the NEXT chunk are fetched while this one is tested
-            int ri = 0, rs = __shfl_sync(0xffffffffu, my_s, 0), re = __shfl_sync(0xffffffffu, my_e, 0), base = rs;
-            uint4 qj = make_uint4(0u, 0u, 0u, 0u);
-            if (base + lane < re) qj = q[base + lane];
-            while (true) {
-                int nri = ri, nrs = rs, nre = re, nbase = base + 32;
-                if (nbase >= re) {
-                    nri = ri + 1;
-                    if (nri < nr) { nrs = __shfl_sync(0xffffffffu, my_s, nri); nre = __shfl_sync(0xffffffffu, my_e, nri); nbase = nrs; }
-                }
-                const bool has_next = nri < nr;
-                const int jj = base + lane;
-                float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
-                if (jj < re)
-                    cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), __int_as_float(jj));
-                __syncwarp();
-                cand[lane] = cd;
-                __syncwarp();
-                uint4 qn = make_uint4(0u, 0u, 0u, 0u);
-                if (has_next && nbase + lane < nre) qn = q[nbase + lane];
-                const int ncand = min(32, re - base);
-                // room for 32 more entries in every lane's column?  (warp-uniform)
-                if (__any_sync(0xffffffffu, (int)((saddr - saddr0) >> 7) > NBW_SCAP - 32)) flush();
-                if (!(base < i0 + 32 && base + 32 > i0)) {
-                    nbw_chunk_append(cand, ncand, xi, yi, zi, neg_rl2s, neg_bw, bandmin, saddr);
-                } else {   // the chunk overlaps the tile's own slots: mask path with self exclusion
-                    unsigned m = nbw_test_chunk(cand, ncand, xi, yi, zi, neg_rl2s, neg_bw, bandmin);
-                    const long long self = i - base;
-                    if (self >= 0 && self < 32) m &= ~(1u << self);
-                    while (m) {
-                        const int t1 = __ffs(m) - 1;
-                        m &= m - 1;
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(base + t1));
-                        saddr += 128u;
-                    }
-                }
-                if (!has_next) break;
-                ri = nri; rs = nrs; re = nre; base = nbase; qj = qn;
             }
         }
     }
-    flush();
     if (valid) {
-        int cnt = flushed;
         if (__builtin_expect(bandmin <= bw, 0)) {   // a candidate sat in the guard band: canonical float64 redo of this particle
             bool band = false;
             cnt = nb_particle<true>(i, qi, c, r, q, cap, cell_start, cell_end, nc, L, halfL, rl2, rl2s_lo, rl2s_hi, max_nbr, row0, band);
@@ -895,9 +836,10 @@ k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *_
 __global__ void __launch_bounds__(256)
 k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
                   const int *__restrict__ id, long long n, long long cap, long long row_stride, int *__restrict__ id_row,
-                  double dt, double g_dt, const StepScalars *__restrict__ sc, double *__restrict__ ke_part,
-                  double *__restrict__ r_row, double *__restrict__ v_row, int guarded) {
+                  double dt, double g_dt, StepScalars *__restrict__ sc, double *__restrict__ ke_part,
+                  double *__restrict__ r_row, double *__restrict__ v_row, int guarded, FinalizeArgs fin) {
     __shared__ double red[32];
+    __shared__ bool   s_last;
     if (guarded && sc->rebuild_flag) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double v2 = 0.0;
@@ -922,7 +864,19 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
         }
     }
     const double b = md_block_sum(v2, red);
-    if (threadIdx.x == 0) ke_part[blockIdx.x] = b;
+    // the step's reductions and bookkeeping (k_finalize of the all-pairs path) are done by whichever block publishes
+    // its KE partial last: no separate single-block launch on the critical path of every step
+    if (threadIdx.x == 0) {
+        ke_part[blockIdx.x] = b;
+        __threadfence();
+        s_last = atomicAdd(&sc->finish_blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        md_finalize_body(fin, sc, red);
+        if (threadIdx.x == 0) sc->finish_blocks_done = 0u;
+    }
 }
 
 __global__ void k_unsort(const double *__restrict__ src, const int *__restrict__ id, long long n, long long cap,
@@ -1007,9 +961,10 @@ k_scan_add(int *__restrict__ out, long long n, const int *__restrict__ block_sum
 // K6: domain decomposition -- rebuild-time migration / ghost selection and per-step halo refresh
 // ---------------------------------------------------------------------------------------------------
 // pass 0 (count) / pass 1 (fill): every held particle goes to each rank whose extended block contains its cell
+struct RouteDst { PMsg *pool[MD_MAXW]; };   // per destination rank: where its messages are written (fill pass)
 __global__ void k_mr_route(const double *__restrict__ r, const double *__restrict__ v, const int *__restrict__ id, long long n,
                            long long cap, double L, double cl, int nc, Decomp D, int fill, int *__restrict__ counter,
-                           PMsg *__restrict__ pool) {
+                           RouteDst dst) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = r[i], y = r[cap + i], z = r[2 * cap + i];
@@ -1022,7 +977,7 @@ __global__ void k_mr_route(const double *__restrict__ r, const double *__restric
             m.r[0] = x; m.r[1] = y; m.r[2] = z;
             m.v[0] = v[i]; m.v[1] = v[cap + i]; m.v[2] = v[2 * cap + i];
             m.id = id[i];
-            pool[pos] = m;
+            dst.pool[q][pos] = m;
         }
     }
 }
@@ -1058,10 +1013,13 @@ __global__ void k_select_owned(const double *__restrict__ rg, const double *__re
 // RECEIVED from rank q (q owns its cell).  One scan over the whole [world][n_tot] array then yields, per peer,
 // the send list followed by the receive list, both in slot order = canonical (cell id, particle id) order --
 // the same order on the sending and on the receiving rank, so no index exchange is needed.
-__global__ void k_halo_flags(const int *__restrict__ cell, long long n_own, long long n_tot, int nc, Decomp D,
+__global__ void k_halo_flags(const int *__restrict__ cell, long long base, long long n_own, long long n_tot, int nc, Decomp D,
                              int *__restrict__ flag) {
-    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_tot) return;
+    // only the owned BOUNDARY slots [base, n_own) can be in somebody's halo, and only the ghost slots [n_own, n_tot)
+    // are received: the interior slots [0, base) are left out of the flag / scan arrays altogether
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long m = n_tot - base, s = base + t;
+    if (t >= m) return;
     const int c = cell[s];
     const int cx = c % nc, cy = (c / nc) % nc, cz = c / (nc * nc);
     const int owner = dc_owner(D, cx, cy, cz);
@@ -1069,16 +1027,16 @@ __global__ void k_halo_flags(const int *__restrict__ cell, long long n_own, long
         int f;
         if (s < n_own) f = (q != D.rank && dc_in_ext(D, q, cx, cy, cz)) ? 1 : 0;
         else f = (owner == q) ? 1 : 0;
-        flag[(long long)q * n_tot + s] = f;
+        flag[(long long)q * m + t] = f;
     }
 }
-__global__ void k_halo_lists(const int *__restrict__ flag, const int *__restrict__ scan, long long n_tot, int world,
+__global__ void k_halo_lists(const int *__restrict__ flag, const int *__restrict__ scan, long long m, long long base, int world,
                              int *__restrict__ idx) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tot * world) return;
+    if (t >= m * world) return;
     if (!flag[t]) return;
-    const long long q = t / n_tot, s = t - q * n_tot;
-    idx[q * n_tot + (scan[t] - scan[q * n_tot])] = (int)s;
+    const long long q = t / m, k = t - q * m;
+    idx[q * m + (scan[t] - scan[q * m])] = (int)(base + k);
 }
 // One message per peer and step: [3 * n positions][1 double: this rank's skin-trigger flag].  Every rank sends to
 // every other rank every step (an empty halo still carries the flag), so after the unpack each rank holds the
@@ -1339,27 +1297,31 @@ static int mr_assemble(mdsea_ctx *c) {
     CellState *s = c->cells;
     const int W = c->p.world, me = c->p.rank;
     const long long n = c->n;
+    RouteDst none;
+    memset(&none, 0, sizeof(none));
     MD_CUDA(c, cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * MD_MAXW, c->stream));
     k_mr_route<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, 0, s->d_cnt,
-                                               nullptr);
+                                               none);
     MD_TRY(md_comm_allgather_i32(c, s->d_cnt, MD_MAXW, s->d_cnt_all));
     MD_CUDA(c, cudaMemcpyAsync(s->h_cnt_all, s->d_cnt_all, sizeof(int) * MD_MAXW * W, cudaMemcpyDeviceToHost, c->stream));
+    MD_CUDA(c, cudaMemsetAsync(s->d_cursor, 0, sizeof(int) * MD_MAXW, c->stream));
     MD_CUDA(c, cudaStreamSynchronize(c->stream));
     long long soff[MD_MAXW + 1], roff[MD_MAXW + 1];
-    int cursor[MD_MAXW];
     soff[0] = roff[0] = 0;
     for (int q = 0; q < W; ++q) {
-        soff[q + 1] = soff[q] + s->h_cnt_all[me * MD_MAXW + q];
+        soff[q + 1] = soff[q] + (q == me ? 0 : s->h_cnt_all[me * MD_MAXW + q]);
         roff[q + 1] = roff[q] + s->h_cnt_all[q * MD_MAXW + me];
-        cursor[q] = (int)soff[q];
     }
     if (soff[W] > s->sendpool_cap || roff[W] > s->cap) {
         md_set_error(c, "rebuild: migration/ghost buffer capacity exceeded on this rank");
         return MDSEA_ERR_CAPACITY;
     }
-    MD_CUDA(c, cudaMemcpyAsync(s->d_cursor, cursor, sizeof(int) * W, cudaMemcpyHostToDevice, c->stream));
-    k_mr_route<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, 1,
-                                               s->d_cursor, s->sendpool);
+    // fill pass: messages for peer q -> its segment of the send pool; what this rank keeps -> straight into its own
+    // segment of the receive pool (the union is unpacked from there in one go; the sort canonicalises the order)
+    RouteDst dst;
+    for (int q = 0; q < MD_MAXW; ++q) dst.pool[q] = q < W ? (q == me ? s->recvpool + roff[me] : s->sendpool + soff[q]) : nullptr;
+    k_mr_route<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, 1, s->d_cursor,
+                                               dst);
     void  *sp[MD_MAXW], *rp[MD_MAXW];
     size_t sb[MD_MAXW], rbytes[MD_MAXW];
     for (int q = 0; q < W; ++q) {
@@ -1369,15 +1331,8 @@ static int mr_assemble(mdsea_ctx *c) {
         rbytes[q] = q == me ? 0 : sizeof(PMsg) * (size_t)(roff[q + 1] - roff[q]);
     }
     MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes));
-    // stage = [what I keep] + [what every peer sent], any order (the sort below canonicalises it)
-    for (int q = 0; q < W; ++q) {
-        const long long cnt = roff[q + 1] - roff[q];
-        if (!cnt) continue;
-        const PMsg *src = q == me ? s->sendpool + soff[me] : s->recvpool + roff[q];
-        k_mr_unpack<<<g256(cnt), 256, 0, c->stream>>>(src, cnt, roff[q], s->cap, s->r_alt, s->v_alt, s->id_alt);
-        c->stats.kernel_launches += 1;
-    }
-    c->stats.kernel_launches += 2;
+    if (roff[W] > 0) k_mr_unpack<<<g256(roff[W]), 256, 0, c->stream>>>(s->recvpool, roff[W], 0, s->cap, s->r_alt, s->v_alt, s->id_alt);
+    c->stats.kernel_launches += 3;
     MD_CUDA(c, cudaGetLastError());
     s->n_tot = roff[W];
     return MDSEA_OK;
@@ -1386,24 +1341,29 @@ static int mr_assemble(mdsea_ctx *c) {
 static int build_halo_lists(mdsea_ctx *c) {
     CellState *s = c->cells;
     const int W = c->p.world;
-    const long long nt = s->n_tot, tot = nt * W;
-    k_halo_flags<<<g256(nt), 256, 0, c->stream>>>(s->cell, c->n, nt, s->nc, s->D, s->halo_flag);
+    const long long base = s->n_int, m = s->n_tot - base, tot = m * W;
+    k_halo_flags<<<g256(m), 256, 0, c->stream>>>(s->cell, base, c->n, s->n_tot, s->nc, s->D, s->halo_flag);
     MD_CUDA(c, cudaMemsetAsync(s->halo_flag + tot, 0, sizeof(int), c->stream));  // sentinel: scan[tot] = grand total
     MD_TRY(scan_exclusive(c, s->halo_flag, s->halo_scan, tot + 1));
-    k_halo_lists<<<g256(tot), 256, 0, c->stream>>>(s->halo_flag, s->halo_scan, nt, W, s->halo_idx);
+    k_halo_lists<<<g256(tot), 256, 0, c->stream>>>(s->halo_flag, s->halo_scan, m, base, W, s->halo_idx);
     c->stats.kernel_launches += 2;
-    // list sizes from the scan at the segment starts (A) and at the owned/ghost split of each segment (B)
+    // list sizes from the scan at the segment starts (A) and at the owned/ghost split of each segment (B):
+    // two strided copies (one int per segment)
     int *h = s->h_cnt_all;  // pinned scratch, >= 2 * MD_MAXW + 1 ints
-    for (int q = 0; q <= W; ++q)
-        MD_CUDA(c, cudaMemcpyAsync(&h[q], s->halo_scan + (size_t)q * nt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    for (int q = 0; q < W; ++q)
-        MD_CUDA(c, cudaMemcpyAsync(&h[MD_MAXW + 1 + q], s->halo_scan + (size_t)q * nt + c->n, sizeof(int), cudaMemcpyDeviceToHost,
-                                   c->stream));
-    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t pitch = sizeof(int) * (size_t)(m > 0 ? m : 1);
+    if (m > 0) {
+        MD_CUDA(c, cudaMemcpy2DAsync(&h[0], sizeof(int), s->halo_scan, pitch, sizeof(int), (size_t)W + 1, cudaMemcpyDeviceToHost,
+                                     c->stream));
+        MD_CUDA(c, cudaMemcpy2DAsync(&h[MD_MAXW + 1], sizeof(int), s->halo_scan + (c->n - base), pitch, sizeof(int), (size_t)W,
+                                     cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    } else {
+        for (int q = 0; q <= 2 * MD_MAXW + 1; ++q) h[q] = 0;
+    }
     for (int q = 0; q < W; ++q) {
         s->halo_nsend[q] = h[MD_MAXW + 1 + q] - h[q];
         s->halo_nrecv[q] = h[q + 1] - h[MD_MAXW + 1 + q];
-        s->halo_base[q] = (long long)q * nt;
+        s->halo_base[q] = (long long)q * m;
     }
     return MDSEA_OK;
 }
@@ -1625,11 +1585,12 @@ static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k,
     md_prof_begin(c);
     c->n_ke_part = g256(c->n);
     k_cut_kick_finish<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride, idr,
-                                                        c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded);
+                                                        c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded,
+                                                        md_finalize_args(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k));
     md_prof_end(c, &c->stats.ms_integrate);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
-    return md_finalize_step(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k, guarded);
+    return MDSEA_OK;
 }
 
 // After a drift the skin trigger sits in a device flag.  To keep the GPU busy while the host learns its value,

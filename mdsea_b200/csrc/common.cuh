@@ -69,6 +69,7 @@ struct StepScalars {
     unsigned long long steps_done;
     int    rebuild_flag;             // cutoff path: max displacement exceeded skin/2
     int    overflow_flag;            // capacity overflow reported by a kernel
+    unsigned finish_blocks_done;     // cut-off path: blocks of k_cut_kick_finish that have published their KE partial
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 //   finalize   : fixed-order reduction of the per-block partial sums -> mean_pe, mean_ke, temp row;
 //                temperature bookkeeping for the next step's quench
 #include "ctx.h"
+#include "finalize.cuh"
 
 #define IG_THREADS 256
 
@@ -94,56 +95,10 @@ k_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double
 }
 
 // single block; deterministic fixed-order tree over the partial sums
-__global__ void __launch_bounds__(1024)
-k_finalize(const double *__restrict__ pe_part, int n_pe,
-           const double *__restrict__ ke_part, int n_ke, double pe_factor /* lam_eps / 2 / N */,
-           double ke_factor /* 0.5 m / N */, double kb, StepScalars *__restrict__ sc, double *__restrict__ pe_rows,
-           double *__restrict__ ke_rows, double *__restrict__ temp_rows, int row, const double *__restrict__ quench_next,
-           long long step_index, int guarded) {
+__global__ void __launch_bounds__(1024) k_finalize(FinalizeArgs A, StepScalars *__restrict__ sc, int guarded) {
     __shared__ double red[32];
     if (guarded && sc->rebuild_flag) return;  // speculative launch of the cut-off path (see cells.cu)
-    double pe = 0.0, ke = 0.0;
-    {   // four independent accumulators per thread: the loads are latency-, not bandwidth-bound
-        double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-        const int st = blockDim.x;
-        int k = threadIdx.x;
-        for (; k + 3 * st < n_pe; k += 4 * st) { p0 += pe_part[k]; p1 += pe_part[k + st]; p2 += pe_part[k + 2 * st]; p3 += pe_part[k + 3 * st]; }
-        for (; k < n_pe; k += st) p0 += pe_part[k];
-        pe = (p0 + p1) + (p2 + p3);
-        p0 = p1 = p2 = p3 = 0;
-        k = threadIdx.x;
-        for (; k + 3 * st < n_ke; k += 4 * st) { p0 += ke_part[k]; p1 += ke_part[k + st]; p2 += ke_part[k + 2 * st]; p3 += ke_part[k + 3 * st]; }
-        for (; k < n_ke; k += st) p0 += ke_part[k];
-        ke = (p0 + p1) + (p2 + p3);
-    }
-    pe = md_block_sum(pe, red);
-    ke = md_block_sum(ke, red);
-    if (threadIdx.x == 0) {
-        const double mean_pe = pe * pe_factor;  // sum over unique pairs / N, simulator.py:249
-        const double mean_ke = ke * ke_factor;  // 0.5 m mean(v.v), simulator.py:244
-        pe_rows[row] = mean_pe;
-        ke_rows[row] = mean_ke;
-        temp_rows[row] = sc->temp;              // self.temp as written by update_files, simulator.py:147
-        if (!(isfinite(mean_pe) && isfinite(mean_ke)) && sc->first_nonfinite_step < 0) sc->first_nonfinite_step = step_index;
-        sc->ke_prev = mean_ke;
-        sc->ke_valid = 1;
-        sc->steps_done += 1;
-        sc->pairs_directed += sc->pairs_pending;
-        sc->pairs_pending = 0ull;
-        // quench bookkeeping for the NEXT step (simulator.py:185-195, 233-239)
-        double scale = 1.0, temp = sc->temp;
-        if (quench_next) {
-            for (int t = 0; t < 2; ++t) {
-                const double target = quench_next[t];
-                if (target == target) {  // not NaN
-                    temp = (2.0 / 3.0) * mean_ke / kb;
-                    if (temp != 0.0) scale *= sqrt(target / temp);
-                }
-            }
-        }
-        sc->temp = temp;
-        sc->scale = scale;
-    }
+    md_finalize_body(A, sc, red);
 }
 
 __global__ void k_commit_pairs(StepScalars *sc) {
@@ -237,14 +192,23 @@ int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, 
     return MDSEA_OK;
 }
 
-int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index, int guarded) {
+FinalizeArgs md_finalize_args(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index) {
     const double N = (double)c->n_global;
-    const double pe_factor = (c->pot.fast == POTF_IDEAL) ? 0.0 : c->pot.lam_eps * 0.5 / N;
-    const double ke_factor = 0.5 * c->p.mass / N;
-    const double *qn = next_row_valid ? c->d_quench + (size_t)(row + 1) * 2 : nullptr;
-    k_finalize<<<1, 1024, 0, c->stream>>>(c->d_pe_part, c->n_pe_part, c->d_ke_part, c->n_ke_part, pe_factor,
-                                         ke_factor, kb, c->d_sc, c->d_pe_rows, c->d_ke_rows, c->d_temp_rows, row, qn,
-                                         step_index, guarded);
+    FinalizeArgs A;
+    A.pe_part = c->d_pe_part; A.n_pe = c->n_pe_part;
+    A.ke_part = c->d_ke_part; A.n_ke = c->n_ke_part;
+    A.pe_factor = (c->pot.fast == POTF_IDEAL) ? 0.0 : c->pot.lam_eps * 0.5 / N;
+    A.ke_factor = 0.5 * c->p.mass / N;
+    A.kb = kb;
+    A.pe_rows = c->d_pe_rows; A.ke_rows = c->d_ke_rows; A.temp_rows = c->d_temp_rows;
+    A.row = row;
+    A.quench_next = next_row_valid ? c->d_quench + (size_t)(row + 1) * 2 : nullptr;
+    A.step_index = step_index;
+    return A;
+}
+
+int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index, int guarded) {
+    k_finalize<<<1, 1024, 0, c->stream>>>(md_finalize_args(c, row, next_row_valid, kb, step_index), c->d_sc, guarded);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;

@@ -1,3 +1,4 @@
 set -x
-A="python profiles/ab_cutoff.py fp32 20"
-$A > gpurun_out/plain_ab.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_nbr_build' -s 1 -c 1 -o gpurun_out/prof_b4 $A > gpurun_out/ncu_b4.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python profiles/ab_cutoff.py fp32 40
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['roofline']['ms_per_launch'])"
