@@ -258,19 +258,39 @@ def run_ours(args, wl):
     energy_ok = bool(np.isfinite(rows["pe"]).all() and np.isfinite(rows["ke"]).all())
 
     # ---------------- end to end through the C ABI with host buffers ----------------
-    def body_e2e():
-        ctx.set_state(r_pin, v_pin)
-        ctx.run(md_steps, kb=1.0, record=True, rows=rows)
-    body_e2e()
+    # Every step: upload the batch's initial (r, v) from pinned memory, run md_steps, copy every dataset row of the
+    # batch back into pinned host buffers.  Two batches are kept in flight (run_async / wait): the library
+    # alternates between two device ring sets, so the rows of step s cross PCIe while step s+1 is computed.  The
+    # timed region is the wall clock of all K steps including the final drain.  No L2 flush here: a flush needs a
+    # device-wide synchronisation that would serialise the pipeline, and the working set (state + neighbour list
+    # + row rings, > 1 GB at 1e6 particles) is far larger than the 126 MB L2 anyway.
+    rows_b = dict(r=pin((md_steps, ndim, width)), v=pin((md_steps, ndim, width)), pe=pin((md_steps,)), ke=pin((md_steps,)),
+                  temp=pin((md_steps,)))
+    if decomposed:
+        rows_b["ids"] = pin((md_steps, width), torch.int32)
+        rows_b["n_owned"] = pin((md_steps,), torch.int64)
+    row_sets = [rows, rows_b]
+
+    def e2e_steps(k):
+        in_flight = 0
+        for s in range(k):
+            ctx.set_state(r_pin, v_pin)
+            ctx.run(md_steps, kb=1.0, record=True, rows=row_sets[s % 2], asynchronous=True)
+            in_flight += 1
+            if in_flight == 2:
+                ctx.wait()
+                in_flight -= 1
+        while in_flight:
+            ctx.wait()
+            in_flight -= 1
+
+    e2e_steps(2)
     barrier()
     p0 = ctx.stats()["pair_evals_unique"]
-    e2e_times = []
-    for _ in range(args.steps):
-        flush_buf.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        body_e2e()
-        e2e_times.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)
+    torch.cuda.synchronize()
+    e2e_times = [time.perf_counter() - t0]
     barrier()
     e2e_pairs = ctx.stats()["pair_evals_unique"] - p0
     t_e2e = sum(e2e_times)
@@ -349,7 +369,9 @@ def run_ours(args, wl):
                        f"dd{world} grid {PROC_GRIDS.get(world)}", "list_rebuilds_in_timed_region": int(s1["list_rebuilds"] - s0["list_rebuilds"])},
             "e2e": {"value": tot_e2e_pairs / t_e2e_max, "unit": "pair-interactions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "timesteps_per_s": (1 if decomposed else world) * args.steps * md_steps / t_e2e_max,
-                    "ms_per_step": 1e3 * t_e2e_max / args.steps},
+                    "ms_per_step": 1e3 * t_e2e_max / args.steps,
+                    "pipeline": "2 batches in flight (run_async/wait): D2H of step s overlaps the compute of step s+1; "
+                                "wall clock over all K steps incl. the final drain; no L2 flush (working set >> L2)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64" if fp64 else "fp32", "kernel": "all-pairs force" if wl["r_cutoff"] <= 0 else "neighbour-list force",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

@@ -231,11 +231,14 @@ class Context:
             rw.row_stride = rows["r"].shape[2]
         fn = self.lib.mdsea_b200_run_async if asynchronous else self.lib.mdsea_b200_run
         self._ck(fn(self.h, C.byref(a), C.byref(rw)))
-        self._keep = (qbuf, rows)
+        # the library copies into `rows` asynchronously: keep the buffers of the batches in flight alive
+        self._keep = (getattr(self, "_keep", ()) + ((qbuf, rows),))[-3:]
         del E
         return rows
 
     def wait(self):
+        """Complete the OLDEST batch submitted with run(..., asynchronous=True); its row buffers are valid afterwards.
+        Up to two batches can be in flight (the library alternates between two device ring sets)."""
         self._ck(self.lib.mdsea_b200_wait(self.h))
 
     def stats(self) -> dict:

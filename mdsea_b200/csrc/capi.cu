@@ -123,7 +123,6 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
         CK(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi));
     }
     CK(cudaEventCreateWithFlags(&c->ev_batch_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev_a));
     CK(cudaEventCreate(&c->ev_b));
     CK(cudaMalloc(&c->d_pe_rows, sizeof(double) * c->ring));
@@ -145,8 +144,9 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
         CK(cudaMalloc(&c->d_v, sizeof(double) * c->E));
         CK(cudaMalloc(&c->d_acc, sizeof(double) * c->E));
         CK(cudaMemset(c->d_acc, 0, sizeof(double) * c->E));
-        CK(cudaMalloc(&c->d_r_rows, sizeof(double) * c->E * c->ring));
-        CK(cudaMalloc(&c->d_v_rows, sizeof(double) * c->E * c->ring));
+        c->coord_rows_bytes = sizeof(double) * c->E * c->ring;
+        CK(cudaMalloc(&c->d_r_rows, c->coord_rows_bytes));
+        CK(cudaMalloc(&c->d_v_rows, c->coord_rows_bytes));
         c->n_ke_part = md_div_up((long long)c->E, 256);
         CK(cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
         st = md_allpairs_setup(c);
@@ -157,6 +157,16 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
         g_err = c->err;
         mdsea_b200_destroy(c);
         return st;
+    }
+    {   // ring set 0 = what was just allocated; set 1 is allocated on first use
+        mdsea_ctx::RingSet &R = c->rings[0];
+        R.r_rows = c->d_r_rows; R.v_rows = c->d_v_rows; R.pe_rows = c->d_pe_rows; R.ke_rows = c->d_ke_rows;
+        R.temp_rows = c->d_temp_rows; R.id_rows = c->d_id_rows; R.d_quench = c->d_quench; R.h_quench = c->h_quench;
+        CK(cudaMallocHost(&R.h_sc, sizeof(StepScalars)));
+        CK(cudaMalloc(&R.d_sc_snap, sizeof(StepScalars)));
+        memcpy(R.h_sc, c->h_sc, sizeof(StepScalars));
+        CK(cudaEventCreateWithFlags(&R.ev_copy_done, cudaEventDisableTiming));
+        R.allocated = true;
     }
 #undef CK
     *out = c;
@@ -173,13 +183,20 @@ extern "C" void mdsea_b200_destroy(mdsea_ctx *c) {
     cudaFree(c->d_r); cudaFree(c->d_v); cudaFree(c->d_acc); cudaFree(c->d_fpart);
     cudaFree(c->d_pe_part); cudaFree(c->d_cnt_part); cudaFree(c->d_ke_part);
     cudaFree(c->d_rhi); cudaFree(c->d_rlo);
-    cudaFree(c->d_r_rows); cudaFree(c->d_v_rows);
-    cudaFree(c->d_pe_rows); cudaFree(c->d_ke_rows); cudaFree(c->d_temp_rows);
-    cudaFree(c->d_quench); cudaFree(c->d_sc);
+    for (int i = 0; i < 2; ++i) {
+        mdsea_ctx::RingSet &R = c->rings[i];
+        if (i == 0 && !R.allocated) {   // create() failed before the sets were registered
+            R.r_rows = c->d_r_rows; R.v_rows = c->d_v_rows; R.pe_rows = c->d_pe_rows; R.ke_rows = c->d_ke_rows;
+            R.temp_rows = c->d_temp_rows; R.id_rows = c->d_id_rows; R.d_quench = c->d_quench; R.h_quench = c->h_quench;
+        }
+        cudaFree(R.r_rows); cudaFree(R.v_rows); cudaFree(R.pe_rows); cudaFree(R.ke_rows); cudaFree(R.temp_rows); cudaFree(R.id_rows); cudaFree(R.d_quench); cudaFree(R.d_sc_snap);
+        if (R.h_quench) cudaFreeHost(R.h_quench);
+        if (R.h_sc) cudaFreeHost(R.h_sc);
+        if (R.ev_copy_done) cudaEventDestroy(R.ev_copy_done);
+    }
+    cudaFree(c->d_sc);
     if (c->h_sc) cudaFreeHost(c->h_sc);
-    if (c->h_quench) cudaFreeHost(c->h_quench);
     if (c->ev_batch_done) cudaEventDestroy(c->ev_batch_done);
-    if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -189,6 +206,38 @@ extern "C" void mdsea_b200_destroy(mdsea_ctx *c) {
 }
 
 extern "C" void *mdsea_b200_stream(mdsea_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+// drain every batch whose rows are still being copied out (oldest first)
+static int wait_all(mdsea_ctx *c) {
+    while (c->n_pending > 0) MD_TRY(mdsea_b200_wait(c));
+    return MDSEA_OK;
+}
+
+// second ring set (same sizes as the first); false if the device cannot hold it
+static bool ring_alloc_second(mdsea_ctx *c) {
+    mdsea_ctx::RingSet &R = c->rings[1];
+    if (R.allocated) return true;
+    bool ok = cudaMalloc(&R.r_rows, c->coord_rows_bytes) == cudaSuccess && cudaMalloc(&R.v_rows, c->coord_rows_bytes) == cudaSuccess &&
+              cudaMalloc(&R.pe_rows, sizeof(double) * c->ring) == cudaSuccess && cudaMalloc(&R.ke_rows, sizeof(double) * c->ring) == cudaSuccess &&
+              cudaMalloc(&R.temp_rows, sizeof(double) * c->ring) == cudaSuccess &&
+              cudaMalloc(&R.d_quench, sizeof(double) * 2 * (c->ring + 1)) == cudaSuccess &&
+              (c->id_rows_bytes == 0 || cudaMalloc(&R.id_rows, c->id_rows_bytes) == cudaSuccess) &&
+              cudaMallocHost(&R.h_sc, sizeof(StepScalars)) == cudaSuccess && cudaMalloc(&R.d_sc_snap, sizeof(StepScalars)) == cudaSuccess &&
+              cudaMallocHost(&R.h_quench, sizeof(double) * 2 * (c->ring + 1)) == cudaSuccess &&
+              cudaEventCreateWithFlags(&R.ev_copy_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        cudaFree(R.r_rows); cudaFree(R.v_rows); cudaFree(R.pe_rows); cudaFree(R.ke_rows); cudaFree(R.temp_rows); cudaFree(R.d_quench);
+        cudaFree(R.id_rows); cudaFree(R.d_sc_snap);
+        if (R.h_sc) cudaFreeHost(R.h_sc);
+        if (R.h_quench) cudaFreeHost(R.h_quench);
+        if (R.ev_copy_done) cudaEventDestroy(R.ev_copy_done);
+        R = mdsea_ctx::RingSet();
+        return false;
+    }
+    R.allocated = true;
+    return true;
+}
 
 extern "C" int mdsea_b200_set_profiling(mdsea_ctx *c, int32_t on) {
     if (!c) return MDSEA_ERR_BAD_ARG;
@@ -205,7 +254,8 @@ int md_cutoff_get_state(mdsea_ctx *c, double *r, double *v, double *a, int64_t *
 extern "C" int mdsea_b200_set_state(mdsea_ctx *c, const double *r, const double *v) {
     if (!c || !r || !v) return bad(c, "set_state: NULL argument");
     MD_CUDA(c, cudaSetDevice(c->p.device));
-    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    // no wait for batches that are still being copied out: the upload is ordered after their compute on the stream
+    // and does not touch the row rings, so a caller can pipeline set_state / run_async / wait
     if (c->cutoff_path) {
         MD_TRY(md_cutoff_set_state(c, r, v));
     } else {
@@ -234,7 +284,7 @@ extern "C" int mdsea_b200_get_state(mdsea_ctx *c, double *r, double *v, double *
     if (!c) return MDSEA_ERR_BAD_ARG;
     if (!c->have_state) { md_set_error(c, "get_state: no state set"); return MDSEA_ERR_STATE; }
     MD_CUDA(c, cudaSetDevice(c->p.device));
-    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    MD_TRY(wait_all(c));
     if (c->cutoff_path) return md_cutoff_get_state(c, r, v, a, ids, n_owned);
     if (r) MD_CUDA(c, cudaMemcpyAsync(r, c->d_r, sizeof(double) * c->E, cudaMemcpyDeviceToHost, c->stream));
     if (v) MD_CUDA(c, cudaMemcpyAsync(v, c->d_v, sizeof(double) * c->E, cudaMemcpyDeviceToHost, c->stream));
@@ -272,7 +322,7 @@ extern "C" int mdsea_b200_update_acc(mdsea_ctx *c, double *acc, double *mean_pe)
     if (!c) return MDSEA_ERR_BAD_ARG;
     if (!c->have_state) { md_set_error(c, "update_acc: no state set"); return MDSEA_ERR_STATE; }
     MD_CUDA(c, cudaSetDevice(c->p.device));
-    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    MD_TRY(wait_all(c));
     ForceSrc s;
     MD_TRY(eval_forces(c, &s));
     if (s.f != c->d_acc) MD_TRY(md_reduce_acc(c, s.f, s.nparts, s.stride));
@@ -301,7 +351,7 @@ extern "C" int mdsea_b200_update_dists(mdsea_ctx *c, double *dists, double *unit
     if (!c->have_state) { md_set_error(c, "update_dists: no state set"); return MDSEA_ERR_STATE; }
     if (c->cutoff_path || c->n > 32768) { md_set_error(c, "update_dists: only available in all-pairs mode with N <= 32768"); return MDSEA_ERR_UNSUPPORTED; }
     MD_CUDA(c, cudaSetDevice(c->p.device));
-    if (c->pending) MD_TRY(mdsea_b200_wait(c));
+    MD_TRY(wait_all(c));
     const long long P = c->n * (c->n - 1) / 2;
     double *dd = nullptr, *du = nullptr;
     MD_CUDA(c, cudaMalloc(&dd, sizeof(double) * (P > 0 ? P : 1)));
@@ -354,10 +404,20 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     // record_coords with NULL r/v: rows are buffered in the device ring but not copied out
     if (!(a->k_boltzmann > 0)) return bad(c, "run: k_boltzmann must be positive");
     MD_CUDA(c, cudaSetDevice(c->p.device));
-    if (c->pending) MD_TRY(mdsea_b200_wait(c));
 
-    // quench targets of this batch -> device
-    // (pinned staging; the previous batch has fully drained at this point, so it is free to overwrite)
+    // ---- pick the ring set of this batch (two sets alternate; the second one is allocated on first use) ----
+    if (c->n_pending == 2) MD_TRY(mdsea_b200_wait(c));   // both sets busy: the oldest batch has to drain first
+    int sel = c->ring_cur;
+    if (c->rings[sel].pending) {   // only possible while the other set does not exist yet
+        if (ring_alloc_second(c)) sel = 1;
+        else MD_TRY(wait_all(c));  // no memory for a second set: fall back to one batch in flight
+    }
+    mdsea_ctx::RingSet &R = c->rings[sel];
+    c->d_r_rows = R.r_rows; c->d_v_rows = R.v_rows; c->d_pe_rows = R.pe_rows; c->d_ke_rows = R.ke_rows;
+    c->d_temp_rows = R.temp_rows; c->d_id_rows = R.id_rows; c->d_quench = R.d_quench; c->h_quench = R.h_quench;
+    // (R.pending is false here, i.e. the copies that last read this set have completed on the host's clock)
+
+    // quench targets of this batch -> device (staging and device array belong to the ring set)
     for (int k = 0; k < 2 * (a->nsteps + 1); ++k)
         c->h_quench[k] = (a->quench_targets && k < 2 * a->nsteps) ? a->quench_targets[k] : NAN;
     MD_CUDA(c, cudaMemcpyAsync(c->d_quench, c->h_quench, sizeof(double) * 2 * (a->nsteps + 1), cudaMemcpyHostToDevice, c->stream));
@@ -368,7 +428,8 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     else MD_TRY(allpairs_steps(c, a, g_dt));
     c->stats.steps += a->nsteps;
 
-    // buffered rows -> caller (copy stream, overlaps with whatever the compute stream does next)
+    // buffered rows -> caller on the copy stream: overlaps with the compute of the NEXT batch, which uses the other set
+    MD_CUDA(c, cudaMemcpyAsync(R.d_sc_snap, c->d_sc, sizeof(StepScalars), cudaMemcpyDeviceToDevice, c->stream));  // scalars as of THIS batch
     MD_CUDA(c, cudaEventRecord(c->ev_batch_done, c->stream));
     MD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_batch_done, 0));
     const size_t rowb = sizeof(double) * (size_t)c->ndim * (size_t)c->n_global;
@@ -380,26 +441,29 @@ extern "C" int mdsea_b200_run_async(mdsea_ctx *c, const mdsea_run_args *a, const
     MD_CUDA(c, cudaMemcpyAsync(rows->pe, c->d_pe_rows, sizeof(double) * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
     MD_CUDA(c, cudaMemcpyAsync(rows->ke, c->d_ke_rows, sizeof(double) * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
     MD_CUDA(c, cudaMemcpyAsync(rows->temp, c->d_temp_rows, sizeof(double) * a->nsteps, cudaMemcpyDeviceToHost, c->copy_stream));
-    MD_CUDA(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(StepScalars), cudaMemcpyDeviceToHost, c->copy_stream));
-    MD_CUDA(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
-    // the ring is reused by the next batch: make the compute stream wait for the copies
-    MD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
-    c->pending = true;
-    c->pending_rows = *rows;
-    c->pending_nsteps = a->nsteps;
-    c->pending_record = a->record_coords;
+    MD_CUDA(c, cudaMemcpyAsync(R.h_sc, R.d_sc_snap, sizeof(StepScalars), cudaMemcpyDeviceToHost, c->copy_stream));
+    MD_CUDA(c, cudaEventRecord(R.ev_copy_done, c->copy_stream));
+    R.pending = true;
+    if (c->n_pending == 0) c->ring_oldest = sel;
+    c->n_pending += 1;
+    if (c->rings[1].allocated) c->ring_cur = sel ^ 1;
     return MDSEA_OK;
 }
 
 int md_cutoff_finish_rows(mdsea_ctx *c);
 
+// completes the OLDEST batch still in flight (its row buffers are then valid); no-op when nothing is pending
 extern "C" int mdsea_b200_wait(mdsea_ctx *c) {
     if (!c) return MDSEA_ERR_BAD_ARG;
-    if (!c->pending) return MDSEA_OK;
+    if (c->n_pending == 0) return MDSEA_OK;
     MD_CUDA(c, cudaSetDevice(c->p.device));
-    MD_CUDA(c, cudaEventSynchronize(c->ev_copy_done));
-    c->pending = false;
+    mdsea_ctx::RingSet &R = c->rings[c->ring_oldest];
+    MD_CUDA(c, cudaEventSynchronize(R.ev_copy_done));
+    R.pending = false;
+    c->n_pending -= 1;
+    c->ring_oldest ^= 1;
     if (c->cutoff_path) MD_TRY(md_cutoff_finish_rows(c));
+    memcpy(c->h_sc, R.h_sc, sizeof(StepScalars));
     c->stats.pair_evals_unique = (long long)(c->h_sc->pairs_directed >> 1);
     if (c->h_sc->overflow_flag) {
         md_set_error(c, "run: neighbour/ghost buffer capacity exceeded (raise max_neighbors)");
@@ -410,7 +474,7 @@ extern "C" int mdsea_b200_wait(mdsea_ctx *c) {
 
 extern "C" int mdsea_b200_run(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows) {
     MD_TRY(mdsea_b200_run_async(c, a, rows));
-    return mdsea_b200_wait(c);
+    return wait_all(c);
 }
 
 extern "C" int64_t mdsea_b200_rank_capacity(mdsea_ctx *c) {

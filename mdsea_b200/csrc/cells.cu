@@ -93,7 +93,6 @@ struct CellState {
     int   *scan_tmp = nullptr;
     long long halo_nsend[MD_MAXW], halo_nrecv[MD_MAXW], halo_base[MD_MAXW];
     double *halo_send = nullptr, *halo_recv = nullptr;   // packed positions, 3 doubles per entry
-    int   *id_rows = nullptr;             // [ring][cap] ids of the rows buffered on the device (world > 1)
     std::vector<long long> row_n_own;     // owned count of every buffered row
     int   *cell_end = nullptr;
     int       nc = 0, ncell = 0;
@@ -120,7 +119,8 @@ struct CellState {
     int    *cell_start = nullptr;         // ncell + 1
     int    *nbr = nullptr, *nbr_cnt = nullptr;
     double *scratch = nullptr;            // [3][N] for id-ordered downloads
-    int    *h_flag = nullptr;             // pinned
+    int    *h_flag = nullptr;             // pinned + mapped: the skin trigger is published with a store over PCIe
+    int    *d_flag_mapped = nullptr;      // device alias of h_flag
     cudaEvent_t ev_flag = nullptr;
     int     id_bits = 0, cell_bits = 0;
 };
@@ -888,6 +888,11 @@ __global__ void k_unsort(const double *__restrict__ src, const int *__restrict__
     for (int d = 0; d < 3; ++d) dst[d * n_global + gid] = src[d * cap + i];
 }
 
+// The host learns the skin trigger through a store into mapped pinned memory instead of a D2H memcpy: a copy would
+// queue on the copy engine behind the bulk row transfers of the previous batch (run_async pipelining) and stall
+// every step for milliseconds.
+__global__ void k_publish_flag(const StepScalars *__restrict__ sc, int *__restrict__ host_flag) { *host_flag = sc->rebuild_flag; }
+
 __global__ void k_iota(int *a, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = (int)i;
@@ -1204,13 +1209,15 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
     MD_CUDA(c, cudaMalloc(&s->nbr_cnt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->d_cnt, sizeof(int) * (MD_MAXW + 8)));
-    MD_CUDA(c, cudaMallocHost(&s->h_flag, sizeof(int) * 4));
+    MD_CUDA(c, cudaHostAlloc(&s->h_flag, sizeof(int) * 4, cudaHostAllocMapped));
+    MD_CUDA(c, cudaHostGetDevicePointer((void **)&s->d_flag_mapped, s->h_flag, 0));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_drift, cudaEventDisableTiming));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_flag, cudaEventDisableTiming));
     MD_CUDA(c, cudaMallocHost(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8)));
     const size_t row_stride = W == 1 ? (size_t)N : (size_t)s->cap;
-    MD_CUDA(c, cudaMalloc(&c->d_r_rows, sizeof(double) * 3 * row_stride * c->ring));
-    MD_CUDA(c, cudaMalloc(&c->d_v_rows, sizeof(double) * 3 * row_stride * c->ring));
+    c->coord_rows_bytes = sizeof(double) * 3 * row_stride * c->ring;
+    MD_CUDA(c, cudaMalloc(&c->d_r_rows, c->coord_rows_bytes));
+    MD_CUDA(c, cudaMalloc(&c->d_v_rows, c->coord_rows_bytes));
     c->n_ke_part = md_div_up(s->cap, 256);
     MD_CUDA(c, cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
     MD_CUDA(c, cudaMemset(c->d_ke_part, 0, sizeof(double) * c->n_ke_part));
@@ -1228,7 +1235,8 @@ int md_cells_setup(mdsea_ctx *c) {
         MD_CUDA(c, cudaMalloc(&s->halo_idx, sizeof(int) * (size_t)W * s->cap));
         MD_CUDA(c, cudaMalloc(&s->halo_send, sizeof(double) * (3 * (size_t)s->cap * std::min(W - 1, 3) + MD_MAXW)));
         MD_CUDA(c, cudaMalloc(&s->halo_recv, sizeof(double) * (3 * (size_t)s->cap + MD_MAXW)));
-        MD_CUDA(c, cudaMalloc(&s->id_rows, sizeof(int) * (size_t)s->cap * c->ring));
+        c->id_rows_bytes = sizeof(int) * (size_t)s->cap * c->ring;
+        MD_CUDA(c, cudaMalloc(&c->d_id_rows, c->id_rows_bytes));
         s->row_n_own.assign(c->ring, 0);
     }
     c->n = 0;
@@ -1246,7 +1254,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
     cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
-    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->id_rows);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
@@ -1580,7 +1588,7 @@ static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k,
     const size_t row_stride = W == 1 ? (size_t)c->n_global : (size_t)s->cap;
     double *rr = a->record_coords ? c->d_r_rows + (size_t)k * 3 * row_stride : nullptr;
     double *vr = a->record_coords ? c->d_v_rows + (size_t)k * 3 * row_stride : nullptr;
-    int *idr = (a->record_coords && W > 1) ? s->id_rows + (size_t)k * s->cap : nullptr;
+    int *idr = (a->record_coords && W > 1) ? c->d_id_rows + (size_t)k * s->cap : nullptr;
     if (W > 1) s->row_n_own[k] = c->n;
     md_prof_begin(c);
     c->n_ke_part = g256(c->n);
@@ -1607,12 +1615,12 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
     }
     const long long fe0 = c->stats.force_evals;
     if (W == 1) {
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        k_publish_flag<<<1, 1, 0, c->stream>>>(c->d_sc, s->d_flag_mapped);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
         MD_TRY(cutoff_force(c, 1));
     } else if (c->profiling) {  // per-family timers need everything on one stream: no overlap
         MD_TRY(halo_exchange(c, c->stream));
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        k_publish_flag<<<1, 1, 0, c->stream>>>(c->d_sc, s->d_flag_mapped);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
         MD_TRY(cutoff_force(c, 1));
     } else {
@@ -1620,7 +1628,7 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
         MD_CUDA(c, cudaEventRecord(s->ev_drift, c->stream));
         MD_CUDA(c, cudaStreamWaitEvent(c->comm_stream, s->ev_drift, 0));
         MD_TRY(halo_exchange(c, c->comm_stream));
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, &c->d_sc->rebuild_flag, sizeof(int), cudaMemcpyDeviceToHost, c->comm_stream));
+        k_publish_flag<<<1, 1, 0, c->comm_stream>>>(c->d_sc, s->d_flag_mapped);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
         const int gi = force_grid(0, s->n_int > 0 ? s->n_int : 1);
         c->n_pe_part = gi + force_grid(s->n_int, c->n > s->n_int ? c->n : s->n_int + 1);
@@ -1692,7 +1700,7 @@ int md_cutoff_copy_rows(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows 
             MD_CUDA(c, cudaMemcpyAsync(rows->v + ((size_t)k * 3 + d) * st, c->d_v_rows + ((size_t)k * 3 + d) * s->cap, sizeof(double) * n,
                                        cudaMemcpyDeviceToHost, c->copy_stream));
         }
-        MD_CUDA(c, cudaMemcpyAsync(rows->ids + (size_t)k * st, s->id_rows + (size_t)k * s->cap, sizeof(int) * n, cudaMemcpyDeviceToHost,
+        MD_CUDA(c, cudaMemcpyAsync(rows->ids + (size_t)k * st, c->d_id_rows + (size_t)k * s->cap, sizeof(int) * n, cudaMemcpyDeviceToHost,
                                    c->copy_stream));
     }
     return MDSEA_OK;

@@ -22,7 +22,7 @@ struct mdsea_ctx {
     cudaStream_t stream = nullptr;       // compute stream
     cudaStream_t copy_stream = nullptr;  // D2H of buffered rows
     cudaStream_t comm_stream = nullptr;  // halo refresh, overlapped with the interior force kernel
-    cudaEvent_t  ev_batch_done = nullptr, ev_copy_done = nullptr;
+    cudaEvent_t  ev_batch_done = nullptr;
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
 
     // state, SoA (ndim, n) float64
@@ -38,10 +38,24 @@ struct mdsea_ctx {
     // fp32 hi/lo split of the positions for the fp32 all-pairs kernel
     float  *d_rhi = nullptr, *d_rlo = nullptr;
 
-    // ring buffer of rows
+    // ring buffer of rows.  Two ring sets alternate between consecutive run_async calls, so the D2H copies of one
+    // batch (copy stream) overlap the compute of the next; the pointers below alias the set of the CURRENT batch.
+    // The second set is allocated on first use (a batch submitted while another one is still being copied out).
     int     ring = 0;
     double *d_r_rows = nullptr, *d_v_rows = nullptr;  // [ring][E]
     double *d_pe_rows = nullptr, *d_ke_rows = nullptr, *d_temp_rows = nullptr;  // [ring]
+    int    *d_id_rows = nullptr;                      // [ring][cap] particle ids of the buffered rows (world > 1)
+    struct RingSet {
+        double *r_rows = nullptr, *v_rows = nullptr, *pe_rows = nullptr, *ke_rows = nullptr, *temp_rows = nullptr;
+        int    *id_rows = nullptr;
+        double *d_quench = nullptr, *h_quench = nullptr;  // quench targets of the batch (device array, pinned staging)
+        StepScalars *h_sc = nullptr;                  // pinned mirror of the scalars at the end of the batch
+        StepScalars *d_sc_snap = nullptr;             // device snapshot taken on the compute stream at the end of the batch
+        cudaEvent_t  ev_copy_done = nullptr;
+        bool    allocated = false, pending = false;
+    } rings[2];
+    size_t  coord_rows_bytes = 0, id_rows_bytes = 0;  // sizes of r_rows / v_rows and id_rows of one set
+    int     ring_cur = 0, ring_oldest = 0, n_pending = 0;
     double *d_quench = nullptr;                       // [ring][2]
     StepScalars *d_sc = nullptr;
     StepScalars *h_sc = nullptr;                      // pinned mirror
@@ -51,11 +65,6 @@ struct mdsea_ctx {
     CellState  *cells = nullptr;
     CommState  *comm = nullptr;
 
-    // pending async run
-    bool       pending = false;
-    mdsea_rows pending_rows;
-    int        pending_nsteps = 0;
-    int        pending_record = 0;
 };
 
 void md_set_error(mdsea_ctx *ctx, const char *msg);

@@ -149,12 +149,19 @@ class _BaseSimulator:
                 sm._open_datafile()
         self._ctx.set_temperature(self.temp, reset_ke=self.mean_ke is None)
         width = n if self._world == 1 else self._ctx.rank_capacity()
-        self._rows = dict(r=_pinned_empty((k, nd, width)), v=_pinned_empty((k, nd, width)),
-                          pe=_pinned_empty((k,)), ke=_pinned_empty((k,)), temp=_pinned_empty((k,)))
-        if self._world > 1:
-            self._rows["ids"] = np.full((k, width), -1, dtype=np.int32)
-            self._rows["n_owned"] = np.zeros(k, dtype=np.int64)
+        self._rows_width = width
+        self._rows = self._new_rows()
+        self._rows_alt = None   # second host buffer set, created when run_simulation pipelines more than one batch
         return self._ctx
+
+    def _new_rows(self) -> dict:
+        k, nd, width = self._k, self.sm.NDIM, self._rows_width
+        rows = dict(r=_pinned_empty((k, nd, width)), v=_pinned_empty((k, nd, width)),
+                    pe=_pinned_empty((k,)), ke=_pinned_empty((k,)), temp=_pinned_empty((k,)))
+        if self._world > 1:
+            rows["ids"] = np.full((k, width), -1, dtype=np.int32)
+            rows["n_owned"] = np.zeros(k, dtype=np.int64)
+        return rows
 
     def _sync_to_device(self):
         ctx = self._ensure_ctx()
@@ -301,18 +308,27 @@ class ContinuousPotentialSolver(_BaseSimulator):
                 log.warning("Cannot update the temperature without first evaluating the mean kinetic energy.")
         return q if not np.isnan(q).all() else None
 
-    def _run_batch(self, first_step: int, nsteps: int, record: bool):
+    def _submit_batch(self, first_step: int, nsteps: int, record: bool, rows: dict):
+        """Enqueue `nsteps` steps; the rows land in `rows` once the batch has been completed with _complete_batch."""
         if self.apply_restcoeff:
             raise NotImplementedError  # apply_collision_damping, simulator.py:546-548,565-566
         ctx = self._sync_to_device()
         q = self._quench_targets(first_step, nsteps)
         g = Config.gravity_acceleration if self.gravity else 0.0
-        rows = ctx.run(nsteps, kb=Config.k_boltzmann, g=g, quench=q, record=record, rows=self._rows)
+        ctx.run(nsteps, kb=Config.k_boltzmann, g=g, quench=q, record=record, rows=rows, asynchronous=True)
         self._device_fresh = True
+
+    def _complete_batch(self, nsteps: int, rows: dict):
+        self._ctx.wait()   # oldest batch in flight
         self.mean_pe = float(rows["pe"][nsteps - 1])
         self.mean_ke = float(rows["ke"][nsteps - 1])
         self.temp = float(rows["temp"][nsteps - 1])
         return rows
+
+    def _run_batch(self, first_step: int, nsteps: int, record: bool):
+        self._ensure_ctx()
+        self._submit_batch(first_step, nsteps, record, self._rows)
+        return self._complete_batch(nsteps, self._rows)
 
     def advance(self):
         """Advance the simulation one step (simulator.py:560-568)."""
@@ -326,24 +342,41 @@ class ContinuousPotentialSolver(_BaseSimulator):
             self.update_files()
         self.pbarr.set_start()
         self._ensure_ctx()
+        # Two batches in flight: while batch b is being computed, the rows of batch b-1 travel to the host (the
+        # library alternates between two device ring sets) and are written into the datasets.
+        def store(first: int, n: int, rows: dict) -> None:
+            self._complete_batch(n, rows)
+            if self._world > 1:
+                if not sm.dfile.id.valid:
+                    sm._open_datafile()
+                parallel.scatter_rows(sm, rows, n, first, self._rank)
+            else:
+                sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], first)
+                sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], first)
+                sm.update_ds_block(sm.potenergy_dsname, rows["pe"][:n], first)
+                sm.update_ds_block(sm.kinenergy_dsname, rows["ke"][:n], first)
+                sm.update_ds_block(sm.temp_dsname, rows["temp"][:n], first)
+            self.step = first + n - 1
+
         s = simrange.start
+        if s + self._k < sm.STEPS and self._rows_alt is None:
+            self._rows_alt = self._new_rows()
+        bufs = [self._rows, self._rows_alt]
+        in_flight = None
+        b = 0
         while s < sm.STEPS:
             n = min(self._k, sm.STEPS - s)
             for i in range(s, s + n):
                 self.pbarr.log_progress(i)
-            rows = self._run_batch(s, n, record=True)
-            if self._world > 1:
-                if not sm.dfile.id.valid:
-                    sm._open_datafile()
-                parallel.scatter_rows(sm, rows, n, s, self._rank)
-            else:
-                sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], s)
-                sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], s)
-                sm.update_ds_block(sm.potenergy_dsname, rows["pe"][:n], s)
-                sm.update_ds_block(sm.kinenergy_dsname, rows["ke"][:n], s)
-                sm.update_ds_block(sm.temp_dsname, rows["temp"][:n], s)
+            rows = bufs[b % 2] if bufs[1] is not None else bufs[0]
+            self._submit_batch(s, n, True, rows)
+            if in_flight is not None:
+                store(*in_flight)
+            in_flight = (s, n, rows)
             s += n
-            self.step = s - 1
+            b += 1
+        if in_flight is not None:
+            store(*in_flight)
         bad = self._ctx.first_nonfinite_step()
         if bad >= 0:
             log.warning("Non-finite energies from step %d on (the reference writes NaN rows silently as well; "

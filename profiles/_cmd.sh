@@ -1,4 +1,4 @@
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python profiles/ab_cutoff.py fp32 40
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['roofline']['ms_per_launch'])"
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra 2>gpurun_out/b.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['roofline']['ms_per_launch'])"
+tail -3 gpurun_out/b.err
