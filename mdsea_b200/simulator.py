@@ -326,6 +326,8 @@ class ContinuousPotentialSolver(_BaseSimulator):
         return rows
 
     def _run_batch(self, first_step: int, nsteps: int, record: bool):
+        if self.apply_restcoeff:
+            raise NotImplementedError  # before any device work, like the reference (simulator.py:565-566)
         self._ensure_ctx()
         self._submit_batch(first_step, nsteps, record, self._rows)
         return self._complete_batch(nsteps, self._rows)
