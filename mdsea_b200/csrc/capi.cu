@@ -465,6 +465,10 @@ extern "C" int mdsea_b200_wait(mdsea_ctx *c) {
     if (c->cutoff_path) MD_TRY(md_cutoff_finish_rows(c));
     memcpy(c->h_sc, R.h_sc, sizeof(StepScalars));
     c->stats.pair_evals_unique = (long long)(c->h_sc->pairs_directed >> 1);
+    if (c->h_sc->overflow_flag == 2) {
+        md_set_error(c, "run: timed out waiting for a neighbour rank's halo data (peer-memory transport)");
+        return MDSEA_ERR_NCCL;
+    }
     if (c->h_sc->overflow_flag) {
         md_set_error(c, "run: neighbour/ghost buffer capacity exceeded (raise max_neighbors)");
         return MDSEA_ERR_CAPACITY;

@@ -88,11 +88,22 @@ struct CellState {
     PMsg  *sendpool = nullptr, *recvpool = nullptr;
     long long sendpool_cap = 0;
     int   *d_cnt = nullptr, *d_cnt_all = nullptr, *d_cursor = nullptr;  // [MAXW], [MAXW*MAXW], [MAXW]
-    int   *h_cnt_all = nullptr;           // pinned [MAXW*MAXW + 8]
+    int   *h_cnt_all = nullptr;           // pinned + mapped [MAXW*MAXW + 8]: small read-backs of the rebuild (k_peek)
+    int   *d_cnt_all_mapped = nullptr;    // device alias of h_cnt_all
     int   *halo_flag = nullptr, *halo_scan = nullptr, *halo_idx = nullptr;  // [world][cap]
     int   *scan_tmp = nullptr;
     long long halo_nsend[MD_MAXW], halo_nrecv[MD_MAXW], halo_base[MD_MAXW];
     double *halo_send = nullptr, *halo_recv = nullptr;   // packed positions, 3 doubles per entry
+    // peer-memory halo (NCCL transport on one node): every rank exposes p2p_buf = [2 parities][p2p_stride doubles] +
+    // [MD_MAXW arrival counters]; the neighbours' kernels store positions and counters straight into it over NVLink
+    bool      p2p = false;
+    double   *p2p_buf = nullptr;
+    double   *stage_r = nullptr, *stage_v = nullptr;   // set_state staging of the global arrays (world > 1)
+    long long p2p_stride = 0;
+    double   *peer_buf[MD_MAXW];
+    long long peer_off[MD_MAXW];          // where this rank's segment starts inside peer q's receive buffer (doubles)
+    int      *d_nsend = nullptr, *d_nsend_all = nullptr;
+    unsigned long long halo_seq = 0;      // exchanges done so far (identical on all ranks)
     std::vector<long long> row_n_own;     // owned count of every buffered row
     int   *cell_end = nullptr;
     int       nc = 0, ncell = 0;
@@ -893,6 +904,13 @@ __global__ void k_unsort(const double *__restrict__ src, const int *__restrict__
 // every step for milliseconds.
 __global__ void k_publish_flag(const StepScalars *__restrict__ sc, int *__restrict__ host_flag) { *host_flag = sc->rebuild_flag; }
 
+// Small device -> host read-backs of the rebuild (counts, class boundaries) are stores into mapped pinned memory for
+// the same reason: dst[i] = src[i * stride].
+__global__ void k_peek(const int *__restrict__ src, long long stride, int n, int *__restrict__ host_dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) host_dst[i] = src[(long long)i * stride];
+}
+
 __global__ void k_iota(int *a, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = (int)i;
@@ -1073,9 +1091,29 @@ __global__ void k_halo_pack(const double *__restrict__ r, long long cap, const i
         if (q != T.rank) buf[3 * T.ent0[q + 1] + q] = (double)sc->rebuild_flag;
     }
 }
+// Arrival counters: rank p bumps counter[p] in rank q's buffer to `seq` after its stores of exchange number `seq`.
+// The consumer polls its OWN memory.  A bounded spin (about 4 s) reports a comm error instead of hanging the GPU.
+struct HaloWait {
+    const unsigned long long *counters;   // nullptr: data came through ncclRecv, nothing to wait for
+    unsigned long long        seq;
+};
+__device__ __forceinline__ void halo_wait_arrivals(const HaloWait &Wt, int world, int rank, StepScalars *__restrict__ sc) {
+    if (!Wt.counters) return;
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+        const volatile unsigned long long *f = Wt.counters + threadIdx.x;
+        const long long t0 = clock64();
+        while (*f < Wt.seq) {
+            if (clock64() - t0 > 8000000000LL) { sc->overflow_flag = 2; break; }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
 __global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restrict__ idx, HaloTab T, long long cap,
                               double *__restrict__ r, int fp32, double inv_h, void *__restrict__ pos4,
-                              StepScalars *__restrict__ sc) {
+                              StepScalars *__restrict__ sc, HaloWait Wt) {
+    halo_wait_arrivals(Wt, T.world, T.rank, sc);
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = T.ent0[T.world];
     if (k < total) {
@@ -1083,14 +1121,41 @@ __global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restr
         const long long l = k - T.ent0[q];
         const int s = idx[T.idx0[q] + l];
         const double *m = buf + 3 * T.ent0[q] + q;
-        const double x = m[3 * l], y = m[3 * l + 1], z = m[3 * l + 2];
+        const double x = __ldcg(m + 3 * l), y = __ldcg(m + 3 * l + 1), z = __ldcg(m + 3 * l + 2);
         r[s] = x; r[cap + s] = y; r[2 * cap + s] = z;
         if (fp32) ((uint4 *)pos4)[s] = make_uint4(md_to_fixed(x, inv_h), md_to_fixed(y, inv_h), md_to_fixed(z, inv_h), 0u);
         else ((double4 *)pos4)[s] = make_double4(x, y, z, 0.0);
     } else if (k < total + T.world) {
         const int q = (int)(k - total);
-        if (q != T.rank && buf[3 * T.ent0[q + 1] + q] != 0.0) sc->rebuild_flag = 1;
+        if (q != T.rank && __ldcg(buf + 3 * T.ent0[q + 1] + q) != 0.0) sc->rebuild_flag = 1;
     }
+}
+
+// fused pack + transfer: the owned boundary positions (and this rank's skin-trigger flag) are stored straight into
+// the receive buffers of the ranks that hold them as ghosts -- no staging buffer, no ncclSend/ncclRecv
+struct PeerDst { double *seg[MD_MAXW]; };   // start of this rank's segment inside peer q's receive buffer
+__global__ void k_halo_push(const double *__restrict__ r, long long cap, const int *__restrict__ idx, HaloTab T,
+                            const StepScalars *__restrict__ sc, PeerDst P) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = T.ent0[T.world];
+    if (k < total) {
+        const int q = halo_peer_of(T, k);
+        const long long l = k - T.ent0[q];
+        const int s = idx[T.idx0[q] + l];
+        double *m = P.seg[q];
+        m[3 * l] = r[s];
+        m[3 * l + 1] = r[cap + s];
+        m[3 * l + 2] = r[2 * cap + s];
+    } else if (k < total + T.world) {
+        const int q = (int)(k - total);
+        if (q != T.rank) P.seg[q][3 * (T.ent0[q + 1] - T.ent0[q])] = (double)sc->rebuild_flag;
+    }
+}
+struct PeerCnt { unsigned long long *cnt[MD_MAXW]; };   // counter[this rank] inside peer q's buffer
+__global__ void k_halo_signal(PeerCnt P, int world, int rank, unsigned long long seq) {
+    __threadfence_system();   // the stores of k_halo_push (previous kernel on this stream) are visible system-wide first
+    const int q = threadIdx.x;
+    if (q < world && q != rank) *(volatile unsigned long long *)P.cnt[q] = seq;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1213,7 +1278,8 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaHostGetDevicePointer((void **)&s->d_flag_mapped, s->h_flag, 0));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_drift, cudaEventDisableTiming));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_flag, cudaEventDisableTiming));
-    MD_CUDA(c, cudaMallocHost(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8)));
+    MD_CUDA(c, cudaHostAlloc(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8), cudaHostAllocMapped));
+    MD_CUDA(c, cudaHostGetDevicePointer((void **)&s->d_cnt_all_mapped, s->h_cnt_all, 0));
     const size_t row_stride = W == 1 ? (size_t)N : (size_t)s->cap;
     c->coord_rows_bytes = sizeof(double) * 3 * row_stride * c->ring;
     MD_CUDA(c, cudaMalloc(&c->d_r_rows, c->coord_rows_bytes));
@@ -1254,7 +1320,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
     cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
-    cudaFree(s->halo_send); cudaFree(s->halo_recv);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_nsend); cudaFree(s->d_nsend_all); cudaFree(s->stage_r); cudaFree(s->stage_v);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
@@ -1277,18 +1343,21 @@ int md_cutoff_set_state(mdsea_ctx *c, const double *r, const double *v) {
         c->n = N;
     } else {
         if (!c->comm) { md_set_error(c, "set_state: world > 1 needs comm_init first"); return MDSEA_ERR_STATE; }
-        double *rg = nullptr, *vg = nullptr;
-        MD_CUDA(c, cudaMalloc(&rg, sizeof(double) * 3 * N));
-        MD_CUDA(c, cudaMalloc(&vg, sizeof(double) * 3 * N));
+        // persistent staging of the full arrays (allocating / freeing per call would synchronise the whole device,
+        // including the row copies of a batch that is still in flight)
+        if (!s->stage_r) {
+            MD_CUDA(c, cudaMalloc(&s->stage_r, sizeof(double) * 3 * N));
+            MD_CUDA(c, cudaMalloc(&s->stage_v, sizeof(double) * 3 * N));
+        }
+        double *rg = s->stage_r, *vg = s->stage_v;
         MD_CUDA(c, cudaMemcpyAsync(rg, r, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
         MD_CUDA(c, cudaMemcpyAsync(vg, v, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
         MD_CUDA(c, cudaMemsetAsync(s->d_cnt, 0, sizeof(int), c->stream));
         k_select_owned<<<g256(N), 256, 0, c->stream>>>(rg, vg, N, c->box.L, s->cell_len, s->nc, s->D, s->cap, c->d_r, c->d_v,
                                                        s->id, s->d_cnt);
         c->stats.kernel_launches += 1;
-        MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        k_peek<<<1, 32, 0, c->stream>>>(s->d_cnt, 1, 1, s->d_flag_mapped);
         MD_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(rg); cudaFree(vg);
         if (s->h_flag[0] > s->cap) { md_set_error(c, "set_state: particle capacity of this rank exceeded"); return MDSEA_ERR_CAPACITY; }
         c->n = s->h_flag[0];
     }
@@ -1311,7 +1380,7 @@ static int mr_assemble(mdsea_ctx *c) {
     k_mr_route<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, 0, s->d_cnt,
                                                none);
     MD_TRY(md_comm_allgather_i32(c, s->d_cnt, MD_MAXW, s->d_cnt_all));
-    MD_CUDA(c, cudaMemcpyAsync(s->h_cnt_all, s->d_cnt_all, sizeof(int) * MD_MAXW * W, cudaMemcpyDeviceToHost, c->stream));
+    k_peek<<<md_div_up(MD_MAXW * W, 256), 256, 0, c->stream>>>(s->d_cnt_all, 1, MD_MAXW * W, s->d_cnt_all_mapped);
     MD_CUDA(c, cudaMemsetAsync(s->d_cursor, 0, sizeof(int) * MD_MAXW, c->stream));
     MD_CUDA(c, cudaStreamSynchronize(c->stream));
     long long soff[MD_MAXW + 1], roff[MD_MAXW + 1];
@@ -1358,12 +1427,9 @@ static int build_halo_lists(mdsea_ctx *c) {
     // list sizes from the scan at the segment starts (A) and at the owned/ghost split of each segment (B):
     // two strided copies (one int per segment)
     int *h = s->h_cnt_all;  // pinned scratch, >= 2 * MD_MAXW + 1 ints
-    const size_t pitch = sizeof(int) * (size_t)(m > 0 ? m : 1);
     if (m > 0) {
-        MD_CUDA(c, cudaMemcpy2DAsync(&h[0], sizeof(int), s->halo_scan, pitch, sizeof(int), (size_t)W + 1, cudaMemcpyDeviceToHost,
-                                     c->stream));
-        MD_CUDA(c, cudaMemcpy2DAsync(&h[MD_MAXW + 1], sizeof(int), s->halo_scan + (c->n - base), pitch, sizeof(int), (size_t)W,
-                                     cudaMemcpyDeviceToHost, c->stream));
+        k_peek<<<1, 64, 0, c->stream>>>(s->halo_scan, m, W + 1, s->d_cnt_all_mapped);
+        k_peek<<<1, 64, 0, c->stream>>>(s->halo_scan + (c->n - base), m, W, s->d_cnt_all_mapped + MD_MAXW + 1);
         MD_CUDA(c, cudaStreamSynchronize(c->stream));
     } else {
         for (int q = 0; q <= 2 * MD_MAXW + 1; ++q) h[q] = 0;
@@ -1373,6 +1439,42 @@ static int build_halo_lists(mdsea_ctx *c) {
         s->halo_nrecv[q] = h[q + 1] - h[MD_MAXW + 1 + q];
         s->halo_base[q] = (long long)q * m;
     }
+    if (s->p2p) {
+        // where does my segment start inside peer q's receive buffer?  q lays its buffer out by source rank:
+        // offset(q <- me) = 3 * sum_{p < me, p != q} N[p][q] + me, with N[p][q] = entries p sends to q (all-gathered)
+        int hs[MD_MAXW];
+        for (int q = 0; q < MD_MAXW; ++q) hs[q] = q < W && q != c->p.rank ? (int)s->halo_nsend[q] : 0;
+        MD_CUDA(c, cudaMemcpyAsync(s->d_nsend, hs, sizeof(int) * MD_MAXW, cudaMemcpyHostToDevice, c->stream));
+        MD_TRY(md_comm_allgather_i32(c, s->d_nsend, MD_MAXW, s->d_nsend_all));
+        int *N = s->h_cnt_all;   // pinned, MD_MAXW * MD_MAXW ints
+        k_peek<<<md_div_up(MD_MAXW * W, 256), 256, 0, c->stream>>>(s->d_nsend_all, 1, MD_MAXW * W, s->d_cnt_all_mapped);
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int q = 0; q < W; ++q) {
+            long long off = 0;
+            for (int p = 0; p < c->p.rank; ++p)
+                if (p != q) off += N[p * MD_MAXW + q];
+            s->peer_off[q] = 3 * off + c->p.rank;
+        }
+    }
+    return MDSEA_OK;
+}
+
+// called by comm_init once the communicator exists: map every peer's receive buffer (CUDA IPC over NVLink).  Any
+// failure (peer access impossible, MDSEA_HALO=nccl) leaves the ncclSend/ncclRecv path in place, on all ranks alike.
+int md_cells_comm_ready(mdsea_ctx *c) {
+    CellState *s = c->cells;
+    if (!s || c->p.world < 2 || md_comm_backend(c) != 1) return MDSEA_OK;
+    if (getenv("MDSEA_HALO") && !strcmp(getenv("MDSEA_HALO"), "nccl")) return MDSEA_OK;
+    s->p2p_stride = 3 * s->cap + MD_MAXW;
+    const size_t bytes = sizeof(double) * 2 * (size_t)s->p2p_stride + sizeof(unsigned long long) * (MD_MAXW + 2);
+    MD_CUDA(c, cudaMalloc(&s->p2p_buf, bytes));
+    MD_CUDA(c, cudaMemset(s->p2p_buf, 0, bytes));
+    MD_CUDA(c, cudaMalloc(&s->d_nsend, sizeof(int) * MD_MAXW));
+    MD_CUDA(c, cudaMalloc(&s->d_nsend_all, sizeof(int) * MD_MAXW * MD_MAXW));
+    const int st = md_comm_share_buffer(c, s->p2p_buf, (void **)s->peer_buf);
+    if (st == MDSEA_ERR_UNSUPPORTED) return MDSEA_OK;   // keep NCCL send/recv
+    if (st != MDSEA_OK) return st;
+    s->p2p = true;
     return MDSEA_OK;
 }
 
@@ -1399,10 +1501,32 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
         sb[q] = q == me ? 0 : sizeof(double) * (3 * (size_t)s->halo_nsend[q] + 1);
         rbytes[q] = q == me ? 0 : sizeof(double) * (3 * (size_t)s->halo_nrecv[q] + 1);
     }
-    k_halo_pack<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, s->halo_send);
-    MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes, st));
-    k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->halo_recv, s->halo_idx, tr, s->cap, c->d_r,
-                                                        c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc);
+    if (s->p2p) {
+        const unsigned long long seq = ++s->halo_seq;
+        const long long par = (long long)(seq & 1ull) * s->p2p_stride;
+        PeerDst pd;
+        PeerCnt pc;
+        for (int q = 0; q < MD_MAXW; ++q) {
+            pd.seg[q] = q < W && q != me ? s->peer_buf[q] + par + s->peer_off[q] : nullptr;
+            pc.cnt[q] = q < W && q != me ? (unsigned long long *)(s->peer_buf[q] + 2 * s->p2p_stride) + me : nullptr;
+        }
+        HaloWait wt;
+        wt.counters = (const unsigned long long *)(s->p2p_buf + 2 * s->p2p_stride);
+        wt.seq = seq;
+        k_halo_push<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, pd);
+        k_halo_signal<<<1, 32, 0, st>>>(pc, W, me, seq);
+        k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->p2p_buf + par, s->halo_idx, tr, s->cap, c->d_r,
+                                                            c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt);
+        c->stats.kernel_launches += 1;
+    } else {
+        HaloWait wt;
+        wt.counters = nullptr;
+        wt.seq = 0;
+        k_halo_pack<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, s->halo_send);
+        MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes, st));
+        k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->halo_recv, s->halo_idx, tr, s->cap, c->d_r,
+                                                            c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt);
+    }
     c->stats.kernel_launches += 2;
     if (st == c->stream) md_prof_end(c, &c->stats.ms_comm);
     MD_CUDA(c, cudaGetLastError());
@@ -1454,8 +1578,7 @@ static int rebuild(mdsea_ctx *c) {
                                                      c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, s->qfix);
         launches += 3;
         if (W > 1)   // owned interior | owned boundary | ghost: the class boundaries are bucket starts
-            MD_CUDA(c, cudaMemcpy2DAsync(s->h_flag, sizeof(int), s->bstart + s->ncell, sizeof(int) * (size_t)s->ncell, sizeof(int), 2,
-                                         cudaMemcpyDeviceToHost, c->stream));
+            k_peek<<<1, 32, 0, c->stream>>>(s->bstart + s->ncell, s->ncell, 2, s->d_cnt_all_mapped);
     } else {
         MD_CUDA(c, cudaMemsetAsync(s->d_cnt + MD_MAXW, 0, 2 * sizeof(int), c->stream));
         k_cell_keys<<<g256(nt), 256, 0, c->stream>>>(src_r, src_id, nt, s->cap, c->box.L, s->cell_len, s->nc, s->D, s->key, s->val,
@@ -1483,7 +1606,7 @@ static int rebuild(mdsea_ctx *c) {
                                                           s->qfix);
         launches += 4;
         if (W > 1)   // {owned, owned interior}
-            MD_CUDA(c, cudaMemcpyAsync(s->h_flag, s->d_cnt + MD_MAXW, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            k_peek<<<1, 32, 0, c->stream>>>(s->d_cnt + MD_MAXW, 1, 2, s->d_cnt_all_mapped);
     }
     if (W == 1) {
         std::swap(c->d_r, s->r_alt);
@@ -1491,8 +1614,8 @@ static int rebuild(mdsea_ctx *c) {
         std::swap(s->id, s->id_alt);
     } else {
         MD_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (s->radix_binning) { c->n = s->h_flag[0]; s->n_int = s->h_flag[1]; }
-        else { s->n_int = s->h_flag[0]; c->n = s->h_flag[1]; }
+        if (s->radix_binning) { c->n = s->h_cnt_all[0]; s->n_int = s->h_cnt_all[1]; }
+        else { s->n_int = s->h_cnt_all[0]; c->n = s->h_cnt_all[1]; }
         c->stats.n_local = c->n;
         c->stats.n_ghost = nt - c->n;
     }

@@ -18,6 +18,8 @@
 #include "ctx.h"
 #include "comm.h"
 
+int md_cells_comm_ready(mdsea_ctx *c);  // cells.cu: peer-memory halo set-up once the communicator exists
+
 struct LocalGroup {
     int               world = 0;
     pthread_barrier_t bar;
@@ -35,6 +37,7 @@ struct CommState {
     long long   key = 0;
     double     *h_tmp = nullptr;  // pinned scratch for the LOCAL reductions
     size_t      h_tmp_bytes = 0;
+    std::vector<void *> ipc_mapped;  // peer buffers mapped with cudaIpcOpenMemHandle
 };
 
 // NCCL is bound at run time (dlopen) instead of at link time: a process that also imports PyTorch must end up
@@ -123,7 +126,7 @@ extern "C" int mdsea_b200_comm_init(mdsea_ctx *c, const void *unique_id128) {
     }
     s->backend = 1;
     c->comm = s;
-    return MDSEA_OK;
+    return md_cells_comm_ready(c);
 }
 
 extern "C" int mdsea_b200_comm_init_local(mdsea_ctx *c, int64_t group_key) {
@@ -150,6 +153,7 @@ extern "C" int mdsea_b200_comm_init_local(mdsea_ctx *c, int64_t group_key) {
 void md_comm_free(mdsea_ctx *c) {
     CommState *s = c->comm;
     if (!s) return;
+    for (void *p : s->ipc_mapped) cudaIpcCloseMemHandle(p);
     if (s->backend == 1 && s->nccl) g_nccl.CommDestroy(s->nccl);
     if (s->backend == 2) {
         std::lock_guard<std::mutex> lk(g_lg_mu);
@@ -236,6 +240,51 @@ int md_comm_allreduce_sum_f64(mdsea_ctx *c, double *d_buf, int count) {
     }
     return local_allreduce<double, false>(c, d_buf, count);
 }
+
+// Peer-memory plumbing (NCCL transport, one process per GPU on ONE node): every rank owns one cudaMalloc'ed buffer;
+// its CUDA IPC handle travels to all peers through an all-gather and each peer maps it, so that kernels can store
+// straight into the neighbour's memory over NVLink.  peers[q] receives the mapped base pointer of rank q's buffer
+// (peers[rank] = own).  Returns MDSEA_ERR_UNSUPPORTED (on EVERY rank, agreed through an all-reduce) when some rank
+// cannot map some peer, so that the caller can fall back to ncclSend/ncclRecv consistently.
+int md_comm_share_buffer(mdsea_ctx *c, void *own, void **peers) {
+    CommState *s = c->comm;
+    if (!s || s->backend != 1) return MDSEA_ERR_UNSUPPORTED;
+    const int W = s->world;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t mine;
+    int ok = cudaIpcGetMemHandle(&mine, own) == cudaSuccess ? 1 : 0;
+    int *d_buf = nullptr;
+    MD_CUDA(c, cudaMalloc(&d_buf, sizeof(int) * 16 * (W + 1) + sizeof(int) * 4));
+    int *d_all = d_buf + 16, *d_ok = d_all + 16 * W;
+    MD_CUDA(c, cudaMemcpyAsync(d_buf, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    int st = md_comm_allgather_i32(c, d_buf, 16, d_all);
+    std::vector<cudaIpcMemHandle_t> all(W);
+    if (st == MDSEA_OK) {
+        MD_CUDA(c, cudaMemcpyAsync(all.data(), d_all, 64 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int q = 0; q < W && ok; ++q) {
+            if (q == s->rank) { peers[q] = own; continue; }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+            peers[q] = p;
+            s->ipc_mapped.push_back(p);
+        }
+        // all ranks take the same decision: min over ranks = -(max of the negated flags)
+        int neg = -ok;
+        MD_CUDA(c, cudaMemcpy(d_ok, &neg, sizeof(int), cudaMemcpyHostToDevice));
+        st = md_comm_allreduce_max_i32(c, d_ok, 1);
+        if (st == MDSEA_OK) {
+            MD_CUDA(c, cudaStreamSynchronize(c->stream));
+            MD_CUDA(c, cudaMemcpy(&neg, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+            ok = -neg;
+        }
+    }
+    cudaFree(d_buf);
+    if (st != MDSEA_OK) return st;
+    return ok ? MDSEA_OK : MDSEA_ERR_UNSUPPORTED;
+}
+
+int md_comm_backend(const mdsea_ctx *c) { return c->comm ? c->comm->backend : 0; }
 
 // personalised exchange: send[q] (send_bytes[q]) goes to rank q, recv[p] (recv_bytes[p]) comes from rank p.
 // Entries for q == rank are ignored (the caller handles its own data in place).
