@@ -101,9 +101,11 @@ struct CellState {
     double   *stage_r = nullptr, *stage_v = nullptr;   // set_state staging of the global arrays (world > 1)
     long long p2p_stride = 0;
     double   *peer_buf[MD_MAXW];
-    long long peer_off[MD_MAXW];          // where this rank's segment starts inside peer q's receive buffer (doubles)
-    int      *d_nsend = nullptr, *d_nsend_all = nullptr;
     unsigned long long halo_seq = 0;      // exchanges done so far (identical on all ranks)
+    unsigned long long asm_seq = 0;       // rebuilds done so far (identical on all ranks)
+    long long seg_cap = 0;                // rebuild inbox: one segment of seg_cap messages per source rank
+    size_t    ctrl_off = 0, inbox_off = 0; // byte offsets of the control block / the inbox inside p2p_buf
+    int      *d_roff = nullptr;           // [MD_MAXW + 2] staging offsets of the received segments, n_tot, n_self
     std::vector<long long> row_n_own;     // owned count of every buffered row
     int   *cell_end = nullptr;
     int       nc = 0, ncell = 0;
@@ -116,7 +118,7 @@ struct CellState {
     int    *id = nullptr, *id_alt = nullptr;
     double *rb = nullptr;                 // positions at the last build, slot order
     void   *pos4 = nullptr;               // double4[cap] (fp64) or uint4[cap] (fp32)
-    cudaTextureObject_t tex_pos = 0;      // experiment (MDSEA_FORCE_TEX=1): gather the fp32 positions through the texture path
+    cudaTextureObject_t tex_pos = 0;      // fp32 positions as a linear texture (default gather path of the fp32 force kernel)
     unsigned long long *key = nullptr, *key_alt = nullptr;
     int    *val = nullptr, *val_alt = nullptr;
     int    *hist = nullptr, *hist_tot = nullptr;
@@ -1032,6 +1034,112 @@ __global__ void k_select_owned(const double *__restrict__ rg, const double *__re
     id[s] = (int)g;
 }
 
+// ---- rebuild-time routing over peer memory (NCCL transport on one node) ----
+// Control block every rank exposes next to its halo buffers; peers store into it over NVLink.
+struct PeerCtrl {
+    int                cnt_from[MD_MAXW];       // messages rank p appended to my inbox segment p in the current rebuild
+    unsigned long long asm_seq_from[MD_MAXW];   // ... valid once this reaches the rebuild number
+    long long          halo_off_from[MD_MAXW];  // where MY halo segment starts inside rank p's receive buffer (doubles)
+    unsigned long long off_seq_from[MD_MAXW];   // ... valid once this reaches the rebuild number
+};
+struct RouteP2P {
+    PMsg *seg[MD_MAXW];   // my segment inside rank q's inbox (q == rank: unused)
+    int   seg_cap;
+};
+// one pass: what this rank keeps goes straight into the staging arrays, everything else straight into the inbox of
+// the rank that needs it (as owner or as ghost); no count pass, no send pool, no ncclSend/ncclRecv
+__global__ void k_mr_route_p2p(const double *__restrict__ r, const double *__restrict__ v, const int *__restrict__ id, long long n,
+                               long long cap, double L, double cl, int nc, Decomp D, int *__restrict__ cursor, RouteP2P dst,
+                               double *__restrict__ r_st, double *__restrict__ v_st, int *__restrict__ id_st,
+                               StepScalars *__restrict__ sc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = r[i], y = r[cap + i], z = r[2 * cap + i];
+    const int cx = md_cell_coord(x, L, cl, nc), cy = md_cell_coord(y, L, cl, nc), cz = md_cell_coord(z, L, cl, nc);
+    for (int q = 0; q < D.world; ++q) {
+        if (!dc_in_ext(D, q, cx, cy, cz)) continue;
+        const int pos = atomicAdd(&cursor[q], 1);
+        if (q == D.rank) {
+            if (pos < cap) {
+                r_st[pos] = x; r_st[cap + pos] = y; r_st[2 * cap + pos] = z;
+                v_st[pos] = v[i]; v_st[cap + pos] = v[cap + i]; v_st[2 * cap + pos] = v[2 * cap + i];
+                id_st[pos] = id[i];
+            }
+        } else if (pos < dst.seg_cap) {
+            PMsg m;
+            m.r[0] = x; m.r[1] = y; m.r[2] = z;
+            m.v[0] = v[i]; m.v[1] = v[cap + i]; m.v[2] = v[2 * cap + i];
+            m.id = id[i];
+            dst.seg[q][pos] = m;
+        } else {
+            sc->overflow_flag = 1;
+        }
+    }
+}
+struct CtrlPtrs { PeerCtrl *p[MD_MAXW]; };
+__global__ void k_mr_signal(const int *__restrict__ cursor, CtrlPtrs peers, int world, int rank, unsigned long long seq) {
+    __threadfence_system();   // the messages of k_mr_route_p2p first
+    const int q = threadIdx.x;
+    if (q < world && q != rank) {
+        peers.p[q]->cnt_from[rank] = cursor[q];
+        __threadfence_system();
+        *(volatile unsigned long long *)&peers.p[q]->asm_seq_from[rank] = seq;
+    }
+}
+// wait for every peer's segment, lay the segments out behind the self-kept particles; roff[q] = first staging slot of
+// source q, roff[W] = n_tot, roff[W + 1] = n_self; the two totals also go to the host through mapped memory
+__global__ void k_mr_collect(const PeerCtrl *__restrict__ ctrl, const int *__restrict__ cursor, int world, int rank,
+                             unsigned long long seq, int *__restrict__ roff, int *__restrict__ host_out,
+                             StepScalars *__restrict__ sc) {
+    const int q = threadIdx.x;
+    if (q < world && q != rank) {
+        const volatile unsigned long long *f = &ctrl->asm_seq_from[q];
+        const long long t0 = clock64();
+        while (*f < seq)
+            if (clock64() - t0 > 8000000000LL) { sc->overflow_flag = 2; break; }
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        int run = cursor[rank];
+        for (int p = 0; p < world; ++p) {
+            roff[p] = run;
+            if (p != rank) run += ((const volatile PeerCtrl *)ctrl)->cnt_from[p];
+        }
+        roff[world] = run;
+        roff[world + 1] = cursor[rank];
+        host_out[0] = run;
+        host_out[1] = cursor[rank];
+    }
+}
+__global__ void k_mr_unpack_p2p(const PMsg *__restrict__ inbox, long long seg_cap, const int *__restrict__ roff, int world, int rank,
+                                long long cap, double *__restrict__ r, double *__restrict__ v, int *__restrict__ id) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index among the RECEIVED particles
+    const int n_self = roff[world + 1], n_tot = roff[world];
+    if (t >= n_tot - n_self) return;
+    const int s = n_self + (int)t;
+    int p = 0;
+    for (int k = 0; k < world; ++k)
+        if (k != rank && s >= roff[k]) p = k;   // sources are laid out in rank order: the last one starting at or before s
+    const PMsg m = inbox[(long long)p * seg_cap + (s - roff[p])];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        r[d * cap + s] = m.r[d];
+        v[d * cap + s] = m.v[d];
+    }
+    id[s] = (int)m.id;
+}
+// the receive layout of this rank's halo buffer, told to the senders: off_for[p] = 3 * (entries from ranks before p) + p
+struct HaloOff { long long off_for[MD_MAXW]; };
+__global__ void k_publish_halo_off(CtrlPtrs peers, HaloOff H, int world, int rank, unsigned long long seq) {
+    const int p = threadIdx.x;
+    if (p < world && p != rank) {
+        peers.p[p]->halo_off_from[rank] = H.off_for[p];
+        __threadfence_system();
+        *(volatile unsigned long long *)&peers.p[p]->off_seq_from[rank] = seq;
+    }
+}
+
 // flag[q][s]: owned slot s must be SENT to rank q every step (its cell lies in q's halo); ghost slot s is
 // RECEIVED from rank q (q owns its cell).  One scan over the whole [world][n_tot] array then yields, per peer,
 // the send list followed by the receive list, both in slot order = canonical (cell id, particle id) order --
@@ -1133,22 +1241,32 @@ __global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restr
 
 // fused pack + transfer: the owned boundary positions (and this rank's skin-trigger flag) are stored straight into
 // the receive buffers of the ranks that hold them as ghosts -- no staging buffer, no ncclSend/ncclRecv
-struct PeerDst { double *seg[MD_MAXW]; };   // start of this rank's segment inside peer q's receive buffer
+struct PeerDst { double *base[MD_MAXW]; };   // rank q's receive buffer (current parity); my segment starts at the offset q published
 __global__ void k_halo_push(const double *__restrict__ r, long long cap, const int *__restrict__ idx, HaloTab T,
-                            const StepScalars *__restrict__ sc, PeerDst P) {
+                            StepScalars *__restrict__ sc, PeerDst P, const PeerCtrl *__restrict__ ctrl, unsigned long long rebuild_seq) {
+    __shared__ long long s_off[MD_MAXW];
+    if ((int)threadIdx.x < T.world && (int)threadIdx.x != T.rank) {   // the receivers' layouts of THIS list generation
+        const volatile unsigned long long *f = &ctrl->off_seq_from[threadIdx.x];
+        const long long t0 = clock64();
+        while (*f < rebuild_seq)
+            if (clock64() - t0 > 8000000000LL) { sc->overflow_flag = 2; break; }
+        __threadfence_system();
+        s_off[threadIdx.x] = ((const volatile PeerCtrl *)ctrl)->halo_off_from[threadIdx.x];
+    }
+    __syncthreads();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = T.ent0[T.world];
     if (k < total) {
         const int q = halo_peer_of(T, k);
         const long long l = k - T.ent0[q];
         const int s = idx[T.idx0[q] + l];
-        double *m = P.seg[q];
+        double *m = P.base[q] + s_off[q];
         m[3 * l] = r[s];
         m[3 * l + 1] = r[cap + s];
         m[3 * l + 2] = r[2 * cap + s];
     } else if (k < total + T.world) {
         const int q = (int)(k - total);
-        if (q != T.rank) P.seg[q][3 * (T.ent0[q + 1] - T.ent0[q])] = (double)sc->rebuild_flag;
+        if (q != T.rank) P.base[q][s_off[q] + 3 * (T.ent0[q + 1] - T.ent0[q])] = (double)sc->rebuild_flag;
     }
 }
 struct PeerCnt { unsigned long long *cnt[MD_MAXW]; };   // counter[this rank] inside peer q's buffer
@@ -1234,7 +1352,9 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->id_alt, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->pos4, (p.precision == MDSEA_FP32 ? sizeof(uint4) : sizeof(double4)) * (size_t)s->cap));
     MD_CUDA(c, cudaMalloc(&s->qfix, sizeof(uint4) * (size_t)s->cap));
-    if (p.precision == MDSEA_FP32 && getenv("MDSEA_FORCE_TEX") && s->cap <= (1LL << 27)) {
+    // fp32 gathers go through the texture path (measured 3 % faster than ld.global.nc on this access pattern);
+    // MDSEA_FORCE_TEX=0 switches it off, and a linear texture cannot address more than 2^27 elements
+    if (p.precision == MDSEA_FP32 && !(getenv("MDSEA_FORCE_TEX") && !strcmp(getenv("MDSEA_FORCE_TEX"), "0")) && s->cap <= (1LL << 27)) {
         cudaResourceDesc rd;
         memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeLinear;
@@ -1320,7 +1440,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
     cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
-    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_nsend); cudaFree(s->d_nsend_all); cudaFree(s->stage_r); cudaFree(s->stage_v);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_roff); cudaFree(s->stage_r); cudaFree(s->stage_v);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
@@ -1374,6 +1494,35 @@ static int mr_assemble(mdsea_ctx *c) {
     CellState *s = c->cells;
     const int W = c->p.world, me = c->p.rank;
     const long long n = c->n;
+    s->asm_seq += 1;   // rebuild number (all ranks rebuild together)
+    if (s->p2p) {
+        RouteP2P dst;
+        CtrlPtrs cp;
+        for (int q = 0; q < MD_MAXW; ++q) {
+            dst.seg[q] = q < W && q != me ? (PMsg *)((char *)s->peer_buf[q] + s->inbox_off) + (size_t)me * (size_t)s->seg_cap : nullptr;
+            cp.p[q] = q < W ? (PeerCtrl *)((char *)s->peer_buf[q] + s->ctrl_off) : nullptr;
+        }
+        dst.seg_cap = (int)s->seg_cap;
+        MD_CUDA(c, cudaMemsetAsync(s->d_cursor, 0, sizeof(int) * MD_MAXW, c->stream));
+        k_mr_route_p2p<<<g256(n), 256, 0, c->stream>>>(c->d_r, c->d_v, s->id, n, s->cap, c->box.L, s->cell_len, s->nc, s->D, s->d_cursor, dst,
+                                                       s->r_alt, s->v_alt, s->id_alt, c->d_sc);
+        k_mr_signal<<<1, 32, 0, c->stream>>>(s->d_cursor, cp, W, me, s->asm_seq);
+        k_mr_collect<<<1, 32, 0, c->stream>>>((const PeerCtrl *)((char *)s->p2p_buf + s->ctrl_off), s->d_cursor, W, me, s->asm_seq, s->d_roff,
+                                              s->d_cnt_all_mapped, c->d_sc);
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        const long long n_tot = s->h_cnt_all[0], n_self = s->h_cnt_all[1];
+        if (n_tot > s->cap || n_self > s->cap) {
+            md_set_error(c, "rebuild: migration/ghost buffer capacity exceeded on this rank");
+            return MDSEA_ERR_CAPACITY;
+        }
+        if (n_tot > n_self)
+            k_mr_unpack_p2p<<<g256(n_tot - n_self), 256, 0, c->stream>>>((const PMsg *)((char *)s->p2p_buf + s->inbox_off), s->seg_cap, s->d_roff, W,
+                                                                        me, s->cap, s->r_alt, s->v_alt, s->id_alt);
+        c->stats.kernel_launches += 4;
+        MD_CUDA(c, cudaGetLastError());
+        s->n_tot = n_tot;
+        return MDSEA_OK;
+    }
     RouteDst none;
     memset(&none, 0, sizeof(none));
     MD_CUDA(c, cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * MD_MAXW, c->stream));
@@ -1440,21 +1589,17 @@ static int build_halo_lists(mdsea_ctx *c) {
         s->halo_base[q] = (long long)q * m;
     }
     if (s->p2p) {
-        // where does my segment start inside peer q's receive buffer?  q lays its buffer out by source rank:
-        // offset(q <- me) = 3 * sum_{p < me, p != q} N[p][q] + me, with N[p][q] = entries p sends to q (all-gathered)
-        int hs[MD_MAXW];
-        for (int q = 0; q < MD_MAXW; ++q) hs[q] = q < W && q != c->p.rank ? (int)s->halo_nsend[q] : 0;
-        MD_CUDA(c, cudaMemcpyAsync(s->d_nsend, hs, sizeof(int) * MD_MAXW, cudaMemcpyHostToDevice, c->stream));
-        MD_TRY(md_comm_allgather_i32(c, s->d_nsend, MD_MAXW, s->d_nsend_all));
-        int *N = s->h_cnt_all;   // pinned, MD_MAXW * MD_MAXW ints
-        k_peek<<<md_div_up(MD_MAXW * W, 256), 256, 0, c->stream>>>(s->d_nsend_all, 1, MD_MAXW * W, s->d_cnt_all_mapped);
-        MD_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (int q = 0; q < W; ++q) {
-            long long off = 0;
-            for (int p = 0; p < c->p.rank; ++p)
-                if (p != q) off += N[p * MD_MAXW + q];
-            s->peer_off[q] = 3 * off + c->p.rank;
+        // tell every sender where its segment starts inside my receive buffer (a store into its control block)
+        HaloOff H;
+        CtrlPtrs cp;
+        long long ent = 0;
+        for (int p = 0; p < MD_MAXW; ++p) {
+            H.off_for[p] = 3 * ent + p;
+            if (p < W && p != c->p.rank) ent += s->halo_nrecv[p];
+            cp.p[p] = p < W ? (PeerCtrl *)((char *)s->peer_buf[p] + s->ctrl_off) : nullptr;
         }
+        k_publish_halo_off<<<1, 32, 0, c->stream>>>(cp, H, W, c->p.rank, s->asm_seq);
+        c->stats.kernel_launches += 1;
     }
     return MDSEA_OK;
 }
@@ -1466,11 +1611,14 @@ int md_cells_comm_ready(mdsea_ctx *c) {
     if (!s || c->p.world < 2 || md_comm_backend(c) != 1) return MDSEA_OK;
     if (getenv("MDSEA_HALO") && !strcmp(getenv("MDSEA_HALO"), "nccl")) return MDSEA_OK;
     s->p2p_stride = 3 * s->cap + MD_MAXW;
-    const size_t bytes = sizeof(double) * 2 * (size_t)s->p2p_stride + sizeof(unsigned long long) * (MD_MAXW + 2);
+    s->seg_cap = std::max<long long>(65536, s->cap / 4);
+    s->ctrl_off = sizeof(double) * 2 * (size_t)s->p2p_stride + sizeof(unsigned long long) * (MD_MAXW + 2);
+    s->ctrl_off = (s->ctrl_off + 255) / 256 * 256;
+    s->inbox_off = (s->ctrl_off + sizeof(PeerCtrl) + 255) / 256 * 256;
+    const size_t bytes = s->inbox_off + sizeof(PMsg) * (size_t)s->seg_cap * (size_t)c->p.world;
     MD_CUDA(c, cudaMalloc(&s->p2p_buf, bytes));
-    MD_CUDA(c, cudaMemset(s->p2p_buf, 0, bytes));
-    MD_CUDA(c, cudaMalloc(&s->d_nsend, sizeof(int) * MD_MAXW));
-    MD_CUDA(c, cudaMalloc(&s->d_nsend_all, sizeof(int) * MD_MAXW * MD_MAXW));
+    MD_CUDA(c, cudaMemset(s->p2p_buf, 0, s->inbox_off));
+    MD_CUDA(c, cudaMalloc(&s->d_roff, sizeof(int) * (MD_MAXW + 2)));
     const int st = md_comm_share_buffer(c, s->p2p_buf, (void **)s->peer_buf);
     if (st == MDSEA_ERR_UNSUPPORTED) return MDSEA_OK;   // keep NCCL send/recv
     if (st != MDSEA_OK) return st;
@@ -1507,13 +1655,14 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
         PeerDst pd;
         PeerCnt pc;
         for (int q = 0; q < MD_MAXW; ++q) {
-            pd.seg[q] = q < W && q != me ? s->peer_buf[q] + par + s->peer_off[q] : nullptr;
+            pd.base[q] = q < W && q != me ? s->peer_buf[q] + par : nullptr;
             pc.cnt[q] = q < W && q != me ? (unsigned long long *)(s->peer_buf[q] + 2 * s->p2p_stride) + me : nullptr;
         }
         HaloWait wt;
         wt.counters = (const unsigned long long *)(s->p2p_buf + 2 * s->p2p_stride);
         wt.seq = seq;
-        k_halo_push<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, pd);
+        k_halo_push<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, pd,
+                                                          (const PeerCtrl *)((char *)s->p2p_buf + s->ctrl_off), s->asm_seq);
         k_halo_signal<<<1, 32, 0, st>>>(pc, W, me, seq);
         k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->p2p_buf + par, s->halo_idx, tr, s->cap, c->d_r,
                                                             c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt);
