@@ -149,7 +149,13 @@ int mdsea_b200_get_state(mdsea_ctx *ctx, double *r_soa, double *v_soa, double *a
  * apply_special, update_energies (simulator.py:560-568) and the buffering of the five
  * dataset rows; then copies the buffered rows to `rows`.  Blocks until the copies landed. */
 int mdsea_b200_run(mdsea_ctx *ctx, const mdsea_run_args *args, const mdsea_rows *rows);
-/* same, but returns after enqueueing; mdsea_b200_wait blocks until rows are in host memory. */
+/* same, but returns once the batch is enqueued and its row copies are under way.  Up to TWO batches can be in
+ * flight: the library alternates between two device ring sets, so the device->host copies of one batch overlap
+ * the compute of the next (a third run_async first completes the oldest batch).  mdsea_b200_wait completes the
+ * OLDEST batch in flight -- its `rows` buffers are valid afterwards -- and is a no-op when nothing is pending.
+ * mdsea_b200_set_state may be called while batches are in flight (it is ordered after their compute and does
+ * not touch the rings); every other call drains all pending batches first.  The caller keeps the `rows`
+ * buffers (pinned host memory for true overlap) alive and untouched until the batch has been waited for. */
 int mdsea_b200_run_async(mdsea_ctx *ctx, const mdsea_run_args *args, const mdsea_rows *rows);
 int mdsea_b200_wait(mdsea_ctx *ctx);
 

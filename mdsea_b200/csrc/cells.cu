@@ -136,6 +136,8 @@ struct CellState {
     int    *d_flag_mapped = nullptr;      // device alias of h_flag
     cudaEvent_t ev_flag = nullptr;
     int     id_bits = 0, cell_bits = 0;
+    int     finish_blocks = 1184;         // grid of the finish kernel: 8 blocks per SM
+    double *pe_fold = nullptr;            // [finish_blocks] PE partials of the force kernel folded by the finish blocks
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -644,16 +646,14 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        if (cnt + __popc(m) > max_nbr) {   // row full: keep counting, the overflow is reported below
-                            cnt += __popc(m);
-                            m = 0u;
-                        }
                         while (m) {
                             const int t1 = __ffs(m) - 1;
                             m &= m - 1;
-                            *wp = base + t1;
+                            if (cnt < max_nbr) {   // a full row keeps counting (the overflow is reported below); every
+                                *wp = base + t1;   // entry below nbr_cnt is always a valid slot
+                                wp += 32;          // next entry of the tile-sliced row (md_nbr_off)
+                            }
                             ++cnt;
-                            wp += 32;   // next entry of the tile-sliced row (md_nbr_off)
                         }
                     }
                     rs = s1; re = e1;
@@ -850,14 +850,16 @@ __global__ void __launch_bounds__(256)
 k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
                   const int *__restrict__ id, long long n, long long cap, long long row_stride, int *__restrict__ id_row,
                   double dt, double g_dt, StepScalars *__restrict__ sc, double *__restrict__ ke_part,
-                  double *__restrict__ r_row, double *__restrict__ v_row, int guarded, FinalizeArgs fin) {
+                  double *__restrict__ r_row, double *__restrict__ v_row, int guarded, FinalizeArgs fin,
+                  const double *__restrict__ pe_force, int n_pe_force, double *__restrict__ pe_fold) {
     __shared__ double red[32];
     __shared__ bool   s_last;
     if (guarded && sc->rebuild_flag) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double v2 = 0.0;
-    if (i < n) {
-        const double scale = sc->scale;
+    const double scale = sc->scale;
+    // grid-stride: a bounded number of blocks (8 per SM) keeps the partial-sum array and the number of same-address
+    // atomics of the last-block protocol below small
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int    gid = id[i];
         // single GPU: rows are written in ORIGINAL particle order (core.py:236-238), scattered by id.
         // multi-rank: compact rows in slot order plus the ids; the host scatters them into the shared file.
@@ -877,10 +879,19 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
         }
     }
     const double b = md_block_sum(v2, red);
+    // every block also folds its slice of the force kernel's PE partials, so that the last block reads gridDim.x values
+    double pe_loc = 0.0;
+    {
+        const int chunk = (n_pe_force + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int k1 = min(n_pe_force, ((int)blockIdx.x + 1) * chunk);
+        for (int k = (int)blockIdx.x * chunk + (int)threadIdx.x; k < k1; k += blockDim.x) pe_loc += pe_force[k];
+    }
+    const double bpe = md_block_sum(pe_loc, red);
     // the step's reductions and bookkeeping (k_finalize of the all-pairs path) are done by whichever block publishes
-    // its KE partial last: no separate single-block launch on the critical path of every step
+    // its partials last: no separate single-block launch on the critical path of every step
     if (threadIdx.x == 0) {
         ke_part[blockIdx.x] = b;
+        pe_fold[blockIdx.x] = bpe;
         __threadfence();
         s_last = atomicAdd(&sc->finish_blocks_done, 1u) == gridDim.x - 1;
     }
@@ -1404,6 +1415,12 @@ int md_cells_setup(mdsea_ctx *c) {
     c->coord_rows_bytes = sizeof(double) * 3 * row_stride * c->ring;
     MD_CUDA(c, cudaMalloc(&c->d_r_rows, c->coord_rows_bytes));
     MD_CUDA(c, cudaMalloc(&c->d_v_rows, c->coord_rows_bytes));
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
+        s->finish_blocks = 8 * sms;
+        MD_CUDA(c, cudaMalloc(&s->pe_fold, sizeof(double) * s->finish_blocks));
+    }
     c->n_ke_part = md_div_up(s->cap, 256);
     MD_CUDA(c, cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
     MD_CUDA(c, cudaMemset(c->d_ke_part, 0, sizeof(double) * c->n_ke_part));
@@ -1863,10 +1880,13 @@ static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k,
     int *idr = (a->record_coords && W > 1) ? c->d_id_rows + (size_t)k * s->cap : nullptr;
     if (W > 1) s->row_n_own[k] = c->n;
     md_prof_begin(c);
-    c->n_ke_part = g256(c->n);
-    k_cut_kick_finish<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride, idr,
-                                                        c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded,
-                                                        md_finalize_args(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k));
+    c->n_ke_part = std::min(g256(c->n), s->finish_blocks);
+    FinalizeArgs fin = md_finalize_args(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k);
+    fin.pe_part = s->pe_fold;   // the force kernel's partials, folded per finish block
+    fin.n_pe = c->n_ke_part;
+    k_cut_kick_finish<<<c->n_ke_part, 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride, idr,
+                                                           c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded, fin, c->d_pe_part,
+                                                           c->n_pe_part, s->pe_fold);
     md_prof_end(c, &c->stats.ms_integrate);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;

@@ -5,10 +5,8 @@ C3="python bench.py --steps 2 --warmup 3 --md-steps 10 --no-cpu-baseline --no-ex
 C2="python bench.py --workload c2 --steps 2 --warmup 3 --md-steps 20 --no-cpu-baseline"
 $C3 > gpurun_out/plain_c3.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_c3.csv $C3 > gpurun_out/ncu_l_c3.log 2>&1
 $C2 > gpurun_out/plain_c2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_c2.csv $C2 > gpurun_out/ncu_l_c2.log 2>&1
-F3="python profiles/prof_force.py c3 fp32 3"
-$F3 > gpurun_out/plain_f3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_nbr_force|k_nbr_build|k_cut_kick' -c 6 -o gpurun_out/prof_c3 $F3 > gpurun_out/ncu_f3.log 2>&1
-F2="python profiles/prof_force.py c2 fp64 3"
-$F2 > gpurun_out/plain_f2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_allpairs' -s 1 -c 1 -o gpurun_out/prof_c2_f64 $F2 > gpurun_out/ncu_f2.log 2>&1
-F2b="python profiles/prof_force.py c2 fp32 3"
-$F2b > gpurun_out/plain_f2b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_allpairs' -s 1 -c 1 -o gpurun_out/prof_c2_f32 $F2b > gpurun_out/ncu_f2b.log 2>&1
-ls -la gpurun_out
+F3="python profiles/ab_cutoff.py fp32 20"
+$F3 > gpurun_out/plain_f3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_nbr_force|k_nbr_build|k_cut_kick|k_bin_' -s 10 -c 8 -o gpurun_out/prof_c3 $F3 > gpurun_out/ncu_f3.log 2>&1
+F3d="python profiles/ab_cutoff.py fp64 20"
+$F3d > gpurun_out/plain_f3d.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_nbr_force' -s 4 -c 1 -o gpurun_out/prof_c3_f64 $F3d > gpurun_out/ncu_f3d.log 2>&1
+ls -la gpurun_out | tail -12
