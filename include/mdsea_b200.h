@@ -202,6 +202,14 @@ int mdsea_b200_comm_init_local(mdsea_ctx *ctx, int64_t group_key);
 /* per-rank slot capacity (owned + ghost particles) of the cutoff path; the row_stride to allocate rows with */
 int64_t mdsea_b200_rank_capacity(mdsea_ctx *ctx);
 
+/* Analyser-side reductions (stand-alone, no context needed): streams the `v_coords` dataset
+ * v_coords[steps][ndim][n] (host memory, the HDF5 row layout) through the GPU and returns what mdsea's Analyser
+ * derives from it (mdsea/analytics.py:53-56, quicker.py:44-46): speeds[steps][n] (may be NULL), their global mean
+ * and population standard deviation (maxspeed = mean + 3 std) and the largest speed.  speeds are bit-identical to
+ * quicker.norm; mean / std agree to ~1e-14 (different summation order). */
+int mdsea_b200_analyse_speeds(int32_t device, const double *v_coords, int64_t steps, int32_t ndim, int64_t n,
+                              double *speeds, double *mean, double *stddev, double *max_speed);
+
 /* device micro-benchmarks used by bench.py for the roofline denominators that
  * MEASURED_PEAKS.json does not hold: dependent-free FMA throughput of the fp32 / fp64
  * CUDA-core pipes in TFLOP/s (FMA = 2 flop). */

@@ -60,7 +60,7 @@ EXPORTS = [
     "mdsea_b200_update_dists", "mdsea_b200_get_cells", "mdsea_b200_get_neighbors", "mdsea_b200_set_temperature",
     "mdsea_b200_get_stats", "mdsea_b200_first_nonfinite_step", "mdsea_b200_set_profiling", "mdsea_b200_stream",
     "mdsea_b200_nccl_unique_id", "mdsea_b200_comm_init", "mdsea_b200_comm_init_local", "mdsea_b200_rank_capacity",
-    "mdsea_b200_measure_fma_peak",
+    "mdsea_b200_measure_fma_peak", "mdsea_b200_analyse_speeds",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load():
     lib.mdsea_b200_rank_capacity.argtypes = [vp]
     lib.mdsea_b200_rank_capacity.restype = C.c_int64
     lib.mdsea_b200_measure_fma_peak.argtypes = [i32, i32, dp]
+    lib.mdsea_b200_analyse_speeds.argtypes = [i32, vp, C.c_int64, i32, C.c_int64, vp, dp, dp, dp]
     _lib = lib
     return lib
 
@@ -278,3 +279,18 @@ def measure_fma_peak(device=0, fp64=False) -> float:
     if st != 0:
         raise MdseaError(st, lib.mdsea_b200_last_error(None).decode())
     return out.value
+
+
+def analyse_speeds(v_coords: np.ndarray, device=0, want_speeds=True):
+    """Device version of Analyser's speed statistics (mdsea/analytics.py:53-56): v_coords is the (STEPS, NDIM, N)
+    dataset; returns (speeds (STEPS, N) or None, mean, std, max)."""
+    lib = load()
+    v = np.ascontiguousarray(v_coords, dtype=np.float64)
+    steps, ndim, n = v.shape
+    speeds = np.empty((steps, n)) if want_speeds else None
+    mean, std, mx = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+    st = lib.mdsea_b200_analyse_speeds(device, _ptr(v), steps, ndim, n, _ptr(speeds) if want_speeds else None, C.byref(mean),
+                                       C.byref(std), C.byref(mx))
+    if st != 0:
+        raise MdseaError(st, lib.mdsea_b200_last_error(None).decode())
+    return speeds, mean.value, std.value, mx.value

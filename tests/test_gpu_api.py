@@ -173,3 +173,27 @@ def test_two_batches_in_flight_give_the_same_rows(cutoff):
     for x, y in zip(ref, got):
         for key in ("r", "v", "pe", "ke", "temp"):
             np.testing.assert_array_equal(x[key], y[key])
+
+
+def test_analyser_speed_statistics_on_device(in_tmp_cwd):  # noqa: F811
+    """Analyser(sm, device=0) == the reference's NumPy formulation (speeds bit for bit)."""
+    from mdsea_b200 import _capi
+    from mdsea_b200.analytics import Analyser
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.quicker import norm
+
+    sm, _ = _run(dict(simid="an", ndim=3, num_particles=216, steps=40, vol_fraction=0.3, radius_particle=0.5),
+                 dict(flush_every=16), Potential.lennardjones(1, 1), 1)
+    host, dev = Analyser(sm), Analyser(sm, device=0)
+    np.testing.assert_array_equal(dev.speeds, host.speeds)
+    assert abs(dev.maxspeed - host.maxspeed) <= 1e-12 * host.maxspeed
+    # chunked streaming (several chunks, 1-D / 2-D layouts, no speeds output)
+    rng = np.random.default_rng(5)
+    for shape in ((3, 1, 1000), (7, 2, 333), (40, 3, 70000)):
+        v = rng.normal(size=shape)
+        sp, mean, std, mx = _capi.analyse_speeds(v)
+        ref = norm(np.moveaxis(v, 1, -1), axis=-1)
+        np.testing.assert_array_equal(sp, ref)
+        assert abs(mean - ref.mean()) <= 1e-12 * ref.mean() and abs(std - ref.std()) <= 1e-11 * ref.std() and mx == ref.max()
+        _, mean2, _, _ = _capi.analyse_speeds(v, want_speeds=False)
+        assert mean2 == mean
