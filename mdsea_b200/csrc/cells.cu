@@ -98,7 +98,6 @@ struct CellState {
     // [MD_MAXW arrival counters]; the neighbours' kernels store positions and counters straight into it over NVLink
     bool      p2p = false;
     double   *p2p_buf = nullptr;
-    double   *stage_r = nullptr, *stage_v = nullptr;   // set_state staging of the global arrays (world > 1)
     long long p2p_stride = 0;
     double   *peer_buf[MD_MAXW];
     unsigned long long halo_seq = 0;      // exchanges done so far (identical on all ranks)
@@ -924,6 +923,10 @@ __global__ void k_peek(const int *__restrict__ src, long long stride, int n, int
     if (i < n) host_dst[i] = src[(long long)i * stride];
 }
 
+__global__ void k_iota_from(int *a, long long n, int first) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = first + (int)i;
+}
 __global__ void k_iota(int *a, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = (int)i;
@@ -1030,21 +1033,6 @@ __global__ void k_mr_unpack(const PMsg *__restrict__ pool, long long n, long lon
     }
     id[s] = (int)m.id;
 }
-// set_state with world > 1: keep the particles whose canonical cell this rank owns
-__global__ void k_select_owned(const double *__restrict__ rg, const double *__restrict__ vg, long long n_global, double L,
-                               double cl, int nc, Decomp D, long long cap, double *__restrict__ r, double *__restrict__ v,
-                               int *__restrict__ id, int *__restrict__ counter) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_global) return;
-    const double x = rg[g], y = rg[n_global + g], z = rg[2 * n_global + g];
-    if (dc_owner(D, md_cell_coord(x, L, cl, nc), md_cell_coord(y, L, cl, nc), md_cell_coord(z, L, cl, nc)) != D.rank) return;
-    const int s = atomicAdd(counter, 1);
-    if (s >= cap) return;
-    r[s] = x; r[cap + s] = y; r[2 * cap + s] = z;
-    v[s] = vg[g]; v[cap + s] = vg[n_global + g]; v[2 * cap + s] = vg[2 * n_global + g];
-    id[s] = (int)g;
-}
-
 // ---- rebuild-time routing over peer memory (NCCL transport on one node) ----
 // Control block every rank exposes next to its halo buffers; peers store into it over NVLink.
 struct PeerCtrl {
@@ -1457,7 +1445,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->qfix); cudaFree(s->cell); cudaFree(s->cell_start); cudaFree(s->cell_end); cudaFree(s->nbr); cudaFree(s->nbr_cnt);
     cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
-    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_roff); cudaFree(s->stage_r); cudaFree(s->stage_v);
+    cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_roff);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
@@ -1480,23 +1468,21 @@ int md_cutoff_set_state(mdsea_ctx *c, const double *r, const double *v) {
         c->n = N;
     } else {
         if (!c->comm) { md_set_error(c, "set_state: world > 1 needs comm_init first"); return MDSEA_ERR_STATE; }
-        // persistent staging of the full arrays (allocating / freeing per call would synchronise the whole device,
-        // including the row copies of a batch that is still in flight)
-        if (!s->stage_r) {
-            MD_CUDA(c, cudaMalloc(&s->stage_r, sizeof(double) * 3 * N));
-            MD_CUDA(c, cudaMalloc(&s->stage_v, sizeof(double) * 3 * N));
+        // Every rank uploads ONE CONTIGUOUS SLICE of the global arrays (particles [rank*N/W, (rank+1)*N/W)) and
+        // simply holds it: the first rebuild routes every held particle to its owner and to the ranks that need it
+        // as a ghost (k_mr_route_p2p / k_mr_route work on held particles, owned or not).  The host->device traffic
+        // per rank is 1/W of the arrays instead of all of them, and no ownership test runs on the host.
+        const int W = c->p.world;
+        const long long lo = (N * c->p.rank) / W, hi = (N * (c->p.rank + 1)) / W, m = hi - lo;
+        if (m > s->cap) { md_set_error(c, "set_state: particle capacity of this rank exceeded"); return MDSEA_ERR_CAPACITY; }
+        for (int d = 0; d < 3; ++d) {
+            MD_CUDA(c, cudaMemcpyAsync(c->d_r + d * s->cap, r + d * N + lo, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+            MD_CUDA(c, cudaMemcpyAsync(c->d_v + d * s->cap, v + d * N + lo, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
         }
-        double *rg = s->stage_r, *vg = s->stage_v;
-        MD_CUDA(c, cudaMemcpyAsync(rg, r, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
-        MD_CUDA(c, cudaMemcpyAsync(vg, v, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
-        MD_CUDA(c, cudaMemsetAsync(s->d_cnt, 0, sizeof(int), c->stream));
-        k_select_owned<<<g256(N), 256, 0, c->stream>>>(rg, vg, N, c->box.L, s->cell_len, s->nc, s->D, s->cap, c->d_r, c->d_v,
-                                                       s->id, s->d_cnt);
+        k_iota_from<<<g256(m), 256, 0, c->stream>>>(s->id, m, (int)lo);
         c->stats.kernel_launches += 1;
-        k_peek<<<1, 32, 0, c->stream>>>(s->d_cnt, 1, 1, s->d_flag_mapped);
         MD_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (s->h_flag[0] > s->cap) { md_set_error(c, "set_state: particle capacity of this rank exceeded"); return MDSEA_ERR_CAPACITY; }
-        c->n = s->h_flag[0];
+        c->n = m;
     }
     s->n_tot = c->n;
     s->need_rebuild = true;
@@ -1628,7 +1614,7 @@ int md_cells_comm_ready(mdsea_ctx *c) {
     if (!s || c->p.world < 2 || md_comm_backend(c) != 1) return MDSEA_OK;
     if (getenv("MDSEA_HALO") && !strcmp(getenv("MDSEA_HALO"), "nccl")) return MDSEA_OK;
     s->p2p_stride = 3 * s->cap + MD_MAXW;
-    s->seg_cap = std::max<long long>(65536, s->cap / 4);
+    s->seg_cap = s->cap;   // worst case: everything a rank owns arrives from ONE source (first rebuild after set_state)
     s->ctrl_off = sizeof(double) * 2 * (size_t)s->p2p_stride + sizeof(unsigned long long) * (MD_MAXW + 2);
     s->ctrl_off = (s->ctrl_off + 255) / 256 * 256;
     s->inbox_off = (s->ctrl_off + sizeof(PeerCtrl) + 255) / 256 * 256;
