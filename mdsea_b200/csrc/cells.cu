@@ -1477,9 +1477,6 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
     MD_CUDA(c, cudaMemset(c->d_pe_part, 0, sizeof(double) * c->n_pe_part));
     if (W > 1) {
-        s->sendpool_cap = (long long)std::min(W, 3) * s->cap;
-        MD_CUDA(c, cudaMalloc(&s->sendpool, sizeof(PMsg) * (size_t)s->sendpool_cap));
-        MD_CUDA(c, cudaMalloc(&s->recvpool, sizeof(PMsg) * (size_t)s->cap));
         MD_CUDA(c, cudaMalloc(&s->d_cnt_all, sizeof(int) * MD_MAXW * MD_MAXW));
         MD_CUDA(c, cudaMalloc(&s->d_cursor, sizeof(int) * MD_MAXW));
         MD_CUDA(c, cudaMalloc(&s->halo_flag, sizeof(int) * ((size_t)W * s->cap + 1)));
@@ -1559,6 +1556,11 @@ static int mr_assemble(mdsea_ctx *c) {
     const int W = c->p.world, me = c->p.rank;
     const long long n = c->n;
     s->asm_seq += 1;   // rebuild number (all ranks rebuild together)
+    if (!s->p2p && !s->sendpool) {   // message pools of the ncclSend/ncclRecv (and in-process) transport, on first use
+        s->sendpool_cap = (long long)std::min(W, 3) * s->cap;
+        MD_CUDA(c, cudaMalloc(&s->sendpool, sizeof(PMsg) * (size_t)s->sendpool_cap));
+        MD_CUDA(c, cudaMalloc(&s->recvpool, sizeof(PMsg) * (size_t)s->cap));
+    }
     if (s->p2p) {
         RouteP2P dst;
         CtrlPtrs cp;
