@@ -10,6 +10,7 @@
 // fpart[chunk][dim][i]; the integrator sums the chunks in fixed order (no atomics, run-to-run
 // deterministic).  Sign convention: dr = r_j - r_i, a_i += dr * (dV/dr)/(r m)  (simulator.py:266,301-305).
 #include <stdlib.h>
+#include <string.h>
 
 #include "ctx.h"
 
@@ -243,6 +244,148 @@ k_allpairs_f64(const double *__restrict__ r, int n, int jchunk, BoxDev box, PotF
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp64 kernel, Newton's third law (small N: up to AP3_MAXT tiles): one CTA per UNORDERED pair of
+// 128-particle tiles (I <= J), every pair evaluated ONCE -- half the fp64 work of the kernel above, which is what
+// bounds it.  Thread t owns particle i = I*128 + t (force in registers).  The reaction -f goes to the j particle
+// through shared memory without atomics: in batch b, lane l of a warp visits the four j = u*32 + ((l + b) & 31),
+// u = 0..3 -- distinct for the 32 lanes of the warp -- and adds into the WARP's private copy of the tile's force
+// array; __syncwarp() orders the batches; the four copies are summed in fixed order at the end.  Partial forces go
+// to fpart[partner tile][dim][particle]: every (partner, particle) slot is written by exactly one CTA per evaluation,
+// and the integrator sums the T partners in fixed order (deterministic, like the split-j kernel).
+// ---------------------------------------------------------------------------------------------
+#define AP3_MAXT 64
+template <int NDIM, int POTK, bool CUT, bool PBC>
+__global__ void __launch_bounds__(AP_TI)
+k_allpairs_n3_f64(const double *__restrict__ r, int n, BoxDev box, PotF64 P, double rc2, double *__restrict__ fpart,
+                  double *__restrict__ pe_part, unsigned long long *__restrict__ cnt_part, StepScalars *__restrict__ sc) {
+    __shared__ double sj[NDIM][AP_TI];
+    __shared__ double sfj[AP_TI / 32][NDIM][AP_TI];
+    __shared__ double red[32];
+    __shared__ unsigned redu[32];
+    const int J = blockIdx.x, I = blockIdx.y, bidx = blockIdx.y * gridDim.x + blockIdx.x;
+    if (I > J) {   // lower triangle: nothing to do, but the partial-sum slots are read by the finalize kernel
+        if (threadIdx.x == 0) { pe_part[bidx] = 0.0; cnt_part[bidx] = 0ull; }
+        return;
+    }
+    const int  t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int  i = I * AP_TI + t, jg = J * AP_TI + t;
+    const bool active = i < n, diag = I == J;
+    const int  ic = active ? i : n - 1, nj = min(AP_TI, n - J * AP_TI);
+    double ri[NDIM], f[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        ri[d] = r[(size_t)d * n + ic];
+        f[d] = 0.0;
+        sj[d][t] = r[(size_t)d * n + min(jg, n - 1)];
+#pragma unroll
+        for (int ww = 0; ww < AP_TI / 32; ++ww) sfj[ww][d][t] = 0.0;
+    }
+    __syncthreads();
+    double   pe = 0.0;
+    unsigned cnt = 0;
+    const int L_hi = __double2hiint(box.L), L_lo = __double2loint(box.L);
+    const int tie_hi = __double2hiint(box.halfL * (1.0 - 2e-6));
+    for (int b = 0; b < 32; ++b) {
+        const int g = (lane + b) & 31;
+        double   dd[4][NDIM], s4[4];
+        unsigned tie_mask = 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // four independent pairs: keeps the fp64 pipe fed
+            const int jl = u * 32 + g;
+            double r2 = 0.0;
+            int    amax = 0;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                double x = sj[d][jl] - ri[d];
+                if (PBC) {   // same branch-free image as ap_tile_f64; near-tie components are redone exactly below
+                    const int    hi = __double2hiint(x);
+                    const double Ls = __hiloint2double((hi & 0x80000000) | L_hi, L_lo);
+                    if (fabs(x) > box.halfL) x -= Ls;
+                    amax = max(amax, __double2hiint(x) & 0x7fffffff);
+                }
+                dd[u][d] = x;
+                r2 = fma(x, x, r2);
+            }
+            bool ok = active && jl < nj && (!diag || jl > t);
+            if (PBC && amax >= tie_hi) {
+                tie_mask |= ok ? (1u << u) : 0u;
+                ok = false;
+            }
+            if (CUT) ok = ok && (r2 < rc2);
+            double s, uu;
+            md_pair<POTK>(r2, ok, P, s, uu);
+            s4[u] = s;
+            pe += uu;
+            cnt += ok ? 2u : 0u;
+        }
+        if (tie_mask) {   // rare: exact IEEE image (simulator.py:272) for a pair at the half-box tie
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {   // static indices keep dd / s4 in registers
+                if (!((tie_mask >> u) & 1u)) continue;
+                const int jl = u * 32 + g;
+                double r2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    const double x = ap_exact_image(sj[d][jl] - ri[d], box.L);
+                    dd[u][d] = x;
+                    r2 = fma(x, x, r2);
+                }
+                const bool ok = !CUT || r2 < rc2;
+                double s, uu;
+                md_pair<POTK>(r2, ok, P, s, uu);
+                s4[u] = s;
+                pe += uu;
+                cnt += ok ? 2u : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jl = u * 32 + g;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                const double fd = dd[u][d] * s4[u];
+                f[d] += fd;                 // a_i += dr * s   (dr = r_j - r_i)
+                sfj[w][d][jl] -= fd;        // a_j -= dr * s   (this warp's copy; lanes hit distinct j)
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    double fj[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        double a = sfj[0][d][t];
+#pragma unroll
+        for (int ww = 1; ww < AP_TI / 32; ++ww) a += sfj[ww][d][t];
+        fj[d] = a;
+    }
+    if (diag) {
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) fpart[((size_t)I * NDIM + d) * n + i] = f[d] + fj[d];
+        }
+    } else {
+        if (active) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) fpart[((size_t)J * NDIM + d) * n + i] = f[d];
+        }
+        if (jg < n) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) fpart[((size_t)I * NDIM + d) * n + jg] = fj[d];
+        }
+    }
+    // every unordered pair was evaluated once: count its energy for both directions (the finalize factor is
+    // lambda eps / 2 / N over DIRECTED pairs, like the split-j kernel)
+    const double   bpe = md_block_sum(pe, red);
+    const unsigned bc = md_block_sum(cnt, redu);
+    if (threadIdx.x == 0) {
+        pe_part[bidx] = 2.0 * bpe;
+        cnt_part[bidx] = bc;
+        atomicAdd(&sc->pairs_pending, (unsigned long long)bc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp32 kernel: positions as 32-bit fixed point (unit h = L/2^32 periodic, L/2^31 walls).
 // The integer subtraction of two fixed-point coordinates is exact and -- for the periodic box --
 // wraps to the minimum image for free; I2F then rounds RELATIVE to the separation, which keeps
@@ -412,6 +555,9 @@ int md_allpairs_setup(mdsea_ctx *c) {
     c->ap_nsplit = nsplit;
     c->ap_jchunk = md_div_up(md_div_up(n, nsplit), AP_TI) * AP_TI;  // whole tiles: the diagonal tile is block-uniform
     c->ap_nsplit = md_div_up(n, c->ap_jchunk);
+    // fp64, up to AP3_MAXT tiles: the Newton's-third-law kernel (one CTA per unordered tile pair, T partner slots)
+    c->ap_n3 = c->p.precision == MDSEA_FP64 && c->ap_blocks_x <= AP3_MAXT && !(getenv("MDSEA_AP_N3") && !strcmp(getenv("MDSEA_AP_N3"), "0"));
+    if (c->ap_n3) c->ap_nsplit = c->ap_blocks_x;
     c->n_pe_part = c->ap_blocks_x * c->ap_nsplit;
     MD_CUDA(c, cudaMalloc(&c->d_fpart, sizeof(double) * c->E * c->ap_nsplit));
     MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
@@ -426,6 +572,11 @@ template <int NDIM, int POTK, bool CUT, bool PBC>
 static void launch_f64(mdsea_ctx *c, dim3 grid, const PotF64 &P, double rc2) {
     k_allpairs_f64<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(
         c->d_r, (int)c->n, c->ap_jchunk, c->box, P, rc2, c->d_fpart, c->d_pe_part, c->d_cnt_part, c->d_sc);
+}
+template <int NDIM, int POTK, bool CUT, bool PBC>
+static void launch_n3_f64(mdsea_ctx *c, dim3 grid, const PotF64 &P, double rc2) {
+    k_allpairs_n3_f64<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(c->d_r, (int)c->n, c->box, P, rc2, c->d_fpart, c->d_pe_part,
+                                                                        c->d_cnt_part, c->d_sc);
 }
 template <int NDIM, int POTK, bool CUT, bool PBC>
 static void launch_f32(mdsea_ctx *c, dim3 grid, const PotF32 &P, float rc2s, double rc2, double inv_h) {
@@ -476,7 +627,8 @@ int md_allpairs_force(mdsea_ctx *c) {
         PotF64 P;
         P.c = (pd.fast == POTF_LJ ? 6.0 : 1.0) * pd.lam_eps * pd.inv_mass;
         P.sigma = pd.sigma; P.sigma2 = pd.sigma2; P.a2 = pd.a2; P.m = pd.m; P.n = pd.n; P.mi = pd.mi; P.ni = pd.ni;
-        AP_DISPATCH(launch_f64, c, grid, P, rc2);
+        if (c->ap_n3) AP_DISPATCH(launch_n3_f64, c, dim3(c->ap_blocks_x, c->ap_blocks_x), P, rc2);
+        else AP_DISPATCH(launch_f64, c, grid, P, rc2);
         c->stats.kernel_launches += 1;
     } else {
         const double units = c->box.pbc ? 4294967296.0 : 2147483648.0;

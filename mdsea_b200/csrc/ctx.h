@@ -30,6 +30,7 @@ struct mdsea_ctx {
     // all-pairs force partials [nsplit][ndim][n] and per-block reductions
     double *d_fpart = nullptr;
     int     ap_ti = 128, ap_nsplit = 1, ap_jchunk = 0, ap_blocks_x = 0;
+    bool    ap_n3 = false;                 // fp64 Newton's-third-law kernel: fpart holds one slot per partner tile
     double *d_pe_part = nullptr;           // per force-kernel block
     unsigned long long *d_cnt_part = nullptr;
     int     n_pe_part = 0;
