@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "ctx.h"
+#include "finalize.cuh"
 
 static std::string g_err;
 std::string &md_global_error() { return g_err; }
@@ -374,12 +375,16 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt);
 static int allpairs_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
     const bool verlet = c->p.algorithm == MDSEA_ALGO_VERLET;
     const bool reuse = verlet && c->p.force_evals_per_step == 1 && c->box.pbc;
+    // with a(t+dt) reused and no quench in the batch, the finish kernel of step k also does the wrap, first half kick
+    // and drift of step k+1 (same accelerations): three launches per step (drift+force+finish+finalize were four)
+    const bool fuse = reuse && !a->quench_targets;
+    bool drifted = false;   // the previous finish kernel already started this step
     ForceSrc s;
     for (int k = 0; k < a->nsteps; ++k) {
         if (verlet) {
             if (reuse && c->acc_valid) {
                 // a(t) == a(t+dt) of the previous step; the wrap does not change it
-                MD_TRY(md_kick_drift(c, true, true, c->d_acc, 1, 0));
+                if (!drifted) MD_TRY(md_kick_drift(c, true, true, c->d_acc, 1, 0));
             } else {
                 MD_TRY(md_apply_bc(c));
                 MD_TRY(eval_forces(c, &s));                                   // simulator.py:540
@@ -389,9 +394,10 @@ static int allpairs_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
             MD_TRY(md_kick_drift(c, true, false, nullptr, 0, 0));           // simulator.py:533
         }
         MD_TRY(eval_forces(c, &s));                                           // simulator.py:544 / :535
-        MD_TRY(md_kick_finish(c, s.f, s.nparts, s.stride, k, a->record_coords, g_dt));
+        drifted = fuse && k + 1 < a->nsteps;
+        MD_TRY(md_kick_finish(c, s.f, s.nparts, s.stride, k, a->record_coords, g_dt,
+                              md_finalize_args(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k), drifted));
         c->acc_valid = true;
-        MD_TRY(md_finalize_step(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k));
     }
     return MDSEA_OK;
 }

@@ -947,7 +947,7 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
         for (int k = (int)blockIdx.x * chunk + (int)threadIdx.x; k < k1; k += blockDim.x) pe_loc += pe_force[k];
     }
     const double bpe = md_block_sum(pe_loc, red);
-    // the step's reductions and bookkeeping (k_finalize of the all-pairs path) are done by whichever block publishes
+    // the step's reductions and bookkeeping (finalize.cuh) are done by whichever block publishes
     // its partials last: no separate single-block launch on the critical path of every step
     if (threadIdx.x == 0) {
         ke_part[blockIdx.x] = b;

@@ -64,7 +64,7 @@ struct StepScalars {
     double scale;      // velocity scale of the NEXT kick_finish (product of the pending quenches)
     long long first_nonfinite_step;  // -1 while energies are finite
     unsigned long long pairs_directed; // running count of directed in-cutoff pair evaluations (2 x unique pairs)
-    unsigned long long pairs_pending;  // contributions of the current step's force launches; committed by k_finalize
+    unsigned long long pairs_pending;  // contributions of the current step's force launches; committed by the step's finalize (finalize.cuh)
                                        // (a speculative launch that is redone after a rebuild must not count twice)
     unsigned long long steps_done;
     int    rebuild_flag;             // cutoff path: max displacement exceeded skin/2

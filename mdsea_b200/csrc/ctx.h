@@ -89,10 +89,10 @@ int md_allpairs_force(mdsea_ctx *c);          // fills d_fpart / d_pe_part / d_c
 // integrate.cu
 int md_apply_bc(mdsea_ctx *c);
 int md_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, const double *fsrc, int nparts, size_t stride);
-int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt);
-int md_reduce_acc(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride);
-int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index, int guarded = 0);
 struct FinalizeArgs;
+int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt,
+                   const FinalizeArgs &fin, bool drift_next);
+int md_reduce_acc(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride);
 FinalizeArgs md_finalize_args(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index);
 int md_prepare_first(mdsea_ctx *c, double kb);
 int md_commit_pairs(mdsea_ctx *c);

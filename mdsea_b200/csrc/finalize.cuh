@@ -1,5 +1,5 @@
-// Per-step reductions and bookkeeping shared by k_finalize (all-pairs path: its own single-block launch) and by the
-// LAST block of k_cut_kick_finish (cut-off path: no extra launch).  Deterministic: every thread sums a fixed strided
+// Per-step reductions and bookkeeping, run by the LAST block of the finish kernels (k_kick_finish of the all-pairs
+// path, k_cut_kick_finish of the cut-off path): no single-block launch on the critical path of a step.  Deterministic: every thread sums a fixed strided
 // subset of the partials, then a fixed shuffle tree -- the result does not depend on which block runs it.
 #pragma once
 #include "common.cuh"

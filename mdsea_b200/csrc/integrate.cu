@@ -5,8 +5,8 @@
 //
 //   kick_drift : [boundary condition] ; [v += a dt/2] ; r += v dt        (before a force evaluation)
 //   kick_finish: v += a dt/2 ; gravity ; quench scale ; sum v^2 ; row(r, v) into the device ring
-//   finalize   : fixed-order reduction of the per-block partial sums -> mean_pe, mean_ke, temp row;
-//                temperature bookkeeping for the next step's quench
+//   (finalize) : fixed-order reduction of the per-block partial sums -> mean_pe, mean_ke, temp row, temperature
+//                bookkeeping for the next step's quench: done by the LAST block of kick_finish (finalize.cuh)
 #include "ctx.h"
 #include "finalize.cuh"
 
@@ -68,12 +68,18 @@ k_reduce_acc(const double *__restrict__ fsrc, int nparts, size_t stride, double 
     if (e < E) acc[e] = md_sum_parts(fsrc, nparts, stride, e);
 }
 
+// kick_finish of step k, optionally followed (DRIFT_NEXT) by the wrap + first half kick + drift of step k+1, which
+// use the same accelerations when a(t+dt) is reused (periodic box, one force evaluation per step, no quench in the
+// batch): r, v and the force partials are read once and one launch per step disappears.  The LAST block to publish
+// its KE partial also does the step's reductions and bookkeeping (k_finalize), saving another launch.
+template <bool DRIFT_NEXT>
 __global__ void __launch_bounds__(IG_THREADS)
-k_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ fsrc, int nparts,
+k_kick_finish(double *__restrict__ r, double *__restrict__ v, const double *__restrict__ fsrc, int nparts,
               size_t stride, double *__restrict__ acc_out, size_t E, size_t last_dim_start, double dt, double g_dt,
-              const StepScalars *__restrict__ sc, double *__restrict__ ke_part, double *__restrict__ r_row,
-              double *__restrict__ v_row) {
+              StepScalars *__restrict__ sc, double *__restrict__ ke_part, double *__restrict__ r_row,
+              double *__restrict__ v_row, double L, FinalizeArgs fin) {
     __shared__ double red[32];
+    __shared__ bool   s_last;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     double v2 = 0.0;
     if (e < E) {
@@ -83,22 +89,33 @@ k_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double
         if (g_dt != 0.0 && e >= last_dim_start) u -= g_dt;   // v[-1] -= g * dt, simulator.py:205
         const double scale = sc->scale;                       // (T_target / T)^0.5, simulator.py:195
         if (scale != 1.0) u *= scale;
-        v[e] = u;
         v2 = u * u;
+        double x = r[e];
         if (r_row) {
-            r_row[e] = r[e];
+            r_row[e] = x;
             v_row[e] = u;
         }
+        if (DRIFT_NEXT) {   // step k+1: apply_pbc (simulator.py:165-166), v += a dt/2 (:540), r += v dt (:542)
+            if (x < 0.0) x += L;
+            if (x > L) x -= L;
+            u += __dmul_rn(__dmul_rn(0.5, a), dt);
+            x += __dmul_rn(u, dt);
+            r[e] = x;
+        }
+        v[e] = u;
     }
     const double b = md_block_sum(v2, red);
-    if (threadIdx.x == 0) ke_part[blockIdx.x] = b;
-}
-
-// single block; deterministic fixed-order tree over the partial sums
-__global__ void __launch_bounds__(1024) k_finalize(FinalizeArgs A, StepScalars *__restrict__ sc, int guarded) {
-    __shared__ double red[32];
-    if (guarded && sc->rebuild_flag) return;  // speculative launch of the cut-off path (see cells.cu)
-    md_finalize_body(A, sc, red);
+    if (threadIdx.x == 0) {
+        ke_part[blockIdx.x] = b;
+        __threadfence();
+        s_last = atomicAdd(&sc->finish_blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        md_finalize_body(fin, sc, red);
+        if (threadIdx.x == 0) sc->finish_blocks_done = 0u;
+    }
 }
 
 __global__ void k_commit_pairs(StepScalars *sc) {
@@ -178,14 +195,21 @@ int md_reduce_acc(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride) {
     return MDSEA_OK;
 }
 
-int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt) {
+// kick_finish of step `row` (+ the step's reductions); drift_next also starts step row+1 (see k_kick_finish)
+int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt,
+                   const FinalizeArgs &fin, bool drift_next) {
     double *acc_out = (fsrc != c->d_acc) ? c->d_acc : nullptr;
     double *rr = record ? c->d_r_rows + (size_t)row * c->E : nullptr;
     double *vr = record ? c->d_v_rows + (size_t)row * c->E : nullptr;
     md_prof_begin(c);
-    k_kick_finish<<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
-                                                            (size_t)(c->ndim - 1) * c->n, c->p.dt, g_dt, c->d_sc,
-                                                            c->d_ke_part, rr, vr);
+    if (drift_next)
+        k_kick_finish<true><<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
+                                                                      (size_t)(c->ndim - 1) * c->n, c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr,
+                                                                      vr, c->box.L, fin);
+    else
+        k_kick_finish<false><<<ig_grid(c), IG_THREADS, 0, c->stream>>>(c->d_r, c->d_v, fsrc, nparts, stride, acc_out, c->E,
+                                                                       (size_t)(c->ndim - 1) * c->n, c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr,
+                                                                       vr, c->box.L, fin);
     md_prof_end(c, &c->stats.ms_integrate);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
@@ -205,13 +229,6 @@ FinalizeArgs md_finalize_args(mdsea_ctx *c, int row, int next_row_valid, double 
     A.quench_next = next_row_valid ? c->d_quench + (size_t)(row + 1) * 2 : nullptr;
     A.step_index = step_index;
     return A;
-}
-
-int md_finalize_step(mdsea_ctx *c, int row, int next_row_valid, double kb, long long step_index, int guarded) {
-    k_finalize<<<1, 1024, 0, c->stream>>>(md_finalize_args(c, row, next_row_valid, kb, step_index), c->d_sc, guarded);
-    c->stats.kernel_launches += 1;
-    MD_CUDA(c, cudaGetLastError());
-    return MDSEA_OK;
 }
 
 int md_commit_pairs(mdsea_ctx *c) {
