@@ -13,93 +13,9 @@
 #include <string.h>
 
 #include "ctx.h"
+#include "pair.cuh"
 
 #define AP_TI 128  // particles i per block == j tile length
-
-// ---------------------------------------------------------------------------------------------
-// pair kernels (sqrt-free where the exponents allow it)
-//   s = (dV/dr) / (r m)   so that   a_i += dr * s
-//   u = V / (lambda eps)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T md_ipow(T b, int e) {
-    T r = T(1);
-    while (e > 0) {
-        if (e & 1) r *= b;
-        b *= b;
-        e >>= 1;
-    }
-    return r;
-}
-
-struct PotF64 {
-    double c;      // LJ: 6 lambda eps / m ; Mie: lambda eps / m
-    double sigma, sigma2, a2, m, n;
-    int    mi, ni;
-};
-struct PotF32 {
-    float c;       // same as PotF64::c but divided by the fixed-point unit h (forces come out in real units)
-    float sigma_s, sigma2_s, a2_s, m, n;  // lengths in fixed-point units
-    int   mi, ni;
-};
-
-template <int POTK>
-__device__ __forceinline__ void md_pair(double r2, bool ok, const PotF64 &P, double &s, double &u) {
-    if (POTK == POTF_LJ) {
-        double inv = ok ? md_rcp(r2) : 0.0;
-        double t2 = P.sigma2 * inv;
-        double t6 = t2 * t2 * t2;
-        double w = fma(-2.0, t6, 1.0);
-        s = (P.c * inv) * (t6 * w);
-        u = fma(t6, t6, -t6);
-    } else {
-        double aprs = P.a2 + r2;
-        double inv = ok ? md_rcp(aprs) : 0.0;
-        double tm, tn;
-        if (P.mi >= 0 && P.ni >= 0 && !((P.mi | P.ni) & 1)) {
-            double t2 = P.sigma2 * inv;
-            tm = md_ipow(t2, P.mi >> 1);
-            tn = md_ipow(t2, P.ni >> 1);
-        } else {
-            double t = P.sigma * sqrt(inv);
-            tm = (P.mi >= 0) ? md_ipow(t, P.mi) : pow(t, P.m);
-            tn = (P.ni >= 0) ? md_ipow(t, P.ni) : pow(t, P.n);
-        }
-        tm = ok ? tm : 0.0;
-        tn = ok ? tn : 0.0;
-        s = P.c * inv * (P.n * tn - P.m * tm);
-        u = tm - tn;
-    }
-}
-
-template <int POTK>
-__device__ __forceinline__ void md_pair(float r2, bool ok, const PotF32 &P, float &s, float &u) {
-    if (POTK == POTF_LJ) {
-        float inv = ok ? md_rcpf(r2) : 0.0f;
-        float t2 = P.sigma2_s * inv;
-        float t6 = t2 * t2 * t2;
-        float w = fmaf(-2.0f, t6, 1.0f);
-        s = (P.c * inv) * (t6 * w);
-        u = fmaf(t6, t6, -t6);
-    } else {
-        float aprs = P.a2_s + r2;
-        float inv = ok ? md_rcpf(aprs) : 0.0f;
-        float tm, tn;
-        if (P.mi >= 0 && P.ni >= 0 && !((P.mi | P.ni) & 1)) {
-            float t2 = P.sigma2_s * inv;
-            tm = md_ipow(t2, P.mi >> 1);
-            tn = md_ipow(t2, P.ni >> 1);
-        } else {
-            float t = P.sigma_s * sqrtf(inv);
-            tm = (P.mi >= 0) ? md_ipow(t, P.mi) : powf(t, P.m);
-            tn = (P.ni >= 0) ? md_ipow(t, P.ni) : powf(t, P.n);
-        }
-        tm = ok ? tm : 0.0f;
-        tn = ok ? tn : 0.0f;
-        s = P.c * inv * (P.n * tn - P.m * tm);
-        u = tm - tn;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // fp64 kernel
@@ -624,9 +540,7 @@ int md_allpairs_force(mdsea_ctx *c) {
     const double rc2 = c->p.r_cutoff > 0 ? c->p.r_cutoff * c->p.r_cutoff : 0.0;
     md_prof_begin(c);
     if (c->p.precision == MDSEA_FP64) {
-        PotF64 P;
-        P.c = (pd.fast == POTF_LJ ? 6.0 : 1.0) * pd.lam_eps * pd.inv_mass;
-        P.sigma = pd.sigma; P.sigma2 = pd.sigma2; P.a2 = pd.a2; P.m = pd.m; P.n = pd.n; P.mi = pd.mi; P.ni = pd.ni;
+        const PotF64 P = md_pot_f64(pd);
         if (c->ap_n3) AP_DISPATCH(launch_n3_f64, c, dim3(c->ap_blocks_x, c->ap_blocks_x), P, rc2);
         else AP_DISPATCH(launch_f64, c, grid, P, rc2);
         c->stats.kernel_launches += 1;
@@ -634,12 +548,7 @@ int md_allpairs_force(mdsea_ctx *c) {
         const double units = c->box.pbc ? 4294967296.0 : 2147483648.0;
         const double h = c->box.L / units, inv_h = units / c->box.L;
         k_to_fixed<<<md_div_up((long long)c->E, 256), 256, 0, c->stream>>>(c->d_r, (uint32_t *)c->d_rhi, c->E, inv_h);
-        PotF32 P;
-        P.c = (float)((pd.fast == POTF_LJ ? 6.0 : 1.0) * pd.lam_eps * pd.inv_mass * inv_h);
-        P.sigma_s = (float)(pd.sigma * inv_h);
-        P.sigma2_s = (float)(pd.sigma2 * inv_h * inv_h);
-        P.a2_s = (float)(pd.a2 * inv_h * inv_h);
-        P.m = (float)pd.m; P.n = (float)pd.n; P.mi = pd.mi; P.ni = pd.ni;
+        const PotF32 P = md_pot_f32(pd, inv_h);
         (void)h;
         AP_DISPATCH(launch_f32, c, grid, P, (float)(rc2 * inv_h * inv_h), rc2, inv_h);
         c->stats.kernel_launches += 2;

@@ -23,6 +23,7 @@
 #include "ctx.h"
 #include "comm.h"
 #include "finalize.cuh"
+#include "pair.cuh"
 
 #define SORT_THREADS 256
 #define SORT_ITEMS 8
@@ -137,6 +138,7 @@ struct CellState {
     int     id_bits = 0, cell_bits = 0;
     int     finish_blocks = 1184;         // grid of the finish kernel: 8 blocks per SM
     double *pe_fold = nullptr;            // [finish_blocks] PE partials of the force kernel folded by the finish blocks
+    double *ke_glob = nullptr;            // world > 1: one double, the all-reduced mean_ke of a step (quench bookkeeping)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -741,12 +743,11 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
 // slots are cell-sorted.  Borderline decisions (image tie, |r2 - rc2| within the fp32 guard band) are
 // masked out of the hot loop and redone from the float64 positions, like in the all-pairs kernels.
 // ---------------------------------------------------------------------------------------------------
-struct LjF64 { double c6, sigma2; };   // c6 = 6 lambda eps / m
-struct LjF32 { float c6, sigma2; };    // in fixed-point units (see allpairs.cu)
-
+// POTK = POTF_LJ: sqrt-free Lennard-Jones; POTF_MIE: the generic bounded-Mie member (pair.cuh).
+template <int POTK>
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_own, long long cap, const int *__restrict__ nbr,
-                const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, LjF64 P,
+                const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, PotF64 P,
                 double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
@@ -767,14 +768,12 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_
             const double dz = md_minimg_list(pj.z - pi.z, L, halfL);
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool ok = r2 < rc2;
-            const double inv = ok ? md_rcp(r2) : 0.0;
-            const double t2 = P.sigma2 * inv;
-            const double t6 = t2 * t2 * t2;
-            const double s = (P.c6 * inv) * (t6 * fma(-2.0, t6, 1.0));
+            double s, u;
+            md_pair<POTK>(r2, ok, P, s, u);
             fx = fma(dx, s, fx);
             fy = fma(dy, s, fy);
             fz = fma(dz, s, fz);
-            pe += fma(t6, t6, -t6);
+            pe += u;
             cnt += ok ? 1u : 0u;
         }
         acc[i] = fx;
@@ -789,11 +788,11 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_
     }
 }
 
-template <bool TEX>
+template <bool TEX, int POTK>
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const double *__restrict__ r64, long long i_begin, long long n_own, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
-                double rc2, float rc2s, double inv_h, LjF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
+                double rc2, float rc2s, double inv_h, PotF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
                 StepScalars *__restrict__ sc, int guarded) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
@@ -827,14 +826,12 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const do
                 const bool inside = r2 < cut_lo, maybe = r2 < cut_hi;
                 flagged |= ((maybe && !inside) ? 1u : 0u) << u;
                 const bool  ok = inside && (j[u] != (int)i);
-                const float inv = ok ? md_rcpf(r2) : 0.0f;
-                const float t2 = P.sigma2 * inv;
-                const float t6 = t2 * t2 * t2;
-                const float s = (P.c6 * inv) * (t6 * fmaf(-2.0f, t6, 1.0f));
+                float s, w;
+                md_pair<POTK>(r2, ok, P, s, w);
                 fx = fmaf(dx, s, fx);
                 fy = fmaf(dy, s, fy);
                 fz = fmaf(dz, s, fz);
-                pe += fmaf(t6, t6, -t6);
+                pe += w;
                 cnt += ok ? 1u : 0u;
             }
             while (flagged) {  // rare: decide and evaluate from the float64 positions
@@ -849,14 +846,12 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const do
                 if (r2d < rc2) {
                     const float dx = (float)(ex * inv_h), dy = (float)(ey * inv_h), dz = (float)(ez * inv_h);
                     const float r2 = (float)(r2d * inv_h * inv_h);
-                    const float inv = md_rcpf(r2);
-                    const float t2 = P.sigma2 * inv;
-                    const float t6 = t2 * t2 * t2;
-                    const float s = (P.c6 * inv) * (t6 * fmaf(-2.0f, t6, 1.0f));
+                    float s, w;
+                    md_pair<POTK>(r2, true, P, s, w);
                     fx = fmaf(dx, s, fx);
                     fy = fmaf(dy, s, fy);
                     fz = fmaf(dz, s, fz);
-                    pe += fmaf(t6, t6, -t6);
+                    pe += w;
                     cnt += 1u;
                 }
             }
@@ -961,6 +956,28 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
         md_finalize_body(fin, sc, red);
         if (threadIdx.x == 0) sc->finish_blocks_done = 0u;
     }
+}
+
+// world > 1: the temperature / quench-scale bookkeeping of md_finalize_body redone from the all-reduced mean_ke
+__global__ void k_mr_quench_fix(StepScalars *__restrict__ sc, const double *__restrict__ ke_glob, const double *__restrict__ quench_next,
+                                double kb, int redo) {
+    const double mean_ke = *ke_glob;
+    sc->ke_prev = mean_ke;
+    if (!redo) return;
+    // sc->temp was only overwritten by the finish kernel if the next step has a target, in which case it is
+    // overwritten again here; otherwise it still holds self.temp
+    double scale = 1.0, temp = sc->temp;
+    if (quench_next) {
+        for (int t = 0; t < 2; ++t) {
+            const double target = quench_next[t];
+            if (target == target) {
+                temp = (2.0 / 3.0) * mean_ke / kb;
+                if (temp != 0.0) scale *= sqrt(target / temp);
+            }
+        }
+    }
+    sc->temp = temp;
+    sc->scale = scale;
 }
 
 __global__ void k_unsort(const double *__restrict__ src, const int *__restrict__ id, long long n, long long cap,
@@ -1364,10 +1381,6 @@ int md_cells_setup(mdsea_ctx *c) {
     CellState *s = new CellState();
     c->cells = s;
     const mdsea_params &p = c->p;
-    if (c->pot.fast != POTF_LJ) {
-        md_set_error(c, "cutoff path: only the Lennard-Jones member of the Mie family is implemented on the list kernels");
-        return MDSEA_ERR_UNSUPPORTED;
-    }
     const double skin = p.skin > 0 ? p.skin : 0.0;
     s->rlist = p.r_cutoff + skin;
     s->rl2 = s->rlist * s->rlist;
@@ -1469,6 +1482,7 @@ int md_cells_setup(mdsea_ctx *c) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
         s->finish_blocks = 8 * sms;
         MD_CUDA(c, cudaMalloc(&s->pe_fold, sizeof(double) * s->finish_blocks));
+        MD_CUDA(c, cudaMalloc(&s->ke_glob, sizeof(double)));
     }
     c->n_ke_part = md_div_up(s->cap, 256);
     MD_CUDA(c, cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
@@ -1504,6 +1518,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->scratch); cudaFree(s->d_cnt); cudaFree(s->sendpool); cudaFree(s->recvpool); cudaFree(s->d_cnt_all);
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
     cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_roff);
+    cudaFree(s->pe_fold); cudaFree(s->ke_glob);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
@@ -1867,28 +1882,32 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
     CellState *s = c->cells;
     if (i1 <= i0) return MDSEA_OK;
     const int grid = force_grid(i0, i1);
+    const bool lj = c->pot.fast == POTF_LJ;
     if (c->p.precision == MDSEA_FP64) {
-        LjF64 P;
-        P.c6 = 6.0 * c->pot.lam_eps * c->pot.inv_mass;
-        P.sigma2 = c->pot.sigma2;
-        k_nbr_force_f64<<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr,
-                                                            c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off, c->d_sc,
-                                                            guarded);
+        const PotF64 P = md_pot_f64(c->pot);
+#define NBR_F64(POTK)                                                                                                              \
+    k_nbr_force_f64<POTK><<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr, \
+                                                              c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off,   \
+                                                              c->d_sc, guarded)
+        if (lj) NBR_F64(POTF_LJ);
+        else NBR_F64(POTF_MIE);
+#undef NBR_F64
     } else {
         const double inv_h = fixed_inv_h(c);
-        LjF32 P;
-        P.c6 = (float)(6.0 * c->pot.lam_eps * c->pot.inv_mass * inv_h);
-        P.sigma2 = (float)(c->pot.sigma2 * inv_h * inv_h);
-        if (s->tex_pos)
-            k_nbr_force_f32<true><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr,
-                                                                     s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,
-                                                                     (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
-                                                                     c->d_pe_part + pe_off, c->d_sc, guarded);
-        else
-            k_nbr_force_f32<false><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, 0, c->d_r, i0, i1, s->cap, s->nbr,
-                                                                      s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,
-                                                                      (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,
-                                                                      c->d_pe_part + pe_off, c->d_sc, guarded);
+        const PotF32 P = md_pot_f32(c->pot, inv_h);
+#define NBR_F32(TEX, POTK)                                                                                                         \
+    k_nbr_force_f32<TEX, POTK><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr, \
+                                                                   s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,         \
+                                                                   (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,            \
+                                                                   c->d_pe_part + pe_off, c->d_sc, guarded)
+        if (s->tex_pos) {
+            if (lj) NBR_F32(true, POTF_LJ);
+            else NBR_F32(true, POTF_MIE);
+        } else {
+            if (lj) NBR_F32(false, POTF_LJ);
+            else NBR_F32(false, POTF_MIE);
+        }
+#undef NBR_F32
     }
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
@@ -1996,10 +2015,11 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
     const int  W = c->p.world;
     const bool verlet = c->p.algorithm == MDSEA_ALGO_VERLET;
     const bool reuse = verlet && c->p.force_evals_per_step == 1;
-    if (W > 1 && a->quench_targets) {
-        md_set_error(c, "run: quench / isothermal runs are not supported with world > 1 yet");
-        return MDSEA_ERR_UNSUPPORTED;
-    }
+    // world > 1: the finish kernel's bookkeeping only sees this rank's share of mean_ke.  _quench needs the GLOBAL
+    // value of the previous step (simulator.py:192-195, 233-239), so a batch that carries quench targets all-reduces
+    // one double per step and redoes the temperature / scale bookkeeping from it; every batch leaves the global
+    // mean_ke of its last step in the scalars for the first step of the next batch.
+    const bool mr_quench = W > 1 && a->quench_targets;
     for (int k = 0; k < a->nsteps; ++k) {
         if (verlet) {
             if (reuse && c->acc_valid) {
@@ -2015,6 +2035,14 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
         }
         MD_TRY(force_after_drift(c, a, k, g_dt));                 // simulator.py:544 + kick + energies + row
         c->acc_valid = true;
+        if (mr_quench || (W > 1 && k == a->nsteps - 1)) {
+            CellState *s = c->cells;
+            MD_CUDA(c, cudaMemcpyAsync(s->ke_glob, c->d_ke_rows + k, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            MD_TRY(md_comm_allreduce_sum_f64(c, s->ke_glob, 1));
+            k_mr_quench_fix<<<1, 1, 0, c->stream>>>(c->d_sc, s->ke_glob, (mr_quench && k + 1 < a->nsteps) ? c->d_quench + (size_t)(k + 1) * 2 : nullptr,
+                                                    a->k_boltzmann, mr_quench ? 1 : 0);
+            c->stats.kernel_launches += 1;
+        }
     }
     if (W > 1) {  // global energies: one small allreduce per batch (the rows hold this rank's share of the means)
         MD_TRY(md_comm_allreduce_sum_f64(c, c->d_pe_rows, a->nsteps));

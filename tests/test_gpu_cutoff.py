@@ -19,9 +19,11 @@ RC, SKIN = 2.5, 0.3
 def _ctx(n, L, dt, precision=0, evals=2, ring=32, rc=RC, skin=SKIN, **kw):
     from mdsea_b200 import _capi
 
-    return _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1,
-                         precision=precision, epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=rc, skin=skin,
-                         force_evals_per_step=evals, ring_rows=ring, device=0, **kw)
+    pot = dict(epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, mass=1.0)
+    pot.update({k: kw.pop(k) for k in list(kw) if k in pot})
+    return _capi.Context(ndim=3, num_particles=n, boxlen=L, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1,
+                         precision=precision, r_cutoff=rc, skin=skin,
+                         force_evals_per_step=evals, ring_rows=ring, device=0, **pot, **kw)
 
 
 def _liquid(per_row, seed=0, vf=0.3, melt_steps=40):
@@ -199,6 +201,100 @@ def test_cutoff_path_from_lattice_start_through_python_api(tmp_path, monkeypatch
     assert np.abs(sm.get_ds("r_coords") - ref["r"]).max() <= 1e-9 * sm.LEN_BOX
     assert np.abs(sm.get_ds("v_coords") - ref["v"]).max() <= 1e-9
     o.close()
+
+
+# ---- the rest of the bounded-Mie family, quench / isothermal and gravity on the list kernels ----
+# Oracle: the NumPy restatement with a cutoff (all pairs, masked by dist < rc) -- the list only changes WHICH pairs
+# are visited, never their arithmetic, so energies / forces / trajectories must agree to the fp64 / fp32 tolerances.
+MIE_CASES = {
+    "mie_9_6": dict(m=9, n=6, a=0.0, epsilon=1.0, sigma=1.0),
+    "boundedmie_a02": dict(m=12, n=6, a=0.2, epsilon=0.8, sigma=1.1),     # examples/initsetup.py's member, eps/sigma != 1
+    "mie_odd_exponents": dict(m=11, n=5, a=0.0, epsilon=1.0, sigma=1.0),  # sqrt path of the pair kernel
+}
+
+
+def _mie_ctx(n, L, dt, case, **kw):
+    c = MIE_CASES[case]
+    return _ctx(n, L, dt, epsilon=c["epsilon"], sigma=c["sigma"], mie_m=float(c["m"]), mie_n=float(c["n"]), mie_a=c["a"], **kw)
+
+
+@pytest.mark.parametrize("case", sorted(MIE_CASES))
+@pytest.mark.parametrize("precision", [0, 1])
+def test_mie_family_forces_and_pe_on_the_list_kernels(case, precision):
+    n, L, r, v, dt = _liquid(10)
+    onp = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(**MIE_CASES[case]), r_cutoff=RC)
+    ref_acc = onp.update_acc()
+    onp.update_energies()
+    ref_pe = onp.mean_pe
+    ctx = _mie_ctx(n, L, dt, case, precision=precision)
+    ctx.set_state(r, v)
+    acc, pe = ctx.update_acc()
+    if precision == 0:
+        assert force_rel_err(acc, ref_acc) <= 1e-10
+        assert abs(pe - ref_pe) <= 1e-10 * abs(ref_pe)
+    else:
+        assert force_rel_err_pairscale(acc, ref_acc, onp.pair_force_scale()) <= 1e-5
+        assert abs(pe - ref_pe) <= 1e-5 * abs(ref_pe)
+    ctx.close()
+
+
+@pytest.mark.parametrize("case,evals", [("mie_9_6", 2), ("boundedmie_a02", 1)])
+def test_mie_family_run_on_the_list_kernels(case, evals):
+    n, L, r, v, dt = _liquid(10)
+    steps = 60
+    ref = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(**MIE_CASES[case]), r_cutoff=RC).run(steps)
+    ctx = _mie_ctx(n, L, dt, case, evals=evals, ring=steps)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    rows = ctx.run(steps, kb=1.0)
+    np.testing.assert_allclose(rows["pe"], ref["pe"], rtol=1e-10)
+    np.testing.assert_allclose(rows["ke"], ref["ke"], rtol=1e-10)
+    assert np.abs(rows["r"] - ref["r"]).max() <= 1e-9 * L
+    assert np.abs(rows["v"] - ref["v"]).max() <= 1e-9
+    assert ctx.stats()["list_rebuilds"] >= 2
+    ctx.close()
+
+
+def _quench_array(steps, temp_init, isothermal, quench_steps, quench_temps):
+    q = np.full((steps, 2), np.nan)
+    qt = list(quench_temps)
+    for k in range(steps):
+        if isothermal:
+            q[k, 0] = temp_init
+        if k in quench_steps:
+            q[k, 1] = qt.pop(0)
+    return q
+
+
+@pytest.mark.parametrize("mode", ["quench", "isothermal", "gravity", "isothermal+quench+gravity"])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_quench_isothermal_gravity_on_the_cutoff_path(mode, precision):
+    """_quench / apply_special / apply_field (simulator.py:185-205) on the cut-off path, batches of 10 steps."""
+    n, L, r, v, dt = _liquid(10)
+    steps, batch = 40, 10
+    iso, grav = "isothermal" in mode, "gravity" in mode
+    qs, qt = ([7, 10, 29], [0.6, 0.3, 0.9]) if "quench" in mode else ([], [])
+    ref = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(), r_cutoff=RC, temp=1.0, kb=1.0, isothermal=iso, gravity=grav,
+                       g_acc=9.80665, quench_steps=list(qs), quench_temps=list(qt)).run(steps)
+    ctx = _ctx(n, L, dt, precision=precision, evals=1, ring=batch)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    q = _quench_array(steps, 1.0, iso, qs, qt)
+    pe, ke, temp, rr, vv = [], [], [], [], []
+    for b in range(steps // batch):
+        qb = q[b * batch:(b + 1) * batch]
+        rows = ctx.run(batch, kb=1.0, g=9.80665 if grav else 0.0, quench=None if np.isnan(qb).all() else qb)
+        pe.append(rows["pe"].copy()); ke.append(rows["ke"].copy()); temp.append(rows["temp"].copy())
+        rr.append(rows["r"][-1].copy()); vv.append(rows["v"][-1].copy())
+    pe, ke, temp = np.concatenate(pe), np.concatenate(ke), np.concatenate(temp)
+    etol, xtol = (1e-10, 1e-9) if precision == 0 else (1e-5, 1e-3)
+    np.testing.assert_allclose(pe, ref["pe"], rtol=etol)
+    np.testing.assert_allclose(ke, ref["ke"], rtol=etol)
+    np.testing.assert_allclose(temp, ref["temp"], rtol=etol)
+    for b in range(steps // batch):
+        assert np.abs(rr[b] - ref["r"][(b + 1) * batch - 1]).max() <= xtol * (L if precision == 0 else 1.0)
+        assert np.abs(vv[b] - ref["v"][(b + 1) * batch - 1]).max() <= xtol * (1.0 if precision == 0 else 10.0)
+    ctx.close()
 
 
 def test_neighbor_capacity_overflow_is_reported():

@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 _KEY = [1000]
 
 
-def _run_ranks(world, grid, n, L, dt, r, v, steps, precision=0, evals=2, batch=None, want_lists=False):
+def _run_ranks(world, grid, n, L, dt, r, v, steps, precision=0, evals=2, batch=None, want_lists=False, quench=None, g=0.0,
+               pot=None):
     from mdsea_b200 import _capi
 
     _KEY[0] += 1
@@ -31,19 +32,24 @@ def _run_ranks(world, grid, n, L, dt, r, v, steps, precision=0, evals=2, batch=N
 
     def worker(rank):
         try:
+            pk = dict(epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0)
+            pk.update(pot or {})
             ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1,
-                                precision=precision, epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=RC,
+                                precision=precision, r_cutoff=RC,
                                 skin=SKIN, force_evals_per_step=evals, ring_rows=batch, device=0, rank=rank, world=world,
-                                proc_grid=grid)
+                                proc_grid=grid, **pk)
             ctx.comm_init_local(key)
             ctx.set_temperature(1.0)
             ctx.set_state(r, v)
-            res = dict(pe=[], ke=[], rows=[])
-            for _ in range(steps // batch):
-                rows = ctx.run(batch, kb=1.0)
-                res["pe"].append(rows["pe"].copy()); res["ke"].append(rows["ke"].copy())
+            res = dict(pe=[], ke=[], temp=[], rows=[])
+            for b in range(steps // batch):
+                qb = None if quench is None else quench[b * batch:(b + 1) * batch]
+                if qb is not None and np.isnan(qb).all():
+                    qb = None
+                rows = ctx.run(batch, kb=1.0, g=g, quench=qb)
+                res["pe"].append(rows["pe"].copy()); res["ke"].append(rows["ke"].copy()); res["temp"].append(rows["temp"].copy())
                 res["rows"].append({k: rows[k].copy() for k in ("r", "v", "ids", "n_owned")})
-            res["pe"] = np.concatenate(res["pe"]); res["ke"] = np.concatenate(res["ke"])
+            res["pe"] = np.concatenate(res["pe"]); res["ke"] = np.concatenate(res["ke"]); res["temp"] = np.concatenate(res["temp"])
             res["stats"] = ctx.stats()
             if want_lists:
                 res["cells"] = ctx.get_cells()
@@ -154,6 +160,37 @@ def test_uneven_blocks_and_lattice_start():
     for res in out2:
         np.testing.assert_allclose(res["pe"], ref2["pe"], rtol=1e-10)
     o.close(); o2.close()
+
+
+def test_decomposed_quench_isothermal_gravity_and_mie():
+    """world > 1: _quench needs the GLOBAL mean_ke of the previous step (one all-reduced double per step); the
+    bounded-Mie list kernels; quench targets in the first step of a batch and in batches that follow plain ones."""
+    from oracle.oracle_np import MiePotential, OracleSolver
+    from test_gpu_cutoff import _quench_array
+
+    n, L, r, v, dt = _liquid(12)
+    steps, batch = 30, 10
+    qs, qt = [10, 14, 29], [0.5, 0.8, 0.2]          # step 10 = first step of the second batch (the first batch is plain)
+    ref = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(), r_cutoff=RC, temp=1.0, kb=1.0, gravity=True,
+                       quench_steps=list(qs), quench_temps=list(qt)).run(steps)
+    q = _quench_array(steps, 1.0, False, qs, qt)
+    out = _run_ranks(4, (2, 2, 1), n, L, dt, r, v, steps, evals=1, batch=batch, quench=q, g=9.80665)
+    for res in out:
+        np.testing.assert_allclose(res["pe"], ref["pe"], rtol=1e-10)
+        np.testing.assert_allclose(res["ke"], ref["ke"], rtol=1e-10)
+        np.testing.assert_allclose(res["temp"], ref["temp"], rtol=1e-10)
+    rr, vv = _assemble_rows(out, steps, n, batch)
+    assert np.abs(rr - ref["r"]).max() <= 1e-9 * L
+    assert np.abs(vv - ref["v"]).max() <= 1e-9
+    # isothermal + Mie(9, 6) on 2 ranks
+    mie = dict(m=9, n=6, a=0.0, epsilon=1.0, sigma=1.0)
+    ref2 = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(**mie), r_cutoff=RC, temp=1.0, kb=1.0, isothermal=True).run(20)
+    out2 = _run_ranks(2, (1, 2, 1), n, L, dt, r, v, 20, evals=2, batch=10, quench=_quench_array(20, 1.0, True, [], []),
+                      pot=dict(mie_m=9.0, mie_n=6.0))
+    for res in out2:
+        np.testing.assert_allclose(res["pe"], ref2["pe"], rtol=1e-10)
+        np.testing.assert_allclose(res["ke"], ref2["ke"], rtol=1e-10)
+        np.testing.assert_allclose(res["temp"], ref2["temp"], rtol=1e-10)
 
 
 def test_multirank_argument_errors():
