@@ -324,6 +324,16 @@ def run_ours(args, wl):
     integ_bytes = n_loc * ndim * (5 * 8 + 4 * 8 + 2 * 8)
     if wl["r_cutoff"] > 0:  # + build positions read (trigger) and the packed position copy written by the drift kernel
         integ_bytes += n_loc * (ndim * 8 + (16 if precision == "fp32" else 32))
+    # DRAM bytes per launch of the force kernel from the tracked ncu --set full capture of this workload (same N)
+    force_traffic, force_traffic_src = None, None
+    if world == 1 and wl is WORKLOADS.get("c3"):
+        src = "r01_ncu_c3_force_f64.txt" if fp64 else "r01_ncu_c3_kernels.txt"
+        force_traffic = ncu_traffic(src, "k_nbr_force_f64" if fp64 else "k_nbr_force_f32")
+        force_traffic_src = "profiles/" + src if force_traffic else None
+    elif world == 1 and wl is WORKLOADS.get("c2"):
+        src = "r01_ncu_c2_allpairs_f64.txt" if fp64 else "r01_ncu_c2_allpairs_f32.txt"
+        force_traffic = ncu_traffic(src, "k_allpairs")
+        force_traffic_src = "profiles/" + src if force_traffic else None
     roof_hbm = None
     if i_ms > 0:
         roof_hbm = {"bound": "hbm", "kernel": "fused integrator (kick_finish + kick_drift)", "achieved": integ_bytes / (i_ms * 1e-3) / 1e9,
@@ -375,7 +385,8 @@ def run_ours(args, wl):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64" if fp64 else "fp32", "kernel": "all-pairs force" if wl["r_cutoff"] <= 0 else "neighbour-list force",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": force_traffic,
+                         "traffic_source": force_traffic_src,
                          "flop_per_unique_pair": FLOP_PER_UNIQUE_PAIR[ndim], "unique_pairs_per_launch": f_pairs,
                          "ms_per_launch": f_ms,
                          "peak_source": "FMA micro-benchmark of the CUDA-core pipe measured in this run "
@@ -389,6 +400,29 @@ def run_ours(args, wl):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def ncu_traffic(summary, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the first block of `kernel` in a tracked
+    `ncu --set full` summary under profiles/ (written by profiles/summarize.py); None when there is no such capture."""
+    try:
+        lines = open(os.path.join(ROOT, "profiles", summary)).read().splitlines()
+    except OSError:
+        return None
+    tot, inside, seen = 0.0, False, 0
+    for ln in lines:
+        if ln.startswith("== "):
+            if inside:
+                break
+            inside = kernel in ln
+        elif inside and ln.startswith("dram__bytes_"):
+            f = ln.split()
+            tot += float(f[1]) * _UNIT.get(f[2], 1.0)
+            seen += 1
+    return tot if seen == 2 else None
 
 
 def allpairs_extra(local):

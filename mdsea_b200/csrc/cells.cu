@@ -136,9 +136,15 @@ struct CellState {
     int    *d_flag_mapped = nullptr;      // device alias of h_flag
     cudaEvent_t ev_flag = nullptr;
     int     id_bits = 0, cell_bits = 0;
-    int     finish_blocks = 1184;         // grid of the finish kernel: 8 blocks per SM
+    int     finish_blocks = 1480;         // grid of the finish kernel: two full waves of its resident blocks per SM (5 -> 10 per SM)
+    int     finish_blocks_fused = 888;    // same for the variant that also starts the next step (3 resident -> 6 per SM)
     double *pe_fold = nullptr;            // [finish_blocks] PE partials of the force kernel folded by the finish blocks
     double *ke_glob = nullptr;            // world > 1: one double, the all-reduced mean_ke of a step (quench bookkeeping)
+    // Skin-trigger tags.  StepScalars::rebuild_flag holds the TAG of the drift whose trigger fired (0: none); every drift
+    // gets the next tag (same sequence on all ranks).  Guards compare against the tag of the drift they depend on, so
+    // the finish kernel of step k can be guarded by drift k's trigger while its fused drift k+1 raises its own.
+    int     drift_tag = 0;
+    int     published_tag = 0;            // single GPU: the fused finish kernel already published this tag's trigger (h_flag[2 + (tag & 1)])
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -552,17 +558,28 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
 // candidate window stays inside half a period: (run + 2) cells < nc in x, 3 cells < nc in y and z.  The host
 // therefore passes run_max = min(NBW_RUN, nc - 3) and uses the thread-per-particle kernel when nc == 3.
 
-// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle
-__device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ cand, int ncand, float xi, float yi, float zi,
-                                                   float neg_rl2s, float neg_bw, float &bandmin) {
+// test one staged chunk (<= 32 candidates, padded with far-away dummies) against this lane's particle.
+// Expanded form r^2 - rl^2 = |c|^2 + (|p|^2 - rl^2) - 2 p.c: the candidate carries w = |c|^2 and the lane k = |p|^2 - rl^2
+// (both rounded ONCE from float64), so a test costs 3 FFMA + 1 FADD on the FMA pipe instead of 3 FADD + 3 FFMA -- the
+// kernel is bound by that pipe.  Offsets stay below ~4 cells in x and 1.5 cells in y / z, which bounds the rounding
+// error of the chain (largest term last) by ~5e-6 rl^2; the guard band (2e-5 rl^2) covers it.
+template <bool EXPANDED>
+__device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ cand, int ncand, float a, float b, float cc, float k,
+                                                   float neg_bw, float &bandmin) {
+    // EXPANDED: (a, b, cc) = -2 p, k = |p|^2 - rl^2; direct form: (a, b, cc) = p, k = -rl^2
     unsigned m = 0u;
     for (int t0 = 0; t0 < ncand; t0 += 8) {
         unsigned m8 = 0u;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 cj = cand[t0 + u];   // broadcast LDS.128
-            const float dx = cj.x - xi, dy = cj.y - yi, dz = cj.z - zi;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, neg_rl2s)));   // r^2 - rl^2
+            float d;                          // r^2 - rl^2
+            if (EXPANDED) {
+                d = fmaf(a, cj.x, fmaf(b, cj.y, fmaf(cc, cj.z, k))) + cj.w;
+            } else {
+                const float dx = cj.x - a, dy = cj.y - b, dz = cj.z - cc;
+                d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, k)));
+            }
             if (d < neg_bw) m8 |= 1u << u;
             bandmin = fminf(bandmin, fabsf(d));
         }
@@ -571,13 +588,72 @@ __device__ __forceinline__ unsigned nbw_test_chunk(const float4 *__restrict__ ca
     return m;
 }
 
-__global__ void __launch_bounds__(NBW_WARPS * 32)
+// staged candidate: float offsets from the pass origin (+ their squared norm, one rounding, for the expanded form)
+template <bool EXPANDED>
+__device__ __forceinline__ float4 nbw_stage(const uint4 qj, uint32_t ox, uint32_t oy, uint32_t oz) {
+    const float x = (float)(int)(qj.x - ox), y = (float)(int)(qj.y - oy), z = (float)(int)(qj.z - oz);
+    if (!EXPANDED) return make_float4(x, y, z, 0.0f);
+    const double w = fma((double)x, (double)x, fma((double)y, (double)y, (double)z * (double)z));
+    return make_float4(x, y, z, (float)w);
+}
+template <bool EXPANDED>
+__device__ __forceinline__ float4 nbw_dummy() {   // a candidate infinitely far away
+    return EXPANDED ? make_float4(0.0f, 0.0f, 0.0f, 1.0e30f) : make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
+}
+
+// Appends are DEFERRED: every tested chunk leaves its 32-bit hit mask per lane (and its first slot per lane group) in
+// shared memory, and the row is written in one pass per NBW_MAXCH chunks.  Appending chunk by chunk made the warp
+// wait for the lane with the most hits in EVERY chunk (7.7 iterations for 3.2 hits on average, 20 % of the kernel's
+// instructions in r01); over a whole tile the lanes' totals are nearly equal (~56 each).
+#define NBW_MAXCH 8
+__device__ __forceinline__ void nbw_flush(const unsigned *__restrict__ mask_w, const int *__restrict__ base_w, int n_ch, int lane,
+                                          int grp, int *__restrict__ row0, int max_nbr, int &cnt) {
+    __syncwarp();
+    const unsigned long long row_addr = (unsigned long long)row0;
+    int      k = 0, base = 0;
+    unsigned m = 0u;
+    for (;;) {
+        // next non-empty mask of this lane (the inner loop reconverges at once; a `continue` on an empty mask instead made
+        // the lane wait at the convergence barrier until every other lane of the warp had met an empty mask too)
+        while (m == 0u && k < n_ch) {
+            m = mask_w[k * 32 + lane];
+            base = base_w[k * NBW_G + grp];
+            ++k;
+        }
+        if (m == 0u) break;
+        const int t1 = __ffs(m) - 1;
+        m &= m - 1;
+        // a full row keeps counting (the overflow is reported by the caller); every entry below nbr_cnt is a valid slot
+        // entry k of the tile-sliced row (md_nbr_off): one IMAD.WIDE + STG
+        asm volatile("st.global.b32 [%0], %1;" ::"l"(row_addr + (unsigned long long)(unsigned)min(cnt, max_nbr - 1) * 128ull), "r"(base + t1) : "memory");
+        ++cnt;
+    }
+    __syncwarp();
+}
+
+// immediate append of one chunk's hits (the r01 scheme; A/B baseline of the deferred flush)
+__device__ __forceinline__ void nbw_append_now(unsigned m, int base, int *&wp, int max_nbr, int &cnt) {
+    while (m) {
+        const int t1 = __ffs(m) - 1;
+        m &= m - 1;
+        if (cnt < max_nbr) {   // a full row keeps counting (the overflow is reported by the caller); every entry
+            *wp = base + t1;   // below nbr_cnt is always a valid slot
+            wp += 32;          // next entry of the tile-sliced row (md_nbr_off)
+        }
+        ++cnt;
+    }
+}
+
+template <bool EXPANDED, bool DEFER>
+__global__ void __launch_bounds__(NBW_WARPS * 32, 9)
 k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
-                 double L, double halfL, double cell_len, double inv_h, double rl2, float rl2s, float bw, float rl2s_lo,
+                 double L, double halfL, double cell_len, double inv_h, double rl2, double rl2s_d, float bw, float rl2s_lo,
                  float rl2s_hi, int max_nbr, int run_max, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
                  StepScalars *__restrict__ sc) {
     __shared__ float4 s_cand[NBW_WARPS][NBW_G][32];
+    __shared__ unsigned s_mask[NBW_WARPS][DEFER ? NBW_MAXCH * 32 : 1];
+    __shared__ int      s_base[NBW_WARPS][DEFER ? NBW_MAXCH * NBW_G : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
     if (i0 >= n_own) return;   // whole warp out of range (only __syncwarp below)
@@ -591,8 +667,9 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
     const int grp = lane / (32 / NBW_G);            // lane group: each group walks its own candidate stream
     float4 *cand_g = s_cand[w][grp];
     int *row0 = nbr + md_nbr_row_base(il, max_nbr);
-    int *wp = row0;   // write cursor inside the row
-    const float neg_rl2s = -rl2s, neg_bw = -bw;
+    int *wp = row0;   // write cursor inside the row (immediate appends)
+    int n_ch = 0;     // chunks buffered in s_mask / s_base (warp-uniform; deferred appends)
+    const float neg_bw = -bw;
     float bandmin = 3.0e38f;
     int cnt = 0;
     unsigned todo = __ballot_sync(0xffffffffu, valid);
@@ -609,6 +686,9 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
         const uint32_t ox = md_to_fixed((cxl + 0.5 * (double)(cxb - cxl + 1)) * cell_len, inv_h);
         const uint32_t oy = md_to_fixed((cyl + 0.5) * cell_len, inv_h), oz = md_to_fixed((czl + 0.5) * cell_len, inv_h);
         const float xi = (float)(int)(qi.x - ox), yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
+        const float px2 = EXPANDED ? -2.0f * xi : xi, py2 = EXPANDED ? -2.0f * yi : yi, pz2 = EXPANDED ? -2.0f * zi : zi;
+        const float ki = EXPANDED ? (float)(fma((double)xi, (double)xi, fma((double)yi, (double)yi, (double)zi * (double)zi)) - rl2s_d)
+                                  : -(float)rl2s_d;
         // Candidate streams per lane group: the 8 consecutive particles of a group span 1-2 cells, so the group only
         // needs the cells [its first cell - 1, its last cell + 1] of every row -- about 3.6 cells instead of the 5.5
         // the whole tile needs.  tlo / thi index the pass's candidate cells (t = 0 is cell cxl - 1).
@@ -649,35 +729,39 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                     const int E_all = __shfl_sync(0xffffffffu, ce_l, dyi * 8 + (grp_on ? thi : 0));
                     const int S = grp_on ? S_all : 0, E = grp_on ? E_all : 0;
                     const int len_max = __reduce_max_sync(0xffffffffu, E - S);
+                    int Sg[NBW_G], Eg[NBW_G];
+#pragma unroll
+                    for (int k = 0; k < NBW_G; ++k) {
+                        Sg[k] = __shfl_sync(0xffffffffu, S, k * (32 / NBW_G));
+                        Eg[k] = __shfl_sync(0xffffffffu, E, k * (32 / NBW_G));
+                    }
                     for (int c0 = 0; c0 < len_max; c0 += 32) {
                         __syncwarp();
 #pragma unroll
                         for (int k = 0; k < NBW_G; ++k) {   // lane L stages candidate L of every group's chunk
-                            const int Sk = __shfl_sync(0xffffffffu, S, k * (32 / NBW_G)), Ek = __shfl_sync(0xffffffffu, E, k * (32 / NBW_G));
+                            const int Sk = Sg[k], Ek = Eg[k];
                             const int jj = Sk + c0 + lane;
-                            float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
-                            if (jj < Ek) {
-                                const uint4 qj = q[jj];
-                                cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), 0.0f);
-                            }
+                            float4 cd = nbw_dummy<EXPANDED>();
+                            if (jj < Ek) cd = nbw_stage<EXPANDED>(q[jj], ox, oy, oz);
                             s_cand[w][k][lane] = cd;
                         }
                         __syncwarp();
                         const int base = S + c0;
                         float bm = 3.0e38f;
-                        unsigned m = nbw_test_chunk(cand_g, min(32, len_max - c0), xi, yi, zi, neg_rl2s, neg_bw, bm);
+                        unsigned m = nbw_test_chunk<EXPANDED>(cand_g, min(32, len_max - c0), px2, py2, pz2, ki, neg_bw, bm);
                         if (mine) bandmin = fminf(bandmin, bm);
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        while (m) {
-                            const int t1 = __ffs(m) - 1;
-                            m &= m - 1;
-                            if (cnt < max_nbr) {
-                                *wp = base + t1;
-                                wp += 32;
+                        if (DEFER) {
+                            s_mask[w][n_ch * 32 + lane] = m;
+                            if ((lane & (32 / NBW_G - 1)) == 0) s_base[w][n_ch * NBW_G + grp] = base;
+                            if (++n_ch == NBW_MAXCH) {
+                                nbw_flush(s_mask[w], s_base[w], n_ch, lane, grp, row0, max_nbr, cnt);
+                                n_ch = 0;
                             }
-                            ++cnt;
+                        } else {
+                            nbw_append_now(m, base, wp, max_nbr, cnt);
                         }
                     }
                     continue;
@@ -694,28 +778,26 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                     // flush the pending range, 32 candidates at a time
                     for (int base = rs; base < re; base += 32) {
                         const int jj = base + lane;
-                        float4 cd = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
-                        if (jj < re) {
-                            const uint4 qj = q[jj];
-                            cd = make_float4((float)(int)(qj.x - ox), (float)(int)(qj.y - oy), (float)(int)(qj.z - oz), 0.0f);
-                        }
+                        float4 cd = nbw_dummy<EXPANDED>();
+                        if (jj < re) cd = nbw_stage<EXPANDED>(q[jj], ox, oy, oz);
                         __syncwarp();
                         cand[lane] = cd;
                         __syncwarp();
                         float bm = 3.0e38f;
-                        unsigned m = nbw_test_chunk(cand, min(32, re - base), xi, yi, zi, neg_rl2s, neg_bw, bm);
+                        unsigned m = nbw_test_chunk<EXPANDED>(cand, min(32, re - base), px2, py2, pz2, ki, neg_bw, bm);
                         if (mine) bandmin = fminf(bandmin, bm);
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        while (m) {
-                            const int t1 = __ffs(m) - 1;
-                            m &= m - 1;
-                            if (cnt < max_nbr) {   // a full row keeps counting (the overflow is reported below); every
-                                *wp = base + t1;   // entry below nbr_cnt is always a valid slot
-                                wp += 32;          // next entry of the tile-sliced row (md_nbr_off)
+                        if (DEFER) {
+                            s_mask[w][n_ch * 32 + lane] = m;
+                            if (lane < NBW_G) s_base[w][n_ch * NBW_G + lane] = base;
+                            if (++n_ch == NBW_MAXCH) {
+                                nbw_flush(s_mask[w], s_base[w], n_ch, lane, grp, row0, max_nbr, cnt);
+                                n_ch = 0;
                             }
-                            ++cnt;
+                        } else {
+                            nbw_append_now(m, base, wp, max_nbr, cnt);
                         }
                     }
                     rs = s1; re = e1;
@@ -723,6 +805,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
             }
         }
     }
+    if (DEFER && n_ch) nbw_flush(s_mask[w], s_base[w], n_ch, lane, grp, row0, max_nbr, cnt);
     if (valid) {
         if (__builtin_expect(bandmin <= bw, 0)) {   // a candidate sat in the guard band: canonical float64 redo of this particle
             bool band = false;
@@ -748,10 +831,10 @@ template <int POTK>
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_own, long long cap, const int *__restrict__ nbr,
                 const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, PotF64 P,
-                double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guarded) {
+                double *__restrict__ acc, double *__restrict__ pe_part, StepScalars *__restrict__ sc, int guard_tag) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
-    if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
+    if (guard_tag && sc->rebuild_flag == guard_tag) return;  // speculative launch: the list is stale, the host will redo this step
     const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   fx = 0.0, fy = 0.0, fz = 0.0, pe = 0.0;
     unsigned cnt = 0;
@@ -793,10 +876,10 @@ __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const double *__restrict__ r64, long long i_begin, long long n_own, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
                 double rc2, float rc2s, double inv_h, PotF32 P, double *__restrict__ acc, double *__restrict__ pe_part,
-                StepScalars *__restrict__ sc, int guarded) {
+                StepScalars *__restrict__ sc, int guard_tag) {
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
-    if (guarded && sc->rebuild_flag) return;  // speculative launch: the list is stale, the host will redo this step
+    if (guard_tag && sc->rebuild_flag == guard_tag) return;  // speculative launch: the list is stale, the host will redo this step
     const long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double   Fx = 0.0, Fy = 0.0, Fz = 0.0, PE = 0.0;
     unsigned cnt = 0;
@@ -877,7 +960,7 @@ __global__ void __launch_bounds__(256)
 k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
                  const double *__restrict__ rb, long long n, long long cap, int do_bc, int do_kick, int do_drift, double L,
                  double halfL, double dt, double trig2, int fp32, double inv_h, void *__restrict__ pos4,
-                 StepScalars *__restrict__ sc) {
+                 StepScalars *__restrict__ sc, int tag) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x[3], d2 = 0.0;
@@ -896,20 +979,33 @@ k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *_
         const double dd = md_minimg_exact(__dsub_rn(xx, rb[d * cap + i]), L, halfL);
         d2 = __dadd_rn(d2, __dmul_rn(dd, dd));
     }
-    if (do_drift && d2 > trig2) sc->rebuild_flag = 1;
+    if (do_drift && d2 > trig2) sc->rebuild_flag = tag;   // the skin trigger of THIS drift (tags: see StepScalars)
     if (fp32) ((uint4 *)pos4)[i] = make_uint4(md_to_fixed(x[0], inv_h), md_to_fixed(x[1], inv_h), md_to_fixed(x[2], inv_h), 0u);
     else ((double4 *)pos4)[i] = make_double4(x[0], x[1], x[2], 0.0);
 }
 
-__global__ void __launch_bounds__(256)
-k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
+// What the finish kernel needs to also START the next step (wrap + first half kick + drift, i.e. k_cut_kick_drift
+// fused behind the second half kick): with a(t+dt) reused as the next step's a(t), v and acc are already in registers,
+// so the fusion saves one launch and re-reading v / acc / re-writing v (96 B per particle and step).
+struct NextDrift {
+    const double *rb;     // build positions (skin trigger)
+    double L, halfL, trig2, inv_h;
+    void  *pos4;
+    int    fp32;
+    int    tag;           // trigger tag of the fused drift
+    int   *host_flag;     // single GPU: mapped host word that receives (trigger fired) from the last block; else nullptr
+};
+
+template <bool FUSE>
+__global__ void __launch_bounds__(256, FUSE ? 3 : 5)
+k_cut_kick_finish(double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
                   const int *__restrict__ id, long long n, long long cap, long long row_stride, int *__restrict__ id_row,
                   double dt, double g_dt, StepScalars *__restrict__ sc, double *__restrict__ ke_part,
-                  double *__restrict__ r_row, double *__restrict__ v_row, int guarded, FinalizeArgs fin,
-                  const double *__restrict__ pe_force, int n_pe_force, double *__restrict__ pe_fold) {
+                  double *__restrict__ r_row, double *__restrict__ v_row, int guard_tag, FinalizeArgs fin,
+                  const double *__restrict__ pe_force, int n_pe_force, double *__restrict__ pe_fold, NextDrift nd) {
     __shared__ double red[32];
     __shared__ bool   s_last;
-    if (guarded && sc->rebuild_flag) return;
+    if (guard_tag && sc->rebuild_flag == guard_tag) return;
     double v2 = 0.0;
     const double scale = sc->scale;
     // grid-stride: a bounded number of blocks (8 per SM) keeps the partial-sum array and the number of same-address
@@ -920,17 +1016,45 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
         // multi-rank: compact rows in slot order plus the ids; the host scatters them into the shared file.
         const long long col = id_row ? i : (long long)gid;
         if (id_row) id_row[i] = gid;
+        // all loads first: the stores below go through the same base pointers (r, v), so the compiler would otherwise
+        // order the next component's loads behind them and serialise three memory round trips per particle
+        double rr[3], vv[3], aa[3], bb[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            double u = v[d * cap + i] + __dmul_rn(__dmul_rn(0.5, acc[d * cap + i]), dt);
+            rr[d] = r[d * cap + i];
+            vv[d] = v[d * cap + i];
+            aa[d] = acc[d * cap + i];
+            bb[d] = FUSE ? nd.rb[d * cap + i] : 0.0;
+        }
+        double x[3], d2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double hk = __dmul_rn(__dmul_rn(0.5, aa[d]), dt);
+            double u = vv[d] + hk;
             if (d == 2 && g_dt != 0.0) u -= g_dt;
             if (scale != 1.0) u *= scale;
-            v[d * cap + i] = u;
             v2 += u * u;
+            double xx = rr[d];
             if (r_row) {
-                r_row[d * row_stride + col] = r[d * cap + i];
+                r_row[d * row_stride + col] = xx;
                 v_row[d * row_stride + col] = u;
             }
+            if (FUSE) {   // the next step: one-shot strict wrap, v += a dt / 2, r += v dt (same arithmetic as k_cut_kick_drift)
+                if (xx < 0.0) xx += nd.L;
+                if (xx > nd.L) xx -= nd.L;
+                u += hk;
+                xx += __dmul_rn(u, dt);
+                r[d * cap + i] = xx;
+                x[d] = xx;
+                const double dd = md_minimg_exact(__dsub_rn(xx, bb[d]), nd.L, nd.halfL);
+                d2 = __dadd_rn(d2, __dmul_rn(dd, dd));
+            }
+            v[d * cap + i] = u;
+        }
+        if (FUSE) {
+            if (d2 > nd.trig2) sc->rebuild_flag = nd.tag;
+            if (nd.fp32) ((uint4 *)nd.pos4)[i] = make_uint4(md_to_fixed(x[0], nd.inv_h), md_to_fixed(x[1], nd.inv_h), md_to_fixed(x[2], nd.inv_h), 0u);
+            else ((double4 *)nd.pos4)[i] = make_double4(x[0], x[1], x[2], 0.0);
         }
     }
     const double b = md_block_sum(v2, red);
@@ -954,7 +1078,12 @@ k_cut_kick_finish(const double *__restrict__ r, double *__restrict__ v, const do
     if (s_last) {
         __threadfence();
         md_finalize_body(fin, sc, red);
-        if (threadIdx.x == 0) sc->finish_blocks_done = 0u;
+        if (threadIdx.x == 0) {
+            sc->finish_blocks_done = 0u;
+            // every block raised its trigger before bumping the counter: the flag of the fused drift is final here, so the
+            // host learns it without a separate k_publish_flag launch
+            if (FUSE && nd.host_flag) *nd.host_flag = *(volatile int *)&sc->rebuild_flag == nd.tag;
+        }
     }
 }
 
@@ -992,7 +1121,7 @@ __global__ void k_unsort(const double *__restrict__ src, const int *__restrict__
 // The host learns the skin trigger through a store into mapped pinned memory instead of a D2H memcpy: a copy would
 // queue on the copy engine behind the bulk row transfers of the previous batch (run_async pipelining) and stall
 // every step for milliseconds.
-__global__ void k_publish_flag(const StepScalars *__restrict__ sc, int *__restrict__ host_flag) { *host_flag = sc->rebuild_flag; }
+__global__ void k_publish_flag(const StepScalars *__restrict__ sc, int *__restrict__ host_flag, int tag) { *host_flag = sc->rebuild_flag == tag; }
 
 // Small device -> host read-backs of the rebuild (counts, class boundaries) are stores into mapped pinned memory for
 // the same reason: dst[i] = src[i * stride].
@@ -1260,7 +1389,7 @@ __device__ __forceinline__ int halo_peer_of(const HaloTab &T, long long k) {
     return q;
 }
 __global__ void k_halo_pack(const double *__restrict__ r, long long cap, const int *__restrict__ idx, HaloTab T,
-                            const StepScalars *__restrict__ sc, double *__restrict__ buf) {
+                            const StepScalars *__restrict__ sc, double *__restrict__ buf, int tag) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = T.ent0[T.world];
     if (k < total) {
@@ -1273,7 +1402,7 @@ __global__ void k_halo_pack(const double *__restrict__ r, long long cap, const i
         m[3 * l + 2] = r[2 * cap + s];
     } else if (k < total + T.world) {
         const int q = (int)(k - total);
-        if (q != T.rank) buf[3 * T.ent0[q + 1] + q] = (double)sc->rebuild_flag;
+        if (q != T.rank) buf[3 * T.ent0[q + 1] + q] = (double)(sc->rebuild_flag == tag);
     }
 }
 // Arrival counters: rank p bumps counter[p] in rank q's buffer to `seq` after its stores of exchange number `seq`.
@@ -1297,7 +1426,7 @@ __device__ __forceinline__ void halo_wait_arrivals(const HaloWait &Wt, int world
 
 __global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restrict__ idx, HaloTab T, long long cap,
                               double *__restrict__ r, int fp32, double inv_h, void *__restrict__ pos4,
-                              StepScalars *__restrict__ sc, HaloWait Wt) {
+                              StepScalars *__restrict__ sc, HaloWait Wt, int tag) {
     halo_wait_arrivals(Wt, T.world, T.rank, sc);
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = T.ent0[T.world];
@@ -1312,7 +1441,7 @@ __global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restr
         else ((double4 *)pos4)[s] = make_double4(x, y, z, 0.0);
     } else if (k < total + T.world) {
         const int q = (int)(k - total);
-        if (q != T.rank && __ldcg(buf + 3 * T.ent0[q + 1] + q) != 0.0) sc->rebuild_flag = 1;
+        if (q != T.rank && __ldcg(buf + 3 * T.ent0[q + 1] + q) != 0.0) sc->rebuild_flag = tag;
     }
 }
 
@@ -1320,7 +1449,8 @@ __global__ void k_halo_unpack(const double *__restrict__ buf, const int *__restr
 // the receive buffers of the ranks that hold them as ghosts -- no staging buffer, no ncclSend/ncclRecv
 struct PeerDst { double *base[MD_MAXW]; };   // rank q's receive buffer (current parity); my segment starts at the offset q published
 __global__ void k_halo_push(const double *__restrict__ r, long long cap, const int *__restrict__ idx, HaloTab T,
-                            StepScalars *__restrict__ sc, PeerDst P, const PeerCtrl *__restrict__ ctrl, unsigned long long rebuild_seq) {
+                            StepScalars *__restrict__ sc, PeerDst P, const PeerCtrl *__restrict__ ctrl, unsigned long long rebuild_seq,
+                            int tag) {
     __shared__ long long s_off[MD_MAXW];
     if ((int)threadIdx.x < T.world && (int)threadIdx.x != T.rank) {   // the receivers' layouts of THIS list generation
         const volatile unsigned long long *f = &ctrl->off_seq_from[threadIdx.x];
@@ -1343,7 +1473,7 @@ __global__ void k_halo_push(const double *__restrict__ r, long long cap, const i
         m[3 * l + 2] = r[2 * cap + s];
     } else if (k < total + T.world) {
         const int q = (int)(k - total);
-        if (q != T.rank) P.base[q][s_off[q] + 3 * (T.ent0[q + 1] - T.ent0[q])] = (double)sc->rebuild_flag;
+        if (q != T.rank) P.base[q][s_off[q] + 3 * (T.ent0[q + 1] - T.ent0[q])] = (double)(sc->rebuild_flag == tag);
     }
 }
 struct PeerCnt { unsigned long long *cnt[MD_MAXW]; };   // counter[this rank] inside peer q's buffer
@@ -1480,7 +1610,8 @@ int md_cells_setup(mdsea_ctx *c) {
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device);
-        s->finish_blocks = 8 * sms;
+        s->finish_blocks = 10 * sms;
+        s->finish_blocks_fused = 6 * sms;
         MD_CUDA(c, cudaMalloc(&s->pe_fold, sizeof(double) * s->finish_blocks));
         MD_CUDA(c, cudaMalloc(&s->ke_glob, sizeof(double)));
     }
@@ -1743,19 +1874,19 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
         wt.counters = (const unsigned long long *)(s->p2p_buf + 2 * s->p2p_stride);
         wt.seq = seq;
         k_halo_push<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, pd,
-                                                          (const PeerCtrl *)((char *)s->p2p_buf + s->ctrl_off), s->asm_seq);
+                                                          (const PeerCtrl *)((char *)s->p2p_buf + s->ctrl_off), s->asm_seq, s->drift_tag);
         k_halo_signal<<<1, 32, 0, st>>>(pc, W, me, seq);
         k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->p2p_buf + par, s->halo_idx, tr, s->cap, c->d_r,
-                                                            c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt);
+                                                            c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt, s->drift_tag);
         c->stats.kernel_launches += 1;
     } else {
         HaloWait wt;
         wt.counters = nullptr;
         wt.seq = 0;
-        k_halo_pack<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, s->halo_send);
+        k_halo_pack<<<g256(ts.ent0[W] + W), 256, 0, st>>>(c->d_r, s->cap, s->halo_idx, ts, c->d_sc, s->halo_send, s->drift_tag);
         MD_TRY(md_comm_exchange(c, sp, sb, rp, rbytes, st));
         k_halo_unpack<<<g256(tr.ent0[W] + W), 256, 0, st>>>(s->halo_recv, s->halo_idx, tr, s->cap, c->d_r,
-                                                            c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt);
+                                                            c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, wt, s->drift_tag);
     }
     c->stats.kernel_launches += 2;
     if (st == c->stream) md_prof_end(c, &c->stats.ms_comm);
@@ -1765,6 +1896,8 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
 
 #include <chrono>
 static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
+static int  g_nbw_variant = getenv("MDSEA_NBW_VARIANT") ? atoi(getenv("MDSEA_NBW_VARIANT")) : 1;   // bit 0: expanded distance test, bit 1: deferred appends
+static bool g_cut_fuse = !(getenv("MDSEA_CUT_FUSE") && !strcmp(getenv("MDSEA_CUT_FUSE"), "0"));   // A/B switch
 static bool g_build_thread = getenv("MDSEA_NBR_BUILD") && !strcmp(getenv("MDSEA_NBR_BUILD"), "thread");  // A/B switch
 struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronises the stream; off by default)
     mdsea_ctx *c;
@@ -1855,16 +1988,25 @@ static int rebuild(mdsea_ctx *c) {
     {
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
-        const float lo = (float)(rl2s * (1.0 - 1e-5)), hi = (float)(rl2s * (1.0 + 1e-5));
+        const float lo = (float)(rl2s * (1.0 - 2e-5)), hi = (float)(rl2s * (1.0 + 2e-5));
         const long long no = c->n > 0 ? c->n : 1;
         if (g_build_thread || s->nc < 4)
             k_nbr_build<<<md_div_up(no, NB_THREADS), NB_THREADS, 0, c->stream>>>(
                 c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
                 s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
-        else
-            k_nbr_build_warp<<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(
-                c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih,
-                s->rl2, (float)rl2s, (float)(rl2s * 1e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc);
+        else {
+#define NBW_LAUNCH(EXP, DEF)                                                                                                        \
+    k_nbr_build_warp<EXP, DEF><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                   \
+        c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
+        rl2s, (float)(rl2s * 2e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc)
+            switch (g_nbw_variant) {   // MDSEA_NBW_VARIANT: A/B switch (profiles/README.md)
+                case 0: NBW_LAUNCH(false, false); break;
+                case 1: NBW_LAUNCH(true, false); break;
+                case 2: NBW_LAUNCH(false, true); break;
+                default: NBW_LAUNCH(true, true); break;
+            }
+#undef NBW_LAUNCH
+        }
     }
     launches += 1;
     pt.lap("nbr build");
@@ -1878,7 +2020,7 @@ static int rebuild(mdsea_ctx *c) {
 }
 
 // force kernel over the owned slots [i0, i1); its per-block PE partials go to pe_part[pe_off ...]
-static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded) {
+static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded /* guard tag, 0 = unguarded */) {
     CellState *s = c->cells;
     if (i1 <= i0) return MDSEA_OK;
     const int grid = force_grid(i0, i1);
@@ -1930,16 +2072,19 @@ int md_cutoff_force(mdsea_ctx *c) { return cutoff_force(c, 0); }
 static int cut_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, bool do_drift) {
     CellState *s = c->cells;
     md_prof_begin(c);
+    if (do_drift) s->drift_tag = s->drift_tag == 0x7fffffff ? 1 : s->drift_tag + 1;
     k_cut_kick_drift<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->rb, c->n, s->cap, do_bc, do_kick, do_drift,
                                                         c->box.L, c->box.halfL, c->p.dt, s->trig2, c->p.precision == MDSEA_FP32,
-                                                        fixed_inv_h(c), s->pos4, c->d_sc);
+                                                        fixed_inv_h(c), s->pos4, c->d_sc, s->drift_tag);
     md_prof_end(c, &c->stats.ms_integrate);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
     return MDSEA_OK;
 }
 
-static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt, int guarded) {
+// guard: tag of the drift this launch depends on (0 = unguarded).  next_tag != 0: the kernel also does wrap + kick +
+// drift of the NEXT step, raising that tag if the skin trigger fires.
+static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt, int guarded, int next_tag) {
     CellState *s = c->cells;
     const int W = c->p.world;
     const size_t row_stride = W == 1 ? (size_t)c->n_global : (size_t)s->cap;
@@ -1948,13 +2093,23 @@ static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k,
     int *idr = (a->record_coords && W > 1) ? c->d_id_rows + (size_t)k * s->cap : nullptr;
     if (W > 1) s->row_n_own[k] = c->n;
     md_prof_begin(c);
-    c->n_ke_part = std::min(g256(c->n), s->finish_blocks);
+    c->n_ke_part = std::min(g256(c->n), next_tag ? s->finish_blocks_fused : s->finish_blocks);
     FinalizeArgs fin = md_finalize_args(c, k, k + 1 < a->nsteps, a->k_boltzmann, c->stats.steps + k);
     fin.pe_part = s->pe_fold;   // the force kernel's partials, folded per finish block
     fin.n_pe = c->n_ke_part;
-    k_cut_kick_finish<<<c->n_ke_part, 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride, idr,
-                                                           c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded, fin, c->d_pe_part,
-                                                           c->n_pe_part, s->pe_fold);
+    NextDrift nd;
+    nd.rb = s->rb; nd.L = c->box.L; nd.halfL = c->box.halfL; nd.trig2 = s->trig2; nd.inv_h = fixed_inv_h(c);
+    nd.pos4 = s->pos4; nd.fp32 = c->p.precision == MDSEA_FP32; nd.tag = next_tag;
+    // two mapped words alternate (tag parity): the host may still be reading the previous drift's word
+    nd.host_flag = (W == 1 && next_tag) ? s->d_flag_mapped + 2 + (next_tag & 1) : nullptr;
+    if (nd.host_flag) s->published_tag = next_tag;
+#define CUT_FINISH(FUSE)                                                                                                            \
+    k_cut_kick_finish<FUSE><<<c->n_ke_part, 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->id, c->n, s->cap, (long long)row_stride, idr, \
+                                                                 c->p.dt, g_dt, c->d_sc, c->d_ke_part, rr, vr, guarded, fin, c->d_pe_part,   \
+                                                                 c->n_pe_part, s->pe_fold, nd)
+    if (next_tag) CUT_FINISH(true);
+    else CUT_FINISH(false);
+#undef CUT_FINISH
     md_prof_end(c, &c->stats.ms_integrate);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;
@@ -1966,48 +2121,55 @@ static int cut_finish_and_finalize(mdsea_ctx *c, const mdsea_run_args *a, int k,
 // return at once when it is set); the host then reads the flag and, only if it fired (every ~6 steps at 1e6
 // particles), rebuilds and launches the three kernels again.  Multi-rank: the per-step halo messages carry every
 // rank's flag, so after the (unconditional) ghost refresh all ranks hold the same MAX and rebuild together.
-static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt) {
+// fuse_next: the finish kernel also starts the next step (wrap + kick + drift); on return s->drift_tag is that drift's tag.
+static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, double g_dt, bool fuse_next) {
     CellState *s = c->cells;
     const int W = c->p.world;
+    const int tag = s->drift_tag;                                     // the drift this step's force evaluation follows
+    const int next_tag = fuse_next ? (tag == 0x7fffffff ? 1 : tag + 1) : 0;
     if (s->need_rebuild) {  // no list yet (first evaluation / new state): nothing to speculate on
         MD_TRY(cutoff_force(c, 0));
-        return cut_finish_and_finalize(c, a, k, g_dt, 0);
+        MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 0, next_tag));
+        if (fuse_next) s->drift_tag = next_tag;
+        return MDSEA_OK;
     }
     const long long fe0 = c->stats.force_evals;
+    const int flag_slot = (W == 1 && s->published_tag == tag) ? 2 + (tag & 1) : 0;
     if (W == 1) {
-        k_publish_flag<<<1, 1, 0, c->stream>>>(c->d_sc, s->d_flag_mapped);
+        if (!flag_slot) k_publish_flag<<<1, 1, 0, c->stream>>>(c->d_sc, s->d_flag_mapped, tag);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
-        MD_TRY(cutoff_force(c, 1));
+        MD_TRY(cutoff_force(c, tag));
     } else if (c->profiling) {  // per-family timers need everything on one stream: no overlap
         MD_TRY(halo_exchange(c, c->stream));
-        k_publish_flag<<<1, 1, 0, c->stream>>>(c->d_sc, s->d_flag_mapped);
+        k_publish_flag<<<1, 1, 0, c->stream>>>(c->d_sc, s->d_flag_mapped, tag);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->stream));
-        MD_TRY(cutoff_force(c, 1));
+        MD_TRY(cutoff_force(c, tag));
     } else {
         // comm stream: ghost refresh (+ flags) while the main stream computes the INTERIOR forces, which need no ghosts
         MD_CUDA(c, cudaEventRecord(s->ev_drift, c->stream));
         MD_CUDA(c, cudaStreamWaitEvent(c->comm_stream, s->ev_drift, 0));
         MD_TRY(halo_exchange(c, c->comm_stream));
-        k_publish_flag<<<1, 1, 0, c->comm_stream>>>(c->d_sc, s->d_flag_mapped);
+        k_publish_flag<<<1, 1, 0, c->comm_stream>>>(c->d_sc, s->d_flag_mapped, tag);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
         const int gi = force_grid(0, s->n_int > 0 ? s->n_int : 1);
         c->n_pe_part = gi + force_grid(s->n_int, c->n > s->n_int ? c->n : s->n_int + 1);
         MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
-        MD_TRY(launch_force(c, 0, s->n_int, 0, 1));                       // guarded by the LOCAL flag only (the global one
+        MD_TRY(launch_force(c, 0, s->n_int, 0, tag));                     // guarded by the LOCAL flag only (the global one
                                                                           // is not known yet): redone if any rank fired
         MD_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_flag, 0));
-        MD_TRY(launch_force(c, s->n_int, c->n, gi, 1));                   // boundary particles: ghosts are fresh now
+        MD_TRY(launch_force(c, s->n_int, c->n, gi, tag));                 // boundary particles: ghosts are fresh now
         c->stats.force_evals += 1;
     }
-    MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 1));
+    MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, tag, next_tag));
     MD_CUDA(c, cudaEventSynchronize(s->ev_flag));
-    if (s->h_flag[0]) {  // the guarded kernels did nothing; rebuild (clears the flag) and do the step for real
+    if (((volatile int *)s->h_flag)[flag_slot]) {  // the guarded kernels did nothing; rebuild (clears the flag) and do the step for real
         c->stats.force_evals = fe0;
         s->need_rebuild = true;
         MD_CUDA(c, cudaMemsetAsync(&c->d_sc->pairs_pending, 0, sizeof(unsigned long long), c->stream));
         MD_TRY(cutoff_force(c, 0));
-        MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 0));
+        MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, 0, next_tag));
     }
+    if (fuse_next) s->drift_tag = next_tag;
     return MDSEA_OK;
 }
 
@@ -2020,10 +2182,14 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
     // one double per step and redoes the temperature / scale bookkeeping from it; every batch leaves the global
     // mean_ke of its last step in the scalars for the first step of the next batch.
     const bool mr_quench = W > 1 && a->quench_targets;
+    // reuse mode: the finish kernel of step k also does wrap + kick + drift of step k + 1 (never across a batch
+    // boundary: the caller may read or replace the state between batches).  MDSEA_CUT_FUSE=0 keeps the separate kernels.
+    const bool fuse = reuse && g_cut_fuse;
+    bool drifted = false;   // the previous finish kernel already started this step
     for (int k = 0; k < a->nsteps; ++k) {
         if (verlet) {
             if (reuse && c->acc_valid) {
-                MD_TRY(cut_kick_drift(c, true, true, true));
+                if (!drifted) MD_TRY(cut_kick_drift(c, true, true, true));
             } else {
                 MD_TRY(cut_kick_drift(c, true, false, false));   // apply_bc
                 MD_TRY(md_cutoff_force(c));                       // simulator.py:540
@@ -2033,7 +2199,8 @@ int md_cutoff_steps(mdsea_ctx *c, const mdsea_run_args *a, double g_dt) {
         } else {
             MD_TRY(cut_kick_drift(c, true, false, true));        // simulator.py:533
         }
-        MD_TRY(force_after_drift(c, a, k, g_dt));                 // simulator.py:544 + kick + energies + row
+        drifted = fuse && k + 1 < a->nsteps;
+        MD_TRY(force_after_drift(c, a, k, g_dt, drifted));        // simulator.py:544 + kick + energies + row (+ next drift)
         c->acc_valid = true;
         if (mr_quench || (W > 1 && k == a->nsteps - 1)) {
             CellState *s = c->cells;

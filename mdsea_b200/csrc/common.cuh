@@ -67,7 +67,8 @@ struct StepScalars {
     unsigned long long pairs_pending;  // contributions of the current step's force launches; committed by the step's finalize (finalize.cuh)
                                        // (a speculative launch that is redone after a rebuild must not count twice)
     unsigned long long steps_done;
-    int    rebuild_flag;             // cutoff path: max displacement exceeded skin/2
+    int    rebuild_flag;             // cutoff path: TAG of the drift after which the max displacement exceeded skin/2 (0: none;
+                                     // every drift gets its own tag, cells.cu CellState::drift_tag)
     int    overflow_flag;            // capacity overflow reported by a kernel
     unsigned finish_blocks_done;     // cut-off path: blocks of k_cut_kick_finish that have published their KE partial
 };
