@@ -29,36 +29,57 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, L, r, v, dt = _liquid(16)
     steps = 40
-    ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1, precision=0,
-                        epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=RC, skin=SKIN, force_evals_per_step=2,
-                        ring_rows=steps, device=local, rank=rank, world=world, proc_grid=GRIDS[world])
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid, src=0)
-    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
-    ctx.set_temperature(1.0)
-    ctx.set_state(r, v)
-    rows = ctx.run(steps, kb=1.0)
-    # gather the compact rows on rank 0 through torch.distributed (plumbing)
-    rr = np.zeros((steps, 3, n)); owners = np.zeros((steps, n))
-    for k in range(steps):
-        m = int(rows["n_owned"][k]); ids = rows["ids"][k, :m]
-        rr[k][:, ids] = rows["r"][k, :, :m]; owners[k, ids] = 1
-    t = torch.from_numpy(rr).cuda(); o = torch.from_numpy(owners).cuda()
-    dist.all_reduce(t); dist.all_reduce(o)
-    st = ctx.stats()
-    if rank == 0:
-        s = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
-        ref = s.run(steps, record=True)
-        np.testing.assert_allclose(rows["pe"], ref["pe"], rtol=1e-10)
-        np.testing.assert_allclose(rows["ke"], ref["ke"], rtol=1e-10)
-        assert bool((o == 1).all()), "every particle must be owned by exactly one rank"
-        assert np.abs(t.cpu().numpy() - ref["r"]).max() <= 1e-9 * L
-        assert st["list_rebuilds"] == s.counters()["rebuilds"]
-        print(f"NCCL domain decomposition check OK: world={world} rebuilds={st['list_rebuilds']} n_local={st['n_local']} "
-              f"n_ghost={st['n_ghost']}")
-    ctx.close()
+    # evals = 2: the reference's two force evaluations per step; evals = 1: a(t+dt) reused, the finish kernel also starts
+    # the next step (fused drift, tagged skin trigger riding on the halo messages); the last case adds a quench schedule
+    # (one all-reduced mean_ke per step) and gravity, checked against the NumPy oracle with a cutoff
+    for evals, quench in ((2, False), (1, False), (1, True)):
+        ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1, precision=0,
+                            epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=RC, skin=SKIN,
+                            force_evals_per_step=evals, ring_rows=steps // 2, device=local, rank=rank, world=world,
+                            proc_grid=GRIDS[world])
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")   # one NCCL communicator per context
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        ctx.set_temperature(1.0)
+        ctx.set_state(r, v)
+        q = None
+        if quench:
+            q = np.full((steps, 2), np.nan)
+            q[7, 1], q[20, 1], q[33, 1] = 0.6, 0.3, 0.9     # step 20 = first step of the second batch
+        rr = np.zeros((steps, 3, n)); owners = np.zeros((steps, n))
+        pe, ke, temp = [], [], []
+        half = steps // 2
+        for b in range(2):   # two batches: the fused drift never crosses a batch boundary
+            rows = ctx.run(half, kb=1.0, g=9.80665 if quench else 0.0, quench=None if q is None else q[b * half:(b + 1) * half])
+            pe.append(rows["pe"].copy()); ke.append(rows["ke"].copy()); temp.append(rows["temp"].copy())
+            for k in range(half):
+                m = int(rows["n_owned"][k]); ids = rows["ids"][k, :m]
+                rr[b * half + k][:, ids] = rows["r"][k, :, :m]; owners[b * half + k, ids] = 1
+        pe, ke, temp = np.concatenate(pe), np.concatenate(ke), np.concatenate(temp)
+        # gather the compact rows on rank 0 through torch.distributed (plumbing)
+        t = torch.from_numpy(rr).cuda(); o = torch.from_numpy(owners).cuda()
+        dist.all_reduce(t); dist.all_reduce(o)
+        st = ctx.stats()
+        if rank == 0:
+            if quench:
+                from oracle.oracle_np import MiePotential, OracleSolver
+
+                ref = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(), r_cutoff=RC, temp=1.0, kb=1.0, gravity=True,
+                                   quench_steps=[7, 20, 33], quench_temps=[0.6, 0.3, 0.9]).run(steps)
+                np.testing.assert_allclose(temp, ref["temp"], rtol=1e-10)
+            else:
+                s = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+                ref = s.run(steps, record=True)
+                assert st["list_rebuilds"] == s.counters()["rebuilds"]
+            np.testing.assert_allclose(pe, ref["pe"], rtol=1e-10)
+            np.testing.assert_allclose(ke, ref["ke"], rtol=1e-10)
+            assert bool((o == 1).all()), "every particle must be owned by exactly one rank"
+            assert np.abs(t.cpu().numpy() - ref["r"]).max() <= 1e-9 * L
+            print(f"NCCL domain decomposition check OK: world={world} evals={evals} quench={quench} rebuilds={st['list_rebuilds']} "
+                  f"n_local={st['n_local']} n_ghost={st['n_ghost']}", flush=True)
+        ctx.close()
     dist.destroy_process_group()
 
 
