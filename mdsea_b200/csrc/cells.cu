@@ -601,37 +601,11 @@ __device__ __forceinline__ float4 nbw_dummy() {   // a candidate infinitely far 
     return EXPANDED ? make_float4(0.0f, 0.0f, 0.0f, 1.0e30f) : make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
 }
 
-// Appends are DEFERRED: every tested chunk leaves its 32-bit hit mask per lane (and its first slot per lane group) in
-// shared memory, and the row is written in one pass per NBW_MAXCH chunks.  Appending chunk by chunk made the warp
-// wait for the lane with the most hits in EVERY chunk (7.7 iterations for 3.2 hits on average, 20 % of the kernel's
-// instructions in r01); over a whole tile the lanes' totals are nearly equal (~56 each).
-#define NBW_MAXCH 8
-__device__ __forceinline__ void nbw_flush(const unsigned *__restrict__ mask_w, const int *__restrict__ base_w, int n_ch, int lane,
-                                          int grp, int *__restrict__ row0, int max_nbr, int &cnt) {
-    __syncwarp();
-    const unsigned long long row_addr = (unsigned long long)row0;
-    int      k = 0, base = 0;
-    unsigned m = 0u;
-    for (;;) {
-        // next non-empty mask of this lane (the inner loop reconverges at once; a `continue` on an empty mask instead made
-        // the lane wait at the convergence barrier until every other lane of the warp had met an empty mask too)
-        while (m == 0u && k < n_ch) {
-            m = mask_w[k * 32 + lane];
-            base = base_w[k * NBW_G + grp];
-            ++k;
-        }
-        if (m == 0u) break;
-        const int t1 = __ffs(m) - 1;
-        m &= m - 1;
-        // a full row keeps counting (the overflow is reported by the caller); every entry below nbr_cnt is a valid slot
-        // entry k of the tile-sliced row (md_nbr_off): one IMAD.WIDE + STG
-        asm volatile("st.global.b32 [%0], %1;" ::"l"(row_addr + (unsigned long long)(unsigned)min(cnt, max_nbr - 1) * 128ull), "r"(base + t1) : "memory");
-        ++cnt;
-    }
-    __syncwarp();
-}
-
-// immediate append of one chunk's hits (the r01 scheme; A/B baseline of the deferred flush)
+// append one chunk's hits.  (Two alternatives were measured in r01 and dropped, profiles/README.md section 4: 8 lanes per
+// particle testing 8 candidates at a time with ballot / popc compaction -- no staging, no divergence, but its 4-byte
+// stores hit 8 different list rows per particle and instruction, 1670 us against 750 us; and deferring the appends through shared-memory hit masks, so that a warp does not wait for
+// its busiest lane in every chunk, 13 % slower: the kernel's shared-memory pipe is already the bottleneck of the test
+// loop -- every group-broadcast LDS.128 costs 4 wavefronts.)
 __device__ __forceinline__ void nbw_append_now(unsigned m, int base, int *&wp, int max_nbr, int &cnt) {
     while (m) {
         const int t1 = __ffs(m) - 1;
@@ -644,7 +618,7 @@ __device__ __forceinline__ void nbw_append_now(unsigned m, int base, int *&wp, i
     }
 }
 
-template <bool EXPANDED, bool DEFER>
+template <bool EXPANDED>
 __global__ void __launch_bounds__(NBW_WARPS * 32, 9)
 k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
@@ -652,8 +626,6 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                  float rl2s_hi, int max_nbr, int run_max, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
                  StepScalars *__restrict__ sc) {
     __shared__ float4 s_cand[NBW_WARPS][NBW_G][32];
-    __shared__ unsigned s_mask[NBW_WARPS][DEFER ? NBW_MAXCH * 32 : 1];
-    __shared__ int      s_base[NBW_WARPS][DEFER ? NBW_MAXCH * NBW_G : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
     if (i0 >= n_own) return;   // whole warp out of range (only __syncwarp below)
@@ -667,8 +639,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
     const int grp = lane / (32 / NBW_G);            // lane group: each group walks its own candidate stream
     float4 *cand_g = s_cand[w][grp];
     int *row0 = nbr + md_nbr_row_base(il, max_nbr);
-    int *wp = row0;   // write cursor inside the row (immediate appends)
-    int n_ch = 0;     // chunks buffered in s_mask / s_base (warp-uniform; deferred appends)
+    int *wp = row0;   // write cursor inside the row
     const float neg_bw = -bw;
     float bandmin = 3.0e38f;
     int cnt = 0;
@@ -753,16 +724,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        if (DEFER) {
-                            s_mask[w][n_ch * 32 + lane] = m;
-                            if ((lane & (32 / NBW_G - 1)) == 0) s_base[w][n_ch * NBW_G + grp] = base;
-                            if (++n_ch == NBW_MAXCH) {
-                                nbw_flush(s_mask[w], s_base[w], n_ch, lane, grp, row0, max_nbr, cnt);
-                                n_ch = 0;
-                            }
-                        } else {
-                            nbw_append_now(m, base, wp, max_nbr, cnt);
-                        }
+                        nbw_append_now(m, base, wp, max_nbr, cnt);
                     }
                     continue;
                 }
@@ -789,23 +751,13 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        if (DEFER) {
-                            s_mask[w][n_ch * 32 + lane] = m;
-                            if (lane < NBW_G) s_base[w][n_ch * NBW_G + lane] = base;
-                            if (++n_ch == NBW_MAXCH) {
-                                nbw_flush(s_mask[w], s_base[w], n_ch, lane, grp, row0, max_nbr, cnt);
-                                n_ch = 0;
-                            }
-                        } else {
-                            nbw_append_now(m, base, wp, max_nbr, cnt);
-                        }
+                        nbw_append_now(m, base, wp, max_nbr, cnt);
                     }
                     rs = s1; re = e1;
                 }
             }
         }
     }
-    if (DEFER && n_ch) nbw_flush(s_mask[w], s_base[w], n_ch, lane, grp, row0, max_nbr, cnt);
     if (valid) {
         if (__builtin_expect(bandmin <= bw, 0)) {   // a candidate sat in the guard band: canonical float64 redo of this particle
             bool band = false;
@@ -1896,7 +1848,7 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
 
 #include <chrono>
 static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
-static int  g_nbw_variant = getenv("MDSEA_NBW_VARIANT") ? atoi(getenv("MDSEA_NBW_VARIANT")) : 1;   // bit 0: expanded distance test, bit 1: deferred appends
+static int  g_nbw_variant = getenv("MDSEA_NBW_VARIANT") ? atoi(getenv("MDSEA_NBW_VARIANT")) : 1;   // bit 0: expanded distance test
 static bool g_cut_fuse = !(getenv("MDSEA_CUT_FUSE") && !strcmp(getenv("MDSEA_CUT_FUSE"), "0"));   // A/B switch
 static bool g_build_thread = getenv("MDSEA_NBR_BUILD") && !strcmp(getenv("MDSEA_NBR_BUILD"), "thread");  // A/B switch
 struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronises the stream; off by default)
@@ -1995,16 +1947,12 @@ static int rebuild(mdsea_ctx *c) {
                 c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
                 s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
         else {
-#define NBW_LAUNCH(EXP, DEF)                                                                                                        \
-    k_nbr_build_warp<EXP, DEF><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                   \
+#define NBW_LAUNCH(EXP)                                                                                                             \
+    k_nbr_build_warp<EXP><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                        \
         c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
         rl2s, (float)(rl2s * 2e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc)
-            switch (g_nbw_variant) {   // MDSEA_NBW_VARIANT: A/B switch (profiles/README.md)
-                case 0: NBW_LAUNCH(false, false); break;
-                case 1: NBW_LAUNCH(true, false); break;
-                case 2: NBW_LAUNCH(false, true); break;
-                default: NBW_LAUNCH(true, true); break;
-            }
+            if (g_nbw_variant & 1) NBW_LAUNCH(true);   // MDSEA_NBW_VARIANT=0: direct distance test (A/B)
+            else NBW_LAUNCH(false);
 #undef NBW_LAUNCH
         }
     }

@@ -1,5 +1,2 @@
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_nccl_check.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -8
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu_fused.json 2> gpurun_out/bench_2gpu_fused.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_2gpu_fused.json').read().strip().splitlines()[-1]); print('2GPU', d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['config']['list_rebuilds_in_timed_region'])"
-MDSEA_CUT_FUSE=0 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu_nofuse.json 2> gpurun_out/bench_2gpu_nofuse.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_2gpu_nofuse.json').read().strip().splitlines()[-1]); print('2GPU nofuse', d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['config']['list_rebuilds_in_timed_region'])"
+MDSEA_NBR_BUILD=seg timeout 400 python -m pytest tests/test_gpu_cutoff.py -m gpu -x -q 2>&1 | tail -3
+for B in warp seg warp seg; do MDSEA_NBR_BUILD=$B python profiles/ab_cutoff.py fp32 40 c3 200 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$B', d['rebuild_us'], d['force_us'], d['integrate_us_per_step'], d['rebuilds'], d['pe_last'])"; done 2>&1 | tee gpurun_out/ab_seg.log
