@@ -553,7 +553,9 @@ k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long
 // ---- warp-cooperative build ------------------------------------------------------------------------
 #define NBW_WARPS 4      // warps (= tiles of 32 slots) per block
 #define NBW_RUN   6      // at most this many x-consecutive cells of i-particles per pass (bounds the float error)
-#define NBW_G     4      // lane groups per warp with their own candidate streams (8 consecutive particles each)
+// NBW_G (template parameter): lane groups per warp with their own candidate streams (32 / NBW_G consecutive particles
+// each).  More groups = shorter streams (fewer tests) but more staging and more shared-memory wavefronts per broadcast
+// LDS.128 (4 groups: 4 wavefronts, one address per warp: 2).  MDSEA_NBW_GROUPS selects 4 / 2 / 1 for A/B.
 // Offsets from the common origin are plain floats (no wrap), so they only reproduce the minimum image while the
 // candidate window stays inside half a period: (run + 2) cells < nc in x, 3 cells < nc in y and z.  The host
 // therefore passes run_max = min(NBW_RUN, nc - 3) and uses the thread-per-particle kernel when nc == 3.
@@ -603,22 +605,22 @@ __device__ __forceinline__ float4 nbw_dummy() {   // a candidate infinitely far 
 
 // append one chunk's hits.  (Two alternatives were measured in r01 and dropped, profiles/README.md section 4: 8 lanes per
 // particle testing 8 candidates at a time with ballot / popc compaction -- no staging, no divergence, but its 4-byte
-// stores hit 8 different list rows per particle and instruction, 1670 us against 750 us; and deferring the appends through shared-memory hit masks, so that a warp does not wait for
-// its busiest lane in every chunk, 13 % slower: the kernel's shared-memory pipe is already the bottleneck of the test
-// loop -- every group-broadcast LDS.128 costs 4 wavefronts.)
-__device__ __forceinline__ void nbw_append_now(unsigned m, int base, int *&wp, int max_nbr, int &cnt) {
+// stores hit 8 different list rows per particle and instruction, 1670 us against 750 us; and deferring the appends
+// through shared-memory hit masks, so that a warp does not wait for its busiest lane in every chunk, 13 % slower: the
+// kernel's shared-memory pipe is already the bottleneck of the test loop -- every group-broadcast LDS.128 costs 4
+// wavefronts.)
+__device__ __forceinline__ void nbw_append_now(unsigned m, int base, unsigned long long row_addr, int k_max, int &cnt) {
     while (m) {
         const int t1 = __ffs(m) - 1;
         m &= m - 1;
-        if (cnt < max_nbr) {   // a full row keeps counting (the overflow is reported by the caller); every entry
-            *wp = base + t1;   // below nbr_cnt is always a valid slot
-            wp += 32;          // next entry of the tile-sliced row (md_nbr_off)
-        }
+        // entry cnt of the tile-sliced row (md_nbr_off): 32-bit index, one IMAD.WIDE + STG.  A full row keeps counting (the
+        // overflow is reported by the caller) and overwrites its last slot, so every entry below nbr_cnt is a valid slot.
+        asm volatile("st.global.b32 [%0], %1;" ::"l"(row_addr + (unsigned long long)(unsigned)min(cnt, k_max) * 128ull), "r"(base + t1) : "memory");
         ++cnt;
     }
 }
 
-template <bool EXPANDED>
+template <bool EXPANDED, int NBW_G>
 __global__ void __launch_bounds__(NBW_WARPS * 32, 9)
 k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
@@ -639,7 +641,8 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
     const int grp = lane / (32 / NBW_G);            // lane group: each group walks its own candidate stream
     float4 *cand_g = s_cand[w][grp];
     int *row0 = nbr + md_nbr_row_base(il, max_nbr);
-    int *wp = row0;   // write cursor inside the row
+    const unsigned long long row_addr = (unsigned long long)row0;
+    const int k_max = max_nbr - 1;
     const float neg_bw = -bw;
     float bandmin = 3.0e38f;
     int cnt = 0;
@@ -724,7 +727,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        nbw_append_now(m, base, wp, max_nbr, cnt);
+                        nbw_append_now(m, base, row_addr, k_max, cnt);
                     }
                     continue;
                 }
@@ -751,7 +754,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
                         else m = 0u;
                         const long long self = i - base;
                         if (self >= 0 && self < 32) m &= ~(1u << self);
-                        nbw_append_now(m, base, wp, max_nbr, cnt);
+                        nbw_append_now(m, base, row_addr, k_max, cnt);
                     }
                     rs = s1; re = e1;
                 }
@@ -1848,6 +1851,7 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
 
 #include <chrono>
 static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
+static int  g_nbw_groups = getenv("MDSEA_NBW_GROUPS") ? atoi(getenv("MDSEA_NBW_GROUPS")) : 2;   // r01: 4: 848 us, 2: 832 us, 1: 851 us per rebuild
 static int  g_nbw_variant = getenv("MDSEA_NBW_VARIANT") ? atoi(getenv("MDSEA_NBW_VARIANT")) : 1;   // bit 0: expanded distance test
 static bool g_cut_fuse = !(getenv("MDSEA_CUT_FUSE") && !strcmp(getenv("MDSEA_CUT_FUSE"), "0"));   // A/B switch
 static bool g_build_thread = getenv("MDSEA_NBR_BUILD") && !strcmp(getenv("MDSEA_NBR_BUILD"), "thread");  // A/B switch
@@ -1947,12 +1951,14 @@ static int rebuild(mdsea_ctx *c) {
                 c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
                 s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
         else {
-#define NBW_LAUNCH(EXP)                                                                                                             \
-    k_nbr_build_warp<EXP><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                        \
+#define NBW_LAUNCH(EXP, G)                                                                                                          \
+    k_nbr_build_warp<EXP, G><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                     \
         c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
         rl2s, (float)(rl2s * 2e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc)
-            if (g_nbw_variant & 1) NBW_LAUNCH(true);   // MDSEA_NBW_VARIANT=0: direct distance test (A/B)
-            else NBW_LAUNCH(false);
+            if (!(g_nbw_variant & 1)) NBW_LAUNCH(false, 4);   // MDSEA_NBW_VARIANT=0: direct distance test (A/B)
+            else if (g_nbw_groups == 1) NBW_LAUNCH(true, 1);
+            else if (g_nbw_groups == 2) NBW_LAUNCH(true, 2);
+            else NBW_LAUNCH(true, 4);
 #undef NBW_LAUNCH
         }
     }
