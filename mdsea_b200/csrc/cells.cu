@@ -918,20 +918,29 @@ k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *_
                  StepScalars *__restrict__ sc, int tag) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // all loads first (the stores below go through the same base pointers; see k_cut_kick_finish)
+    double rr[3], vv[3], aa[3], bb[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        rr[d] = r[d * cap + i];
+        vv[d] = v[d * cap + i];
+        aa[d] = do_kick ? acc[d * cap + i] : 0.0;
+        bb[d] = rb[d * cap + i];
+    }
     double x[3], d2 = 0.0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        double xx = r[d * cap + i], u = v[d * cap + i];
+        double xx = rr[d], u = vv[d];
         if (do_bc) {  // one-shot strict wrap, simulator.py:165-166
             if (xx < 0.0) xx += L;
             if (xx > L) xx -= L;
         }
-        if (do_kick) u += __dmul_rn(__dmul_rn(0.5, acc[d * cap + i]), dt);
+        if (do_kick) u += __dmul_rn(__dmul_rn(0.5, aa[d]), dt);
         if (do_drift) xx += __dmul_rn(u, dt);
         r[d * cap + i] = xx;
         if (do_kick) v[d * cap + i] = u;
         x[d] = xx;
-        const double dd = md_minimg_exact(__dsub_rn(xx, rb[d * cap + i]), L, halfL);
+        const double dd = md_minimg_exact(__dsub_rn(xx, bb[d]), L, halfL);
         d2 = __dadd_rn(d2, __dmul_rn(dd, dd));
     }
     if (do_drift && d2 > trig2) sc->rebuild_flag = tag;   // the skin trigger of THIS drift (tags: see StepScalars)

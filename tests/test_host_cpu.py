@@ -184,3 +184,26 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
                 assert "/root/reference" not in src, fn
+
+
+def test_bench_reads_dram_traffic_from_the_tracked_ncu_summaries(tmp_path, monkeypatch):
+    """bench.py fills roofline.traffic from profiles/*.txt (written by profiles/summarize.py): read + write bytes of the
+    FIRST block of the named kernel, None when the summary or the kernel is missing."""
+    import bench
+
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "s.txt").write_text(
+        "# ncu --set full\n\n== void k_other<1>(int)\ndram__bytes_read.sum   1.0 Gbyte\ndram__bytes_write.sum  1.0 Gbyte\n"
+        "\n== void k_nbr_force_f32<1, 1>(const uint4 *)\ngpu__time_duration.sum  114.7 us\n"
+        "dram__bytes_read.sum                     244.5 Mbyte\ndram__bytes_write.sum                     18.5 Mbyte\n"
+        "\n== void k_nbr_force_f32<1, 1>(const uint4 *)\ndram__bytes_read.sum   9 Gbyte\ndram__bytes_write.sum  9 Gbyte\n")
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.ncu_traffic("s.txt", "k_nbr_force_f32") == pytest.approx(263.0e6)
+    assert bench.ncu_traffic("s.txt", "k_missing") is None
+    assert bench.ncu_traffic("missing.txt", "k_nbr_force_f32") is None
+    # the tracked r01 summaries carry the kernels bench.py asks for
+    monkeypatch.undo()
+    assert bench.ncu_traffic("r01_ncu_c3_kernels.txt", "k_nbr_force_f32") > 1e8
+    assert bench.ncu_traffic("r01_ncu_c3_force_f64.txt", "k_nbr_force_f64") > 1e8
+    assert bench.ncu_traffic("r01_ncu_c2_allpairs_f64.txt", "k_allpairs") is not None
