@@ -138,6 +138,19 @@ const char *mdsea_b200_last_error(const mdsea_ctx *ctx); /* ctx may be NULL: las
 /* r_vec / v_vec upload (simulator.py:54-59): (ndim, N) float64 host arrays, GLOBAL particle order.
  * With world > 1 every rank passes the full arrays and keeps the particles it owns. */
 int mdsea_b200_set_state(mdsea_ctx *ctx, const double *r_soa, const double *v_soa);
+/* Initial conditions generated on the device instead of uploaded (opt-in; replaces PosGen.simplecubic + VelGen.mb,
+ * mdsea/gen.py:98-123,144-156 as called by simulator.py:54-59).  The lattice is the reference's bit for bit; the
+ * velocities are Maxwell-Boltzmann by inverse-CDF sampling of `speed_cdf` (the reference's table mb_cdf on the grid
+ * arange(0, 50, speed_step), gen.py:27-37; NULL = all zero, the temp == 0 case) with the reference's direction
+ * factors (3-D: vy, vz scaled by the product of sin(theta_0) over all particles, gen.py:83-92) or, with
+ * isotropic != 0, uniformly distributed directions.  A counter-based generator keyed by (seed, particle id) replaces
+ * the global NumPy stream, so the velocities are NOT the reference's for the same seed.  *mean_speed (may be NULL)
+ * receives mean_i |v_i| over all particles, the input of get_dt (helpers.py:89-100).  With world > 1 every rank
+ * generates its slice and the first rebuild routes it, like set_state. */
+int mdsea_b200_generate_state(mdsea_ctx *ctx, const double *speed_cdf, int64_t n_cdf, double speed_step, uint64_t seed,
+                              int32_t isotropic, double *mean_speed);
+/* time step of the following run calls (simulator.py:86-87 derives it from the initial velocities) */
+int mdsea_b200_set_dt(mdsea_ctx *ctx, double dt);
 /* download of r_vec, v_vec, acc in original particle order; any pointer may be NULL.
  * With world > 1 each rank fills only the entries of particles it owns (others untouched)
  * and returns their ids in `owned_ids` (capacity N, may be NULL) / count in *n_owned. */

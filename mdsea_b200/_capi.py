@@ -60,7 +60,7 @@ EXPORTS = [
     "mdsea_b200_update_dists", "mdsea_b200_get_cells", "mdsea_b200_get_neighbors", "mdsea_b200_set_temperature",
     "mdsea_b200_get_stats", "mdsea_b200_first_nonfinite_step", "mdsea_b200_set_profiling", "mdsea_b200_stream",
     "mdsea_b200_nccl_unique_id", "mdsea_b200_comm_init", "mdsea_b200_comm_init_local", "mdsea_b200_rank_capacity",
-    "mdsea_b200_measure_fma_peak", "mdsea_b200_analyse_speeds",
+    "mdsea_b200_measure_fma_peak", "mdsea_b200_analyse_speeds", "mdsea_b200_generate_state", "mdsea_b200_set_dt",
 ]
 
 _lib = None
@@ -94,6 +94,8 @@ def load():
     lib.mdsea_b200_update_dists.argtypes = [vp, vp, vp]
     lib.mdsea_b200_get_cells.argtypes = [vp, vp, vp, C.POINTER(i32 * 3)]
     lib.mdsea_b200_get_neighbors.argtypes = [vp, i64p, vp, vp]
+    lib.mdsea_b200_generate_state.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_uint64, i32, dp]
+    lib.mdsea_b200_set_dt.argtypes = [vp, C.c_double]
     lib.mdsea_b200_set_temperature.argtypes = [vp, C.c_double, i32]
     lib.mdsea_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mdsea_b200_first_nonfinite_step.argtypes = [vp, i64p]
@@ -182,6 +184,20 @@ class Context:
         v = np.ascontiguousarray(v, dtype=np.float64)
         assert r.shape == (self.ndim, self.n) and v.shape == r.shape
         self._ck(self.lib.mdsea_b200_set_state(self.h, _ptr(r), _ptr(v)))
+
+    def generate_state(self, speed_cdf, speed_step, seed=0, isotropic=False) -> float:
+        """Lattice + Maxwell-Boltzmann state generated on the device; returns the mean speed (input of get_dt)."""
+        ms = C.c_double(0.0)
+        if speed_cdf is None:
+            self._ck(self.lib.mdsea_b200_generate_state(self.h, None, 0, 0.0, C.c_uint64(int(seed)), int(bool(isotropic)), C.byref(ms)))
+        else:
+            cdf = np.ascontiguousarray(speed_cdf, dtype=np.float64)
+            self._ck(self.lib.mdsea_b200_generate_state(self.h, _ptr(cdf), cdf.shape[0], float(speed_step), C.c_uint64(int(seed)),
+                                                        int(bool(isotropic)), C.byref(ms)))
+        return float(ms.value)
+
+    def set_dt(self, dt):
+        self._ck(self.lib.mdsea_b200_set_dt(self.h, float(dt)))
 
     def set_temperature(self, temp, reset_ke=True):
         self._ck(self.lib.mdsea_b200_set_temperature(self.h, float(temp), 1 if reset_ke else 0))

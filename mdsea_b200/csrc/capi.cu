@@ -269,6 +269,27 @@ extern "C" int mdsea_b200_set_state(mdsea_ctx *c, const double *r, const double 
     return MDSEA_OK;
 }
 
+int md_generate_state(mdsea_ctx *c, const double *cdf, long long ncdf, double ds, unsigned long long seed, int isotropic,
+                      double *mean_speed_out);   // gen.cu
+
+extern "C" int mdsea_b200_generate_state(mdsea_ctx *c, const double *speed_cdf, int64_t n_cdf, double speed_step, uint64_t seed,
+                                         int32_t isotropic, double *mean_speed) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    if (speed_cdf && !(speed_step > 0)) return bad(c, "generate_state: speed_step must be positive");
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    MD_TRY(wait_all(c));
+    return md_generate_state(c, speed_cdf, (long long)n_cdf, speed_step, (unsigned long long)seed, isotropic ? 1 : 0, mean_speed);
+}
+
+extern "C" int mdsea_b200_set_dt(mdsea_ctx *c, double dt) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    if (!isfinite(dt)) return bad(c, "set_dt: dt must be finite");
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    MD_TRY(wait_all(c));   // batches in flight were enqueued with the old value
+    c->p.dt = dt;
+    return MDSEA_OK;
+}
+
 extern "C" int mdsea_b200_set_temperature(mdsea_ctx *c, double temp, int32_t reset_ke) {
     // self.temp / self.temp_init seed (simulator.py:79-80); reset_ke puts mean_ke back to None (:75)
     if (!c) return MDSEA_ERR_BAD_ARG;

@@ -1659,6 +1659,21 @@ int md_cutoff_set_state(mdsea_ctx *c, const double *r, const double *v) {
     return MDSEA_OK;
 }
 
+// state generated in place by gen.cu: this rank holds the particles [lo, lo + m) in slots 0 .. m-1 (like the slice upload
+// of md_cutoff_set_state); ids, counts and the pending rebuild follow
+int md_cutoff_adopt_generated(mdsea_ctx *c, long long lo, long long m) {
+    CellState *s = c->cells;
+    k_iota_from<<<g256(m), 256, 0, c->stream>>>(s->id, m, (int)lo);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    c->n = m;
+    s->n_tot = c->n;
+    s->need_rebuild = true;
+    c->stats.n_local = c->n;
+    c->stats.n_ghost = 0;
+    return MDSEA_OK;
+}
+
 // multi-rank front end of a rebuild: route every held particle to the ranks that need it (as owner or as ghost),
 // exchange, and leave the union in the staging arrays (r_alt, v_alt, id_alt); returns the new n_tot.
 static int mr_assemble(mdsea_ctx *c) {

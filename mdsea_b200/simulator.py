@@ -77,12 +77,20 @@ class _BaseSimulator:
     force_evals_per_step: Optional[int] = field(default=None)
     device: int = field(default=0)
     max_neighbors: int = field(default=0)
+    # initial conditions generated on the device (opt-in: same lattice bit for bit and same Maxwell-Boltzmann sampling
+    # scheme as gen.py, but a counter-based generator instead of the global NumPy stream -- not for parity runs)
+    device_init: bool = field(default=False)
+    device_init_seed: int = field(default=0)
+    device_init_isotropic: bool = field(default=False)
 
     def __post_init__(self) -> None:
         sm = self.sm
-        # initial state: same generators, same RNG call order as simulator.py:54-59
-        self._r = PosGen(ndim=sm.NDIM, boxlen=sm.LEN_BOX, nparticles=sm.NUM_PARTICLES).simplecubic()
-        self._v = VelGen(ndim=sm.NDIM, nparticles=sm.NUM_PARTICLES).mb(sm.MASS, sm.TEMP, Config.k_boltzmann)
+        if self.device_init:
+            self._r = self._v = None   # filled from the device on first access
+        else:
+            # initial state: same generators, same RNG call order as simulator.py:54-59
+            self._r = PosGen(ndim=sm.NDIM, boxlen=sm.LEN_BOX, nparticles=sm.NUM_PARTICLES).simplecubic()
+            self._v = VelGen(ndim=sm.NDIM, nparticles=sm.NUM_PARTICLES).mb(sm.MASS, sm.TEMP, Config.k_boltzmann)
         self._acc = np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
         self.ndnp_zeroes = np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
         self._dists = self._drunits = self.pairs_indexes = None
@@ -91,7 +99,7 @@ class _BaseSimulator:
         self.temp_init = sm.TEMP
         self.temp = sm.TEMP
         self.step = 0
-        if self.dt is None:  # simulator.py:86-87
+        if self.dt is None and not self.device_init:  # simulator.py:86-87
             self.dt = get_dt(radius=sm.RADIUS_PARTICLE, mean_speed=float(quicker.norm(self._v, axis=0).mean()))
         self.apply_restcoeff = bool(self.restitution_coeff < 1)
         self.pbarr = ProgressBar("Simulator", sm.STEPS, __name__)
@@ -102,6 +110,26 @@ class _BaseSimulator:
         self._ctx = None
         self._device_fresh = False   # device holds a newer state than the host copies
         self._host_exposed = True    # host arrays may have been edited -> upload before the next device op
+        if self.device_init:
+            self._generate_on_device()
+
+    def _generate_on_device(self) -> None:
+        """PosGen.simplecubic + VelGen.mb + get_dt (simulator.py:54-59,86-87) on the device; needs the GPU at construction."""
+        from mdsea_b200.gen import MONTECARLO_SPEEDRANGE, mb_cdf
+
+        sm = self.sm
+        dt_given = self.dt
+        if self.dt is None:
+            self.dt = 0.0   # placeholder until the mean speed is known
+        ctx = self._ensure_ctx()
+        cdf = None if sm.TEMP == 0 else mb_cdf(sm.MASS, sm.TEMP, Config.k_boltzmann)
+        step = float(MONTECARLO_SPEEDRANGE[1] - MONTECARLO_SPEEDRANGE[0])
+        mean_speed = ctx.generate_state(cdf, step, seed=self.device_init_seed, isotropic=self.device_init_isotropic)
+        if dt_given is None:
+            self.dt = get_dt(radius=sm.RADIUS_PARTICLE, mean_speed=mean_speed)
+            ctx.set_dt(self.dt)
+        self._host_exposed = False
+        self._device_fresh = True
 
     # -- device context --------------------------------------------------------------------------
     def _algorithm_code(self) -> int:

@@ -1,3 +1,9 @@
-timeout 400 python -m pytest tests/test_gpu_cutoff.py tests/test_gpu_multirank.py -m gpu -x -q 2>&1 | tail -2
-for G in 2 4 2; do MDSEA_NBW_GROUPS=$G python profiles/ab_cutoff.py fp32 40 c3 200 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('G$G', d['rebuild_us'], d['force_us'], d['integrate_us_per_step'], d['rebuilds'], d['pe_last'])"; done 2>&1 | tee gpurun_out/ab_append.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], d['config']['list_rebuilds_in_timed_region'], d['gpu_launches'])"
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01_final.json 2> gpurun_out/bench_r01_final.err
+python bench.py --steps 10 --warmup 3 --evals 2 --no-cpu-baseline --no-extra > gpurun_out/bench_r01_c3_evals2.json 2>/dev/null
+python -c "
+import json
+for f in ('bench_r01_final','bench_r01_c3_evals2'):
+    d=json.loads(open('gpurun_out/'+f+'.json').read().strip().splitlines()[-1]); print(f, d.get('value'), d.get('ms_per_step'), d['e2e']['value'], d['roofline']['frac'], d['roofline_hbm']['frac'], d['gpu_launches'])
+"
