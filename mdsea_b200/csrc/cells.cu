@@ -782,7 +782,7 @@ k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long
 // masked out of the hot loop and redone from the float64 positions, like in the all-pairs kernels.
 // ---------------------------------------------------------------------------------------------------
 // POTK = POTF_LJ: sqrt-free Lennard-Jones; POTF_MIE: the generic bounded-Mie member (pair.cuh).
-template <int POTK>
+template <int POTK, bool CS>   // CS: streaming (evict-first) loads of the list rows, see k_nbr_force_f32
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_own, long long cap, const int *__restrict__ nbr,
                 const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL, double rc2, PotF64 P,
@@ -799,7 +799,7 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_
         const int *__restrict__ row0 = nbr + md_nbr_row_base(i, max_nbr);
 #pragma unroll 4
         for (int k = 0; k < nn; ++k) {
-            const int j = row0[k * 32];
+            const int j = CS ? __ldcs(row0 + k * 32) : row0[k * 32];
             const double4 pj = pos[j];
             const double dx = md_minimg_list(pj.x - pi.x, L, halfL);
             const double dy = md_minimg_list(pj.y - pi.y, L, halfL);
@@ -826,7 +826,9 @@ k_nbr_force_f64(const double4 *__restrict__ pos, long long i_begin, long long n_
     }
 }
 
-template <bool TEX, int POTK>
+// CS: the list rows are read once per launch -- streaming loads (evict-first) keep them from displacing the packed
+// positions, which every thread gathers ~56 times, out of L1 / L2.
+template <bool TEX, int POTK, bool CS>
 __global__ void __launch_bounds__(NB_THREADS)
 k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const double *__restrict__ r64, long long i_begin, long long n_own, long long cap,
                 const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int max_nbr, double L, double halfL,
@@ -850,7 +852,7 @@ k_nbr_force_f32(const uint4 *__restrict__ pos, cudaTextureObject_t tex, const do
             int   j[NBG];
             uint4 qj[NBG];
 #pragma unroll
-            for (int u = 0; u < NBG; ++u) j[u] = row0[(k0 + u) * 32];
+            for (int u = 0; u < NBG; ++u) j[u] = CS ? __ldcs(row0 + (k0 + u) * 32) : row0[(k0 + u) * 32];
 #pragma unroll
             for (int u = 0; u < NBG; ++u) qj[u] = TEX ? tex1Dfetch<uint4>(tex, j[u]) : pos[j[u]];
             float    fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
@@ -1877,6 +1879,7 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
 static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
 static int  g_nbw_groups = getenv("MDSEA_NBW_GROUPS") ? atoi(getenv("MDSEA_NBW_GROUPS")) : 2;   // r01: 4: 848 us, 2: 832 us, 1: 851 us per rebuild
 static int  g_nbw_variant = getenv("MDSEA_NBW_VARIANT") ? atoi(getenv("MDSEA_NBW_VARIANT")) : 1;   // bit 0: expanded distance test
+static bool g_force_cs = !(getenv("MDSEA_FORCE_CS") && !strcmp(getenv("MDSEA_FORCE_CS"), "0"));   // A/B switch: streaming list loads
 static bool g_cut_fuse = !(getenv("MDSEA_CUT_FUSE") && !strcmp(getenv("MDSEA_CUT_FUSE"), "0"));   // A/B switch
 static bool g_build_thread = getenv("MDSEA_NBR_BUILD") && !strcmp(getenv("MDSEA_NBR_BUILD"), "thread");  // A/B switch
 struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronises the stream; off by default)
@@ -2006,17 +2009,28 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
     if (c->p.precision == MDSEA_FP64) {
         const PotF64 P = md_pot_f64(c->pot);
 #define NBR_F64(POTK)                                                                                                              \
-    k_nbr_force_f64<POTK><<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr, \
+    do {                                                                                                                           \
+        if (g_force_cs) NBR_F64_(POTK, true);                                                                                      \
+        else NBR_F64_(POTK, false);                                                                                                \
+    } while (0)
+#define NBR_F64_(POTK, CS)                                                                                                         \
+    k_nbr_force_f64<POTK, CS><<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr, \
                                                               c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off,   \
                                                               c->d_sc, guarded)
         if (lj) NBR_F64(POTF_LJ);
         else NBR_F64(POTF_MIE);
 #undef NBR_F64
+#undef NBR_F64_
     } else {
         const double inv_h = fixed_inv_h(c);
         const PotF32 P = md_pot_f32(c->pot, inv_h);
 #define NBR_F32(TEX, POTK)                                                                                                         \
-    k_nbr_force_f32<TEX, POTK><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr, \
+    do {                                                                                                                           \
+        if (g_force_cs) NBR_F32_(TEX, POTK, true);                                                                                 \
+        else NBR_F32_(TEX, POTK, false);                                                                                           \
+    } while (0)
+#define NBR_F32_(TEX, POTK, CS)                                                                                                    \
+    k_nbr_force_f32<TEX, POTK, CS><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr, \
                                                                    s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,         \
                                                                    (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,            \
                                                                    c->d_pe_part + pe_off, c->d_sc, guarded)
@@ -2028,6 +2042,7 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
             else NBR_F32(false, POTF_MIE);
         }
 #undef NBR_F32
+#undef NBR_F32_
     }
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;

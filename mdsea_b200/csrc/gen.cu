@@ -170,7 +170,11 @@ int md_generate_state(mdsea_ctx *c, const double *cdf, long long ncdf, double ds
         k_gen_zero<<<g, 256, 0, c->stream>>>(c->d_v, stride, m, nd);
         c->stats.kernel_launches += 1;
     } else {
-        double *d_cdf = nullptr, *d_part = nullptr;
+        struct Scratch {   // freed on every exit path
+            double *p[3] = {nullptr, nullptr, nullptr};
+            ~Scratch() { for (double *q : p) cudaFree(q); }
+        } scratch;
+        double *&d_cdf = scratch.p[0], *&d_part = scratch.p[1], *&d_tmp = scratch.p[2];
         const int gN = md_div_up(N, 256), nbp = 1024;
         MD_CUDA(c, cudaMalloc(&d_cdf, sizeof(double) * (size_t)ncdf));
         MD_CUDA(c, cudaMalloc(&d_part, sizeof(double) * ((size_t)gN + nbp + 1)));
@@ -186,13 +190,11 @@ int md_generate_state(mdsea_ctx *c, const double *cdf, long long ncdf, double ds
         c->stats.kernel_launches += 1;
         std::vector<double> h((size_t)gN);
         if (W > 1) {   // the mean speed of the WHOLE system: regenerate all norms into scratch (the state slice is untouched)
-            double *d_tmp = nullptr;
             MD_CUDA(c, cudaMalloc(&d_tmp, sizeof(double) * (size_t)nd * (size_t)N));
             k_gen_mb<<<gN, 256, 0, c->stream>>>(d_tmp, N, 0, N, nd, d_cdf, (int)ncdf, ds, seed, isotropic, d_prod, d_part);
             c->stats.kernel_launches += 1;
             MD_CUDA(c, cudaMemcpyAsync(h.data(), d_part, sizeof(double) * (size_t)gN, cudaMemcpyDeviceToHost, c->stream));
             MD_CUDA(c, cudaStreamSynchronize(c->stream));
-            cudaFree(d_tmp);
         } else {
             MD_CUDA(c, cudaMemcpyAsync(h.data(), d_part, sizeof(double) * (size_t)g, cudaMemcpyDeviceToHost, c->stream));
             MD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -201,8 +203,6 @@ int md_generate_state(mdsea_ctx *c, const double *cdf, long long ncdf, double ds
         double sum = 0.0;
         for (double x : h) sum += x;   // fixed order: the same bits on every rank
         mean_speed = sum / (double)N;
-        cudaFree(d_cdf);
-        cudaFree(d_part);
     }
     MD_CUDA(c, cudaGetLastError());
     if (c->cutoff_path) MD_TRY(md_cutoff_adopt_generated(c, lo, m));
