@@ -4,25 +4,32 @@
 (quench temperature); ``Config.gravity_acceleration`` at every run() when gravity is on.
 """
 from contextlib import contextmanager
-from dataclasses import dataclass, fields
 
 from mdsea_b200.f_constants import physical_constants
 
 
-@dataclass
 class _Config:
-    k_boltzmann: float = physical_constants["k_boltzmann"]
-    gravity_acceleration: float = physical_constants["gravity_acceleration"]
+    """Attribute bag restricted to the known physical constants; ``update`` rejects unknown keys
+    with the reference's AttributeError (mdsea/config.py:13-17)."""
+
+    __slots__ = tuple(physical_constants)
+
+    def __init__(self) -> None:
+        for name, default in physical_constants.items():
+            object.__setattr__(self, name, default)
 
     def update(self, new: dict) -> None:
-        known = {f.name for f in fields(self)}
-        for key, value in new.items():
-            if key not in known:
-                raise AttributeError(f"Not a valid config field: {key}")
-            setattr(self, key, value)
+        for name in new:
+            if name not in self.__slots__:
+                raise AttributeError(f"Not a valid config field: {name}")
+        for name, value in new.items():
+            setattr(self, name, value)
 
     def snapshot(self) -> dict:
-        return {f.name: getattr(self, f.name) for f in fields(self)}
+        return {name: getattr(self, name) for name in self.__slots__}
+
+    def __repr__(self) -> str:
+        return "_Config(" + ", ".join(f"{k}={v!r}" for k, v in self.snapshot().items()) + ")"
 
 
 Config = _Config()
@@ -30,6 +37,7 @@ Config = _Config()
 
 @contextmanager
 def config_context(**overrides):
+    """Temporarily override configuration fields (the reference's experimental helper, config.py:23-35)."""
     saved = Config.snapshot()
     Config.update(overrides)
     try:

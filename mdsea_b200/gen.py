@@ -2,7 +2,10 @@
 
 Parity "on the same initial conditions" means reproducing gen.py's output bit for bit, including
 its use of the GLOBAL numpy RNG in a fixed call order and the whole-array ``np.prod`` in the
-direction cosines (gen.py:83-92), which in 3-D leaves vy and vz near zero.
+direction cosines (gen.py:83-92), which in 3-D leaves vy and vz near zero.  The arithmetic below
+therefore keeps the reference's operation order wherever a rounding could differ; everything
+else (structure, naming of internals) is this package's own.  `csrc/gen.cu` samples the same
+table on the device (opt-in, different random stream).
 """
 import logging
 import math
@@ -18,27 +21,52 @@ log = logging.getLogger(__name__)
 MONTECARLO_SPEEDRANGE = np.arange(0, 50, 0.001)
 
 
+class _SpeedTable:
+    """Maxwell-Boltzmann speed law tabulated on the Monte-Carlo grid (gen.py:19-37)."""
+
+    def __init__(self, mass, temp, k_boltzmann, grid=MONTECARLO_SPEEDRANGE):
+        self.mass, self.temp, self.kb, self.grid = mass, temp, k_boltzmann, grid
+        self.kt = k_boltzmann * temp
+
+    def density(self) -> np.ndarray:
+        s2 = self.grid ** 2
+        norm = (self.mass / (2 * math.pi * self.kb * self.temp)) ** 1.5   # products left to right, like gen.py:21-23
+        shell = 4 * math.pi * s2
+        return norm * shell * np.exp(-self.mass * s2 / (2 * self.kb * self.temp))
+
+    def cumulative(self) -> np.ndarray:
+        a = math.sqrt(self.kt / self.mass)
+        head = special.erf(self.grid / (math.sqrt(2) * a))
+        ramp = np.sqrt(2 / math.pi) * self.grid
+        bell = np.exp(-(self.grid ** 2) / (2 * a ** 2)) / a
+        return head - ramp * bell
+
+    def sample(self, uniforms: np.ndarray) -> np.ndarray:
+        """Inverse-CDF transform of uniform deviates (gen.py:104-105; scipy's linear interp1d)."""
+        return interp1d(self.cumulative(), self.grid)(uniforms)
+
+
 def mb(mass, temp, k_boltzmann) -> np.ndarray:
     """Maxwell-Boltzmann speed density on the Monte-Carlo grid (gen.py:19-24)."""
-    s2 = MONTECARLO_SPEEDRANGE ** 2
-    pref = (mass / (2 * math.pi * k_boltzmann * temp)) ** 1.5
-    return pref * (4 * math.pi * s2) * np.exp(-mass * s2 / (2 * k_boltzmann * temp))
+    return _SpeedTable(mass, temp, k_boltzmann).density()
 
 
 def mb_cdf(mass, temp, k_boltzmann) -> np.ndarray:
     """Maxwell-Boltzmann speed CDF on the Monte-Carlo grid (gen.py:27-37)."""
-    a = math.sqrt(k_boltzmann * temp / mass)
-    erf_part = special.erf(MONTECARLO_SPEEDRANGE / (math.sqrt(2) * a))
-    lin = np.sqrt(2 / math.pi) * MONTECARLO_SPEEDRANGE
-    gauss = np.exp(-(MONTECARLO_SPEEDRANGE ** 2) / (2 * a ** 2)) / a
-    return erf_part - lin * gauss
+    return _SpeedTable(mass, temp, k_boltzmann).cumulative()
 
 
 class _Gen:
+    """Holds one (ndim, nparticles) coordinate array and whether a generator has filled it."""
+
     def __init__(self, nparticles: int, ndim: int) -> None:
         self.nparticles, self.ndim = nparticles, ndim
         self.generated = False
         self.coords = np.zeros((ndim, nparticles), dtype=DTYPE)
+
+    def _done(self, coords) -> np.ndarray:
+        self.coords, self.generated = coords, True
+        return self._get()
 
     def _get(self) -> np.ndarray:
         if not self.generated:
@@ -46,41 +74,40 @@ class _Gen:
         return self.coords.astype(DTYPE)
 
 
+def _sine_product(thetas, upto):
+    """gen.py:83-92 multiplies by np.prod over a LIST of per-particle arrays, i.e. over every particle."""
+    return np.prod([np.sin(thetas[j]) for j in range(upto)])
+
+
 class VelGen(_Gen):
     def __init__(self, nparticles: int, ndim: int) -> None:
         super().__init__(nparticles, ndim)
         self.speeds = None
 
-    def _direction(self, i, thetas):
-        """Hyperspherical direction factor of component i, with gen.py's np.prod over all particles."""
-        nd = self.ndim
-        lead_sines = lambda upto: np.prod([np.sin(thetas[j]) for j in range(upto)])
+    def _component(self, i, thetas):
+        """Hyperspherical component i of the velocity (gen.py:83-92), operation order preserved."""
+        nd, s = self.ndim, self.speeds
+        last = nd - 2
         if i == nd - 1:
-            return np.cos(thetas[nd - 2]), lead_sines(nd - 2)
-        if i == nd - 2:
-            return np.sin(thetas[nd - 2]), lead_sines(nd - 2)
+            return s * np.cos(thetas[last]) * _sine_product(thetas, last)
+        if i == last:
+            return s * np.sin(thetas[last]) * _sine_product(thetas, last)
         if i == 0:
-            return np.cos(thetas[0]), None
-        return np.cos(thetas[i]), lead_sines(i)
+            return s * np.cos(thetas[0])
+        return s * np.cos(thetas[i]) * _sine_product(thetas, i)
 
     def mb(self, mass, temp, k_boltzmann) -> np.ndarray:
-        """Inverse-CDF Maxwell-Boltzmann speeds times random directions (gen.py:98-123)."""
+        """Inverse-CDF Maxwell-Boltzmann speeds times random directions (gen.py:98-123).
+
+        RNG call order (global NumPy stream): random(N) for the speeds, then ndim - 2 times
+        uniform(0, pi, N), then uniform(0, 2 pi, N)."""
+        n, nd = self.nparticles, self.ndim
         if temp == 0:
-            self.coords = np.zeros((self.ndim, self.nparticles), dtype=DTYPE)
-            self.generated = True
-            return self._get()
-        inv_cdf = interp1d(mb_cdf(mass, temp, k_boltzmann), MONTECARLO_SPEEDRANGE)
-        self.speeds = inv_cdf(np.random.random(self.nparticles))
-        thetas = [np.random.uniform(0, math.pi, self.nparticles) for _ in range(self.ndim - 2)]
-        thetas.append(np.random.uniform(0, 2 * math.pi, self.nparticles))
-        rows = []
-        for i in range(self.ndim):
-            trig, sines = self._direction(i, thetas)
-            comp = self.speeds * trig
-            rows.append(comp if sines is None else comp * sines)
-        self.coords = np.array(rows)
-        self.generated = True
-        return self._get()
+            return self._done(np.zeros((nd, n), dtype=DTYPE))
+        self.speeds = _SpeedTable(mass, temp, k_boltzmann).sample(np.random.random(n))
+        polar = [np.random.uniform(0, math.pi, n) for _ in range(nd - 2)]
+        thetas = polar + [np.random.uniform(0, 2 * math.pi, n)]
+        return self._done(np.array([self._component(i, thetas) for i in range(nd)]))
 
 
 class PosGen(_Gen):
@@ -90,19 +117,18 @@ class PosGen(_Gen):
 
     def simplecubic(self) -> np.ndarray:
         """Simple cubic lattice, x fastest (gen.py:144-156)."""
-        per_row = round(self.nparticles ** (1 / self.ndim))
-        assert self.nparticles == per_row ** self.ndim
+        nd = self.ndim
+        per_row = round(self.nparticles ** (1 / nd))
+        assert self.nparticles == per_row ** nd
         ticks = 0.5 + np.arange(per_row, dtype=int)
         span = self.boxlen / per_row
-        for d in range(self.ndim):
-            self.coords[d] = span * np.tile(np.repeat(ticks, per_row ** d), per_row ** (self.ndim - d - 1))
-        self.generated = True
-        return self._get()
+        for d in range(nd):
+            self.coords[d] = span * np.tile(np.repeat(ticks, per_row ** d), per_row ** (nd - d - 1))
+        return self._done(self.coords)
 
     def random(self, pradius) -> np.ndarray:
         """Uniform random positions at least one radius from the walls (gen.py:158-168)."""
         usable = self.boxlen - 2 * pradius
-        self.coords = usable * np.random.random((self.ndim, self.nparticles))
-        self.coords += pradius
-        self.generated = True
-        return self._get()
+        coords = usable * np.random.random((self.ndim, self.nparticles))
+        coords += pradius
+        return self._done(coords)
