@@ -177,6 +177,40 @@ def test_product_fails_loudly_without_gpu():
     assert ei.value.status == -2
 
 
+def test_device_init_needs_the_gpu_at_construction(in_tmp_cwd):
+    """device_init=True generates the state on the device: without a GPU the constructor fails loudly (no host fallback),
+    while the default keeps generating on the host and needs no GPU until the first device call."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mdsea_b200 import _capi
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    with config_context(k_boltzmann=1.0):
+        sm = SysManager.new(simid="devinit", ndim=3, num_particles=27, steps=2, vol_fraction=0.2, radius_particle=0.5)
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1))
+        assert sim.r_vec.shape == (3, 27) and sim.dt > 0
+        with pytest.raises(_capi.MdseaError) as ei:
+            ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), device_init=True)
+        assert ei.value.status == -2
+
+
+def test_config_rejects_unknown_fields_and_restores_on_exit():
+    from mdsea_b200.config import Config, config_context
+
+    before = Config.snapshot()
+    with pytest.raises(AttributeError):
+        Config.update({"no_such_field": 1})
+    with config_context(k_boltzmann=2.0, gravity_acceleration=1.0) as cfg:
+        assert cfg.k_boltzmann == 2.0 and Config.gravity_acceleration == 1.0
+    assert Config.snapshot() == before
+    assert set(before) == {"k_boltzmann", "gravity_acceleration"}
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "mdsea_b200")):
         for fn in files:
