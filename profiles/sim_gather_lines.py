@@ -88,3 +88,35 @@ for layout in ("plain", "by_z", "by_yz"):
             nuse += live.shape[0]
             nlines += np.unique(live // 8).shape[0]
     print(f"{layout:8s} {nrows / ntiles:10.1f} {nlines / nrows:10.2f} {nlines / ntiles:11.1f} {nuse / nrows:19.1f}")
+
+# ---- two particles per lane: one gather serves both if the lane walks the UNION of their lists (the r^2 < rc^2 test
+# decides per particle, so no per-particle membership is needed).  How large is the union for slot neighbours?
+def mean_union(pair_order):
+    tot = cnt = 0
+    for a, b in zip(pair_order[0::2], pair_order[1::2]):
+        la, lb = idx[off[a]:off[a + 1]], idx[off[b]:off[b + 1]]
+        tot += np.union1d(la, lb).shape[0] + 0   # (a is in b's list and vice versa: each still needs the other's position)
+        cnt += 1
+    return tot / cnt
+
+
+sample = order[: (min(n, 20000) // 2) * 2]
+print(f"\ntwo particles per lane, gathers per PAIR of particles (2 x {np.diff(off).mean():.1f} = {2 * np.diff(off).mean():.1f} separately):")
+print(f"  canonical (cell, id) order, slots 2l and 2l+1 : {mean_union(sample):.1f}")
+# in-cell order by x (an internal layout that keeps the cells but not the id order inside them)
+key = cell_of.astype(np.float64) * 1e3 + (r[0] % L) / L
+byx = np.argsort(key, kind="stable")
+print(f"  cells kept, particles ordered by x inside a cell: {mean_union(byx[: sample.shape[0]]):.1f}")
+# greedy nearest-neighbour pairing inside each cell (upper bound of what an in-cell spatial order could give)
+pairs = []
+for c in np.unique(cell_of[sample]):
+    members = list(np.where(cell_of == c)[0])
+    while len(members) > 1:
+        a = members.pop(0)
+        d = r[:, members] - r[:, [a]]
+        d -= np.rint(d / L) * L
+        j = int(np.argmin((d ** 2).sum(axis=0)))
+        pairs += [a, members.pop(j)]
+    if len(pairs) >= sample.shape[0]:
+        break
+print(f"  greedy nearest pairs inside a cell               : {mean_union(np.array(pairs)):.1f}")
