@@ -41,8 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s, o = job
         r = subprocess.run([NVCC, *FLAGS, "-c", s, "-o", o], capture_output=True, text=True)
         log = o[:-2] + ".ptxas.log"
-        with open(log, "w") as f:
-            f.write(r.stderr)
+        with open(log, "w") as f:   # registers / spills / shared memory per kernel (tracked); compile times would only add noise
+            f.write("".join(ln for ln in r.stderr.splitlines(True) if "Compile time" not in ln))
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{r.stderr}")
         if verbose:
