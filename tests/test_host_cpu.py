@@ -199,6 +199,33 @@ def test_device_init_needs_the_gpu_at_construction(in_tmp_cwd):
         assert ei.value.status == -2
 
 
+def test_quench_targets_follow_the_reference_call_order(in_tmp_cwd):
+    """Host logic of apply_special (simulator.py:185-190): per step, column 0 = the isothermal target (temp_init), column 1
+    = the scheduled quench of that step (QUENCH_STEP = round(STEPS * timing), targets consumed in order); NaN = no call;
+    None when a batch has no target at all.  No GPU needed: the solver only builds the array here."""
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    with config_context(k_boltzmann=1.0):
+        sm = SysManager.new(simid="q", ndim=2, num_particles=16, steps=40, vol_fraction=0.2, radius_particle=0.5, temp=0.9,
+                            quench_temps=[0.5, 0.1], quench_timings=[0.25, 0.75])
+        assert sm.QUENCH_STEP == [10, 30]
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1))
+        assert sim._quench_targets(0, 10) is None                     # steps 0..9: nothing scheduled
+        q = sim._quench_targets(10, 10)                               # step 10 is the first step of this batch
+        assert q.shape == (10, 2) and q[0, 1] == 0.5 and np.isnan(q[1:]).all() and np.isnan(q[:, 0]).all()
+        assert sim._quench_targets(20, 10) is None
+        q = sim._quench_targets(30, 10)
+        assert q[0, 1] == 0.1 and np.isnan(q[1:, 1]).all()
+        sm2 = SysManager.new(simid="q2", ndim=2, num_particles=16, steps=8, vol_fraction=0.2, radius_particle=0.5, temp=0.9,
+                             quench_temps=[0.3], quench_timings=[0.5])
+        iso = ContinuousPotentialSolver(sm2, pot=Potential.lennardjones(1, 1), isothermal=True)
+        q = iso._quench_targets(0, 8)
+        assert np.all(q[:, 0] == 0.9) and q[4, 1] == 0.3 and np.isnan(np.delete(q[:, 1], 4)).all()
+
+
 def test_config_rejects_unknown_fields_and_restores_on_exit():
     from mdsea_b200.config import Config, config_context
 
