@@ -10,6 +10,7 @@ warp waits for the lane with the most hits of the chunk).  Per tile the model re
     staged     candidates staged into shared memory per particle (x ~16 instructions, one lane each)
     chunks     chunk iterations per tile                         (x ~35 instructions of per-chunk overhead)
     append     append-loop iterations per tile = sum over chunks of max over lanes of the lane's hits (x ~11 instructions)
+    /row       the same if the appends were done once per stencil ROW (max over lanes of the lane's hits in the row)
     ideal      hits of the tile / lanes: what the append loop would cost without divergence
 
     python profiles/sim_list_build.py [per_row=32] [melt_steps=300]
@@ -49,7 +50,7 @@ nbr_slots = [np.sort(slot_of[idx[off[i]:off[i + 1]]]) for i in range(n)]
 def model_warp(tile, group, chunk=32):
     lanes = 32
     per_lane = tile // lanes
-    tests = staged = chunks = append = hits_tot = parts = 0
+    tests = staged = chunks = append = append_row = hits_tot = parts = 0
     for t0 in range(0, n - tile + 1, tile * 5):
         ids = order[t0:t0 + tile]
         parts += tile
@@ -74,6 +75,12 @@ def model_warp(tile, group, chunk=32):
         # lock step over the 9 rows; per row the warp iterates max-over-groups chunks
         for k in range(9):
             longest = max(st[0][k].shape[0] for st in streams)
+            # append once per ROW instead of once per chunk: max over lanes of the lane's hits in the whole row
+            worst_row = 0
+            for rows, mem in streams:
+                for l0 in range(0, len(mem), per_lane):
+                    worst_row = max(worst_row, sum(int(np.isin(rows[k], nbr_slots[i], assume_unique=True).sum()) for i in mem[l0:l0 + per_lane]))
+            append_row += worst_row
             for c0 in range(0, longest, chunk):
                 chunks += 1
                 worst = 0
@@ -90,12 +97,12 @@ def model_warp(tile, group, chunk=32):
                         worst = max(worst, h)
                 append += worst
     tiles = parts / tile
-    return dict(tests=tests / parts, staged=staged / parts, chunks=chunks / tiles, append=append / tiles, ideal=hits_tot / lanes / tiles,
+    return dict(tests=tests / parts, staged=staged / parts, chunks=chunks / tiles, append=append / tiles, append_row=append_row / tiles, ideal=hits_tot / lanes / tiles,
                 tiles_per_1e6=1e6 / tile)
 
 
 print(f"N = {n}, nc = {nc}, mean list length {np.diff(off).mean():.1f}")
-print(f"{'shape':34s} {'tests':>7s} {'staged':>7s} {'chunks':>7s} {'append':>7s} {'ideal':>6s} {'~Minstr per 1e6 particles':>26s}")
+print(f"{'shape':34s} {'tests':>7s} {'staged':>7s} {'chunks':>7s} {'append':>7s} {'/row':>6s} {'ideal':>6s} {'~Minstr per 1e6 particles':>26s}")
 for label, tile, group in (("32 slots, 4 groups of 8 (r01 start)", 32, 8), ("32 slots, 2 groups of 16 (now)", 32, 16),
                            ("32 slots, 1 group", 32, 32), ("64 slots (2 per lane), 4 groups of 16", 64, 16),
                            ("64 slots (2 per lane), 2 groups of 32", 64, 32)):
@@ -104,4 +111,4 @@ for label, tile, group in (("32 slots, 4 groups of 8 (r01 start)", 32, 8), ("32 
     # warp instructions per tile: tests are shared by the lanes (x per_lane particles each), LDS + FMA part ~ 8.75 / test for
     # one particle per lane, ~ 1 + 7.75 x per_lane for several (one broadcast load serves all of a lane's particles)
     instr = (m["tests"] * tile / 32 / per_lane) * (1.0 + 7.75 * per_lane) + m["staged"] * tile / 32 * 16 + m["chunks"] * 35 + m["append"] * 11
-    print(f"{label:34s} {m['tests']:7.0f} {m['staged']:7.1f} {m['chunks']:7.1f} {m['append']:7.1f} {m['ideal']:6.1f} {instr * m['tiles_per_1e6'] / 1e6:26.0f}")
+    print(f"{label:34s} {m['tests']:7.0f} {m['staged']:7.1f} {m['chunks']:7.1f} {m['append']:7.1f} {m['append_row']:6.1f} {m['ideal']:6.1f} {instr * m['tiles_per_1e6'] / 1e6:26.0f}")
