@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MDSEA_B200_ABI_VERSION 1
+#define MDSEA_B200_ABI_VERSION 2
 
 typedef enum {
     MDSEA_OK = 0,
@@ -125,6 +125,11 @@ typedef struct {
     int64_t n_local, n_ghost;    /* owned / ghost particles on this rank (cutoff path)            */
     int64_t nbr_entries;         /* directed entries in the current neighbour list                */
     double  ms_force, ms_integrate, ms_rebuild, ms_comm; /* CUDA-event time sums when profiling is on */
+    /* cut-off path, fp32 pair math: 1 while the current neighbour lists are tile lists (16-bit offsets into per-block
+     * windows that the force kernel stages in shared memory), 0 for the 32-bit per-particle lists */
+    int64_t tile_lists;
+    int64_t tile_window_max;     /* largest window of the current list generation, entries of 16 bytes        */
+    int64_t tile_fallbacks;      /* list generations that fell back to the per-particle lists (window did not fit) */
 } mdsea_stats;
 
 const char *mdsea_b200_version(void);
@@ -189,6 +194,10 @@ int mdsea_b200_update_dists(mdsea_ctx *ctx, double *dists, double *drunits);
  * Two-call pattern: pass idx == NULL to obtain *n_entries first. offsets has N+1 entries. */
 int mdsea_b200_get_cells(mdsea_ctx *ctx, int32_t *cell_of, int32_t *order, int32_t ncell_dim[3]);
 int mdsea_b200_get_neighbors(mdsea_ctx *ctx, int64_t *n_entries, int64_t *offsets, int32_t *idx);
+/* diagnostics of the tile lists (fp32 cut-off path): per block of 128 slots the number of window entries and of
+ * contiguous slot ranges that the force kernel stages in shared memory every step.  Pass NULL arrays to obtain
+ * *n_blocks first; *n_blocks == 0 while the current list generation is not in tile format. */
+int mdsea_b200_get_tile_windows(mdsea_ctx *ctx, int64_t *n_blocks, int32_t *n_win, int32_t *n_rng);
 
 /* seeds self.temp / temp_init (simulator.py:79-80) -- the value written to the `temp` dataset until a
  * quench changes it; reset_ke != 0 puts mean_ke back to None (simulator.py:75). */

@@ -7,7 +7,7 @@ import numpy as np
 
 from mdsea_b200 import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 STATUS = {0: "MDSEA_OK", -1: "MDSEA_ERR_BAD_ARG", -2: "MDSEA_ERR_CUDA", -3: "MDSEA_ERR_NCCL", -4: "MDSEA_ERR_STATE",
           -5: "MDSEA_ERR_NONFINITE", -6: "MDSEA_ERR_CAPACITY", -7: "MDSEA_ERR_UNSUPPORTED"}
@@ -48,7 +48,8 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("force_evals", C.c_int64), ("pair_evals_unique", C.c_int64),
                 ("pair_evals_executed", C.c_int64), ("kernel_launches", C.c_int64), ("list_rebuilds", C.c_int64),
                 ("n_local", C.c_int64), ("n_ghost", C.c_int64), ("nbr_entries", C.c_int64),
-                ("ms_force", C.c_double), ("ms_integrate", C.c_double), ("ms_rebuild", C.c_double), ("ms_comm", C.c_double)]
+                ("ms_force", C.c_double), ("ms_integrate", C.c_double), ("ms_rebuild", C.c_double), ("ms_comm", C.c_double),
+                ("tile_lists", C.c_int64), ("tile_window_max", C.c_int64), ("tile_fallbacks", C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -61,6 +62,7 @@ EXPORTS = [
     "mdsea_b200_get_stats", "mdsea_b200_first_nonfinite_step", "mdsea_b200_set_profiling", "mdsea_b200_stream",
     "mdsea_b200_nccl_unique_id", "mdsea_b200_comm_init", "mdsea_b200_comm_init_local", "mdsea_b200_rank_capacity",
     "mdsea_b200_measure_fma_peak", "mdsea_b200_analyse_speeds", "mdsea_b200_generate_state", "mdsea_b200_set_dt",
+    "mdsea_b200_get_tile_windows",
 ]
 
 _lib = None
@@ -286,6 +288,17 @@ class Context:
         idx = np.empty(max(ne.value, 1), dtype=np.int32)
         self._ck(self.lib.mdsea_b200_get_neighbors(self.h, C.byref(ne), _ptr(offsets), _ptr(idx)))
         return offsets, idx[:ne.value]
+
+
+    def get_tile_windows(self):
+        """(window entries, slot ranges) per block of 128 slots of the current tile lists; empty arrays if not in tile format"""
+        nb = C.c_int64(0)
+        self._ck(self.lib.mdsea_b200_get_tile_windows(self.h, C.byref(nb), None, None))
+        nw = np.zeros(nb.value, dtype=np.int32)
+        nr = np.zeros(nb.value, dtype=np.int32)
+        if nb.value:
+            self._ck(self.lib.mdsea_b200_get_tile_windows(self.h, C.byref(nb), _ptr(nw), _ptr(nr)))
+        return nw, nr
 
 
 def measure_fma_peak(device=0, fp64=False) -> float:

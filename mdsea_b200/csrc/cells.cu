@@ -154,6 +154,16 @@ struct CellState {
     // the finish kernel of step k can be guarded by drift k's trigger while its fused drift k+1 raises its own.
     int     drift_tag = 0;
     int     published_tag = 0;            // single GPU: the fused finish kernel already published this tag's trigger (h_flag[2 + (tag & 1)])
+    // tile path (cells_tile.cuh): fp32 pair math, windows in shared memory, 16-bit window offsets as list entries
+    bool    tile_ok = false;              // available: fp32 mode, >= 4 cells per dimension, not switched off (MDSEA_TILE=0)
+    bool    tile_active = false;          // the CURRENT list generation is in tile format
+    bool    tile_off = false;             // a block's window did not fit: per-particle kernels until the next set_state
+    struct TileDesc *tl_desc = nullptr;   // [ceil(cap / 128)]
+    uint4  *tl_list = nullptr;            // [cap / 32][tl_max_nbr / 8][32] vectors of 8 16-bit window offsets
+    int     tl_max_nbr = 0;
+    int    *tl_stats = nullptr;           // device: fallback flag, max window, max ranges of the last build
+    int     tl_win = 0;                   // largest window of the current list generation (entries): shared memory of the force launch
+    long long tl_fallbacks = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -197,6 +207,7 @@ __device__ __forceinline__ uint32_t md_to_fixed(double x, double inv_h) {
 #include "cells_binning.cuh"
 #include "cells_nbr_build.cuh"
 #include "cells_force.cuh"
+#include "cells_tile.cuh"
 #include "cells_integrate.cuh"
 #include "cells_scan.cuh"
 #include "cells_decomp.cuh"
@@ -213,6 +224,8 @@ static inline double fixed_inv_h(const mdsea_ctx *c) { return 4294967296.0 / c->
 static inline int g256(long long n) { return md_div_up(n > 0 ? n : 1, 256); }
 // blocks of a list force launch over the owned slots [i0, i1)
 static inline int force_grid(long long i0, long long i1) { return md_div_up(i1 - i0, NB_THREADS); }
+// tile path: the blocks of 128 absolute slots that cover [i0, i1) (never more than force_grid(i0, i1) + 1)
+static inline int tile_grid(long long i0, long long i1) { return (int)((i1 + TL_BLOCK - 1) / TL_BLOCK - i0 / TL_BLOCK); }
 
 static int scan_exclusive(mdsea_ctx *c, const int *in, int *out, long long n) {
     CellState *s = c->cells;
@@ -312,8 +325,28 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaMalloc(&s->cell, sizeof(int) * s->cap));
     MD_CUDA(c, cudaMalloc(&s->cell_start, sizeof(int) * ((size_t)s->ncell + 1)));
     MD_CUDA(c, cudaMalloc(&s->cell_end, sizeof(int) * ((size_t)s->ncell + 1)));
-    MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
     MD_CUDA(c, cudaMalloc(&s->nbr_cnt, sizeof(int) * s->cap));
+    // Tile path (fp32 pair math, >= 4 cells per dimension like the warp-cooperative build): windows in shared memory and
+    // 16-bit list entries.  The 32-bit per-particle list is then only allocated if a list generation ever falls back to it.
+    s->tile_ok = p.precision == MDSEA_FP32 && s->nc >= 4 && !(getenv("MDSEA_TILE") && !strcmp(getenv("MDSEA_TILE"), "0"));
+    if (s->tile_ok) {
+        if (p.max_neighbors > 0) s->tl_max_nbr = (p.max_neighbors + 7) / 8 * 8;
+        else {
+            const double rho = (double)N / (p.boxlen * p.boxlen * p.boxlen);
+            const double expect = 4.0 / 3.0 * 3.14159265358979 * s->rlist * s->rlist * s->rlist * rho;
+            s->tl_max_nbr = ((int)(expect * 1.3) + 24 + 7) / 8 * 8;
+        }
+        if (s->tl_max_nbr > 640) s->tl_max_nbr = 640;   // 160 KB of list rows in shared memory per build block
+        const size_t nblk = (size_t)((s->cap + TL_BLOCK - 1) / TL_BLOCK);
+        MD_CUDA(c, cudaMalloc(&s->tl_desc, sizeof(TileDesc) * nblk));
+        MD_CUDA(c, cudaMalloc(&s->tl_list, sizeof(uint4) * (size_t)(s->tl_max_nbr / 8) * (size_t)s->n_pad));
+        MD_CUDA(c, cudaMalloc(&s->tl_stats, sizeof(int) * 4));
+        MD_CUDA(c, cudaFuncSetAttribute(k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (s->tl_max_nbr + 1) * 2 * TL_BLOCK));
+        MD_CUDA(c, cudaFuncSetAttribute(k_tile_force_f32<POTF_LJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TL_WIN_MAX + 1) * 16));
+        MD_CUDA(c, cudaFuncSetAttribute(k_tile_force_f32<POTF_MIE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (TL_WIN_MAX + 1) * 16));
+    } else {
+        MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
+    }
     MD_CUDA(c, cudaMalloc(&s->d_cnt, sizeof(int) * (MD_MAXW + 8)));
     MD_CUDA(c, cudaHostAlloc(&s->h_flag, sizeof(int) * 4, cudaHostAllocMapped));
     MD_CUDA(c, cudaHostGetDevicePointer((void **)&s->d_flag_mapped, s->h_flag, 0));
@@ -336,7 +369,7 @@ int md_cells_setup(mdsea_ctx *c) {
     c->n_ke_part = md_div_up(s->cap, 256);
     MD_CUDA(c, cudaMalloc(&c->d_ke_part, sizeof(double) * c->n_ke_part));
     MD_CUDA(c, cudaMemset(c->d_ke_part, 0, sizeof(double) * c->n_ke_part));
-    c->n_pe_part = force_grid(0, s->cap) + 2;
+    c->n_pe_part = force_grid(0, s->cap) + 4;
     MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
     MD_CUDA(c, cudaMemset(c->d_pe_part, 0, sizeof(double) * c->n_pe_part));
     if (W > 1) {
@@ -368,6 +401,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->d_cursor); cudaFree(s->halo_flag); cudaFree(s->halo_scan); cudaFree(s->halo_idx); cudaFree(s->scan_tmp);
     cudaFree(s->halo_send); cudaFree(s->halo_recv); cudaFree(s->p2p_buf); cudaFree(s->d_roff);
     cudaFree(s->pe_fold); cudaFree(s->ke_glob);
+    cudaFree(s->tl_desc); cudaFree(s->tl_list); cudaFree(s->tl_stats);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
@@ -408,6 +442,7 @@ int md_cutoff_set_state(mdsea_ctx *c, const double *r, const double *v) {
     }
     s->n_tot = c->n;
     s->need_rebuild = true;
+    s->tile_off = false;
     c->stats.n_local = c->n;
     c->stats.n_ghost = 0;
     return MDSEA_OK;
@@ -647,6 +682,36 @@ struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronise
     }
 };
 
+// per-particle 32-bit Verlet lists (k_nbr_build_warp / k_nbr_build): fp64 mode, < 4 cells per dimension, MDSEA_TILE=0, and
+// list generations whose tile windows did not fit.  The list itself is allocated on first use.
+static int legacy_list_build(mdsea_ctx *c) {
+    CellState *s = c->cells;
+    if (!s->nbr) MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
+    {
+        const double ih = fixed_inv_h(c);
+        const double rl2s = s->rl2 * ih * ih;
+        const float lo = (float)(rl2s * (1.0 - 2e-5)), hi = (float)(rl2s * (1.0 + 2e-5));
+        const long long no = c->n > 0 ? c->n : 1;
+        if (g_build_thread || s->nc < 4)
+            k_nbr_build<<<md_div_up(no, NB_THREADS), NB_THREADS, 0, c->stream>>>(
+                c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
+                s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
+        else {
+#define NBW_LAUNCH(EXP, G)                                                                                                          \
+    k_nbr_build_warp<EXP, G><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                     \
+        c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
+        rl2s, (float)(rl2s * 2e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc)
+            if (!(g_nbw_variant & 1)) NBW_LAUNCH(false, 4);   // MDSEA_NBW_VARIANT=0: direct distance test (A/B)
+            else if (g_nbw_groups == 1) NBW_LAUNCH(true, 1);
+            else if (g_nbw_groups == 2) NBW_LAUNCH(true, 2);
+            else NBW_LAUNCH(true, 4);
+#undef NBW_LAUNCH
+        }
+    }
+    c->stats.kernel_launches += 1;
+    return MDSEA_OK;
+}
+
 static int rebuild(mdsea_ctx *c) {
     CellState *s = c->cells;
     const int W = c->p.world;
@@ -720,28 +785,33 @@ static int rebuild(mdsea_ctx *c) {
     pt.lap("place");
     if (W > 1) MD_TRY(build_halo_lists(c));
     pt.lap("halo lists");
-    {
+    s->tile_active = false;
+    if (s->tile_ok && !s->tile_off) {
+        // tile lists + windows; the build reports (mapped memory, one host sync per rebuild) whether every block's window fit
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
-        const float lo = (float)(rl2s * (1.0 - 2e-5)), hi = (float)(rl2s * (1.0 + 2e-5));
         const long long no = c->n > 0 ? c->n : 1;
-        if (g_build_thread || s->nc < 4)
-            k_nbr_build<<<md_div_up(no, NB_THREADS), NB_THREADS, 0, c->stream>>>(
-                c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
-                s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
-        else {
-#define NBW_LAUNCH(EXP, G)                                                                                                          \
-    k_nbr_build_warp<EXP, G><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                     \
-        c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
-        rl2s, (float)(rl2s * 2e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc)
-            if (!(g_nbw_variant & 1)) NBW_LAUNCH(false, 4);   // MDSEA_NBW_VARIANT=0: direct distance test (A/B)
-            else if (g_nbw_groups == 1) NBW_LAUNCH(true, 1);
-            else if (g_nbw_groups == 2) NBW_LAUNCH(true, 2);
-            else NBW_LAUNCH(true, 4);
-#undef NBW_LAUNCH
+        MD_CUDA(c, cudaMemsetAsync(s->tl_stats, 0, sizeof(int) * 4, c->stream));
+        k_tile_build<<<md_div_up(no, TL_BLOCK), TL_BLOCK, (size_t)(s->tl_max_nbr + 1) * 2 * TL_BLOCK, c->stream>>>(
+            c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2,
+            rl2s, (float)(rl2s * 2e-5), s->tl_max_nbr, std::min(NBW_RUN, s->nc - 3), s->tl_desc, s->tl_list, s->nbr_cnt, c->d_sc,
+            s->tl_stats);
+        k_peek<<<1, 32, 0, c->stream>>>(s->tl_stats, 1, 3, s->d_cnt_all_mapped + MD_MAXW * MD_MAXW + 4);
+        launches += 2;
+        MD_CUDA(c, cudaStreamSynchronize(c->stream));
+        const volatile int *h = s->h_cnt_all + MD_MAXW * MD_MAXW + 4;
+        if (h[0]) {
+            s->tile_off = true;
+            s->tl_fallbacks += 1;
+        } else {
+            s->tile_active = true;
+            s->tl_win = h[1];
         }
     }
-    launches += 1;
+    if (!s->tile_active) MD_TRY(legacy_list_build(c));
+    c->stats.tile_lists = s->tile_active ? 1 : 0;
+    c->stats.tile_window_max = s->tile_active ? s->tl_win : 0;
+    c->stats.tile_fallbacks = s->tl_fallbacks;
     pt.lap("nbr build");
     MD_CUDA(c, cudaMemsetAsync(&c->d_sc->rebuild_flag, 0, sizeof(int), c->stream));
     md_prof_end(c, &c->stats.ms_rebuild);
@@ -756,8 +826,25 @@ static int rebuild(mdsea_ctx *c) {
 static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded /* guard tag, 0 = unguarded */) {
     CellState *s = c->cells;
     if (i1 <= i0) return MDSEA_OK;
-    const int grid = force_grid(i0, i1);
     const bool lj = c->pot.fast == POTF_LJ;
+    if (s->tile_active) {
+        const double inv_h = fixed_inv_h(c);
+        const PotF32 P = md_pot_f32(c->pot, inv_h);
+        const float  rc2s = (float)(s->rc2 * inv_h * inv_h);
+        const size_t smem = (size_t)((s->tl_win + 63) / 64 * 64) * 16;
+#define TILE_F32(POTK)                                                                                                              \
+    k_tile_force_f32<POTK><<<tile_grid(i0, i1), TL_BLOCK, smem, c->stream>>>((const uint4 *)s->pos4, c->d_r, s->tl_desc, s->tl_list, s->nbr_cnt, \
+                                                                         s->tl_max_nbr / 8, i0 / TL_BLOCK, i0, i1, s->cap, c->box.L, c->box.halfL, \
+                                                                         s->rc2, rc2s, rc2s * 2e-6f, inv_h, P, c->d_acc, c->d_pe_part + pe_off,    \
+                                                                         c->d_sc, guarded)
+        if (lj) TILE_F32(POTF_LJ);
+        else TILE_F32(POTF_MIE);
+#undef TILE_F32
+        MD_CUDA(c, cudaGetLastError());
+        c->stats.kernel_launches += 1;
+        return MDSEA_OK;
+    }
+    const int grid = force_grid(i0, i1);
     if (c->p.precision == MDSEA_FP64) {
         const PotF64 P = md_pot_f64(c->pot);
 #define NBR_F64(POTK)                                                                                                              \
@@ -805,7 +892,7 @@ static int cutoff_force(mdsea_ctx *c, int guarded) {
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
     md_prof_begin(c);
-    c->n_pe_part = force_grid(0, c->n > 0 ? c->n : 1);
+    c->n_pe_part = s->tile_active ? tile_grid(0, c->n > 0 ? c->n : 1) : force_grid(0, c->n > 0 ? c->n : 1);
     MD_TRY(launch_force(c, 0, c->n, 0, guarded));
     md_prof_end(c, &c->stats.ms_force);
     c->stats.force_evals += 1;
@@ -896,8 +983,9 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
         MD_TRY(halo_exchange(c, c->comm_stream));
         k_publish_flag<<<1, 1, 0, c->comm_stream>>>(c->d_sc, s->d_flag_mapped, tag);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
-        const int gi = force_grid(0, s->n_int > 0 ? s->n_int : 1);
-        c->n_pe_part = gi + force_grid(s->n_int, c->n > s->n_int ? c->n : s->n_int + 1);
+        const long long ni1 = s->n_int > 0 ? s->n_int : 1, nb1 = c->n > s->n_int ? c->n : s->n_int + 1;
+        const int gi = s->tile_active ? tile_grid(0, ni1) : force_grid(0, ni1);
+        c->n_pe_part = gi + (s->tile_active ? tile_grid(s->n_int, nb1) : force_grid(s->n_int, nb1));
         MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
         MD_TRY(launch_force(c, 0, s->n_int, 0, tag));                     // guarded by the LOCAL flag only (the global one
                                                                           // is not known yet): redone if any rank fired
@@ -1063,6 +1151,36 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
     for (long long g = 0; g < c->n_global; ++g) offsets[g + 1] = offsets[g] + count_by_id[g];
     *n_entries = offsets[c->n_global];
     if (!idx) return MDSEA_OK;
+    if (s->tile_active) {
+        // the lists the tile force kernel walks: 16-bit window offsets -> window entry -> slot (through the block's ranges) -> id
+        const size_t nblk = (size_t)((n + TL_BLOCK - 1) / TL_BLOCK), max8 = (size_t)(s->tl_max_nbr / 8);
+        const size_t tiles32 = (size_t)((n + 31) / 32);
+        std::vector<TileDesc> desc(nblk > 0 ? nblk : 1);
+        std::vector<unsigned short> lst(tiles32 * max8 * 32 * 8 + 8);
+        MD_CUDA(c, cudaMemcpy(desc.data(), s->tl_desc, sizeof(TileDesc) * nblk, cudaMemcpyDeviceToHost));
+        MD_CUDA(c, cudaMemcpy(lst.data(), s->tl_list, sizeof(uint4) * tiles32 * max8 * 32, cudaMemcpyDeviceToHost));
+        std::vector<int> slot_of;
+        for (size_t b = 0; b < nblk; ++b) {
+            const TileDesc &D = desc[b];
+            slot_of.assign((size_t)D.n_win, -1);
+            for (int k = 0; k < D.n_rng; ++k) {
+                const int lb = D.rng_lb[k], len = (k + 1 < D.n_rng ? D.rng_lb[k + 1] : D.n_win) - lb;
+                for (int e = 0; e < len; ++e) slot_of[(size_t)lb + e] = D.rng_slot[k] + e;
+            }
+            for (long long k = (long long)b * TL_BLOCK; k < std::min<long long>(n, (long long)(b + 1) * TL_BLOCK); ++k) {
+                int32_t *row = idx + offsets[id[k]];
+                const size_t tile = (size_t)(k >> 5), lane = (size_t)(k & 31);
+                for (int m = 0; m < cnt[k]; ++m) {
+                    const unsigned off = lst[((tile * max8 + (size_t)(m >> 3)) * 32 + lane) * 8 + (size_t)(m & 7)];
+                    const int sl = (off >> 4) < (unsigned)D.n_win ? slot_of[off >> 4] : -1;
+                    if (sl < 0) { md_set_error(c, "get_neighbors: tile list entry outside its window"); return MDSEA_ERR_STATE; }
+                    row[m] = id[sl];
+                }
+                std::sort(row, row + cnt[k]);
+            }
+        }
+        return MDSEA_OK;
+    }
     const size_t tiles = (size_t)((n + 31) / 32);
     std::vector<int> nbr(tiles * (size_t)s->max_nbr * 32);
     MD_CUDA(c, cudaMemcpy(nbr.data(), s->nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost));
@@ -1072,5 +1190,21 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
         for (int m = 0; m < cnt[k]; ++m) row[m] = id[nbr[base + md_nbr_off((unsigned)m)]];
         std::sort(row, row + cnt[k]);
     }
+    return MDSEA_OK;
+}
+
+extern "C" int mdsea_b200_get_tile_windows(mdsea_ctx *c, int64_t *n_blocks, int32_t *n_win, int32_t *n_rng) {
+    if (!c || !n_blocks) return MDSEA_ERR_BAD_ARG;
+    if (!c->cutoff_path || !c->have_state) { md_set_error(c, "get_tile_windows: needs the cutoff path and a state"); return MDSEA_ERR_STATE; }
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    CellState *s = c->cells;
+    if (s->need_rebuild) MD_TRY(rebuild(c));
+    const size_t nblk = s->tile_active ? (size_t)((c->n + TL_BLOCK - 1) / TL_BLOCK) : 0;
+    *n_blocks = (int64_t)nblk;
+    if (!nblk || !n_win || !n_rng) return MDSEA_OK;
+    std::vector<TileDesc> desc(nblk);
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    MD_CUDA(c, cudaMemcpy(desc.data(), s->tl_desc, sizeof(TileDesc) * nblk, cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < nblk; ++b) { n_win[b] = desc[b].n_win; n_rng[b] = desc[b].n_rng; }
     return MDSEA_OK;
 }

@@ -76,29 +76,83 @@ def test_cells_on_lattice_and_box_edges():
     ctx.close()
 
 
-@pytest.mark.parametrize("n,L", [(1000, 14.0), (8000, 24.0)])
-def test_neighbor_list_bit_exact_random(n, L):
+# precision 1 = fp32 pair math: the TILE lists (16-bit offsets into per-block windows, cells_tile.cuh) are read back
+# through the same hook, so the list the tile force kernel walks is held to the same bit-exact contract
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("n,L", [(1000, 14.0), (8000, 24.0), (3000, 11.3)])
+def test_neighbor_list_bit_exact_random(n, L, precision):
     r, v = _random(n, L, seed=7 + n)
-    ctx = _ctx(n, L, 1e-3, max_neighbors=256)
+    ctx = _ctx(n, L, 1e-3, max_neighbors=256, precision=precision)
     ctx.set_state(r, v)
     off, idx = ctx.get_neighbors()
     ref_off, ref_idx = oracle_c.neighbors(r, L, RC + SKIN, brute=(n <= 1000))
     np.testing.assert_array_equal(off, ref_off)
     np.testing.assert_array_equal(idx, ref_idx)
+    assert ctx.stats()["tile_lists"] == precision
     ctx.close()
 
 
-def test_neighbor_list_bit_exact_lattice_ties():
+@pytest.mark.parametrize("precision", [0, 1])
+def test_neighbor_list_bit_exact_lattice_ties(precision):
     """On the perfect lattice many pair distances coincide; 0.3 sigma skin puts shells right at the list radius."""
     n, L, r0, v0, dt = _liquid(12, melt_steps=0)
     for skin in (SKIN, 2.0 * L / 12 * np.sqrt(5.0) / 2.0 - RC):  # second value: list radius exactly on a lattice shell
-        ctx = _ctx(n, L, dt, skin=skin, max_neighbors=128)
+        ctx = _ctx(n, L, dt, skin=skin, max_neighbors=128, precision=precision)
         ctx.set_state(r0, v0)
         off, idx = ctx.get_neighbors()
         ref_off, ref_idx = oracle_c.neighbors(r0, L, RC + skin)
         np.testing.assert_array_equal(off, ref_off)
         np.testing.assert_array_equal(idx, ref_idx)
         ctx.close()
+
+
+def test_tile_lists_of_a_melted_liquid_bit_exact_with_window_stats():
+    n, L, r, v, dt = _liquid(20)
+    ctx = _ctx(n, L, dt, precision=1)
+    ctx.set_state(r, v)
+    off, idx = ctx.get_neighbors()
+    ref_off, ref_idx = oracle_c.neighbors(r, L, RC + SKIN)
+    np.testing.assert_array_equal(off, ref_off)
+    np.testing.assert_array_equal(idx, ref_idx)
+    st = ctx.stats()
+    assert st["tile_lists"] == 1 and st["tile_fallbacks"] == 0 and 128 < st["tile_window_max"] <= 4095, st
+    ctx.close()
+
+
+def test_dilute_gas_falls_back_to_the_per_particle_lists():
+    """< 1 particle per cell: a block of 128 slots spans more x-rows of cells than a window holds -> per-particle kernels."""
+    n, L = 1500, 70.0
+    r, v = _random(n, L, seed=3)
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, 1e-3)
+    ref_acc, ref_pe = o.forces()
+    ctx = _ctx(n, L, 1e-3, precision=1)
+    ctx.set_state(r, v)
+    acc, pe = ctx.update_acc()
+    st = ctx.stats()
+    assert st["tile_lists"] == 0 and st["tile_fallbacks"] == 1, st
+    off, idx = ctx.get_neighbors()
+    ref_off, ref_idx = oracle_c.neighbors(r, L, RC + SKIN)
+    np.testing.assert_array_equal(off, ref_off)
+    np.testing.assert_array_equal(idx, ref_idx)
+    ok = np.abs(ref_acc).max(axis=0) < 1e6   # random placement: skip the overlapping pairs whose forces are astronomically large
+    assert np.abs(acc[:, ok] - ref_acc[:, ok]).max() <= 1e-4 * max(1.0, np.abs(ref_acc[:, ok]).max())
+    ctx.close()
+    o.close()
+
+
+def test_fp32_per_particle_lists_when_the_tile_path_is_switched_off(monkeypatch):
+    monkeypatch.setenv("MDSEA_TILE", "0")
+    n, L, r, v, dt = _liquid(12)
+    o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref_acc, ref_pe = o.forces()
+    ctx = _ctx(n, L, dt, precision=1)
+    ctx.set_state(r, v)
+    acc, pe = ctx.update_acc()
+    assert ctx.stats()["tile_lists"] == 0
+    assert abs(pe - ref_pe) <= 1e-5 * abs(ref_pe)
+    assert force_rel_err(acc, ref_acc) <= 1e-4
+    ctx.close()
+    o.close()
 
 
 @pytest.mark.parametrize("precision", [0, 1])
@@ -168,6 +222,10 @@ def test_fp32_run_matches_oracle():
     np.testing.assert_allclose(ke, ref["ke"], rtol=1e-5)
     assert np.abs(rows2["r"][-1] - ref["r"][-1]).max() <= 1e-3
     assert np.abs(rows2["v"][-1] - ref["v"][-1]).max() <= 1e-3
+    # same rebuild schedule as the oracle, and the tile lists in force at the end are the oracle's, entry for entry
+    # (positions differ by ~1e-6 after 100 fp32 steps; a pair within that of the list radius would show up here)
+    st = ctx.stats()
+    assert st["tile_lists"] == 1 and st["list_rebuilds"] == o.counters()["rebuilds"]
     ctx.close()
     o.close()
 
