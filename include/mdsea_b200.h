@@ -156,6 +156,13 @@ int mdsea_b200_generate_state(mdsea_ctx *ctx, const double *speed_cdf, int64_t n
                               int32_t isotropic, double *mean_speed);
 /* time step of the following run calls (simulator.py:86-87 derives it from the initial velocities) */
 int mdsea_b200_set_dt(mdsea_ctx *ctx, double dt);
+/* replaces self.apply_bc() = apply_pbc / apply_hbc (mdsea/simulator.py:90,156-179) applied to the state on the device:
+ * periodic: the strict one-shot wrap (x < 0 -> x + L, x > L -> x - L); hard walls: clamp to [radius, L - radius] and
+ * v *= -restitution for the entries that crossed.  The next force evaluation sees the moved positions. */
+int mdsea_b200_apply_bc(mdsea_ctx *ctx);
+/* replaces the `com` and `rog` properties (mdsea/simulator.py:207-231): com[ndim] = mean position, *rog = sqrt(mean |r - com|^2)
+ * (separations folded with rint(d / L) when the box is periodic).  Single-rank contexts. */
+int mdsea_b200_com_rog(mdsea_ctx *ctx, double *com, double *rog);
 /* download of r_vec, v_vec, acc in original particle order; any pointer may be NULL.
  * With world > 1 each rank fills only the entries of particles it owns (others untouched)
  * and returns their ids in `owned_ids` (capacity N, may be NULL) / count in *n_owned. */

@@ -62,7 +62,7 @@ EXPORTS = [
     "mdsea_b200_get_stats", "mdsea_b200_first_nonfinite_step", "mdsea_b200_set_profiling", "mdsea_b200_stream",
     "mdsea_b200_nccl_unique_id", "mdsea_b200_comm_init", "mdsea_b200_comm_init_local", "mdsea_b200_rank_capacity",
     "mdsea_b200_measure_fma_peak", "mdsea_b200_analyse_speeds", "mdsea_b200_generate_state", "mdsea_b200_set_dt",
-    "mdsea_b200_get_tile_windows",
+    "mdsea_b200_get_tile_windows", "mdsea_b200_apply_bc", "mdsea_b200_com_rog",
 ]
 
 _lib = None
@@ -98,6 +98,8 @@ def load():
     lib.mdsea_b200_get_neighbors.argtypes = [vp, i64p, vp, vp]
     lib.mdsea_b200_generate_state.argtypes = [vp, vp, C.c_int64, C.c_double, C.c_uint64, i32, dp]
     lib.mdsea_b200_set_dt.argtypes = [vp, C.c_double]
+    lib.mdsea_b200_apply_bc.argtypes = [vp]
+    lib.mdsea_b200_com_rog.argtypes = [vp, vp, dp]
     lib.mdsea_b200_set_temperature.argtypes = [vp, C.c_double, i32]
     lib.mdsea_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mdsea_b200_first_nonfinite_step.argtypes = [vp, i64p]
@@ -200,6 +202,15 @@ class Context:
 
     def set_dt(self, dt):
         self._ck(self.lib.mdsea_b200_set_dt(self.h, float(dt)))
+
+    def apply_bc(self):
+        self._ck(self.lib.mdsea_b200_apply_bc(self.h))
+
+    def com_rog(self):
+        com = np.empty(self.ndim)
+        rog = C.c_double(0.0)
+        self._ck(self.lib.mdsea_b200_com_rog(self.h, _ptr(com), C.byref(rog)))
+        return com, float(rog.value)
 
     def set_temperature(self, temp, reset_ke=True):
         self._ck(self.lib.mdsea_b200_set_temperature(self.h, float(temp), 1 if reset_ke else 0))

@@ -281,6 +281,31 @@ extern "C" int mdsea_b200_generate_state(mdsea_ctx *c, const double *speed_cdf, 
     return md_generate_state(c, speed_cdf, (long long)n_cdf, speed_step, (unsigned long long)seed, isotropic ? 1 : 0, mean_speed);
 }
 
+// self.apply_bc() (simulator.py:90,156-179) on the device state: the strict one-shot wrap when periodic, clamp + reflect
+// with the restitution coefficient otherwise
+extern "C" int mdsea_b200_apply_bc(mdsea_ctx *c) {
+    if (!c) return MDSEA_ERR_BAD_ARG;
+    if (!c->have_state) return bad(c, "apply_bc: no state (call set_state first)");
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    MD_TRY(wait_all(c));
+    if (c->cutoff_path) MD_TRY(md_cutoff_apply_bc(c));
+    else MD_TRY(md_apply_bc(c));
+    MD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->acc_valid = false;
+    return MDSEA_OK;
+}
+
+// com / rog (simulator.py:208-231) of the particles on this rank
+extern "C" int mdsea_b200_com_rog(mdsea_ctx *c, double *com, double *rog) {
+    if (!c || !com || !rog) return bad(c, "com_rog: NULL argument");
+    if (!c->have_state) return bad(c, "com_rog: no state (call set_state first)");
+    if (c->p.world > 1) return bad(c, "com_rog: single-rank contexts only");
+    MD_CUDA(c, cudaSetDevice(c->p.device));
+    MD_TRY(wait_all(c));
+    const size_t stride = c->cutoff_path ? (size_t)md_cutoff_capacity(c) : (size_t)c->n;
+    return md_com_rog(c, c->d_r, c->n, stride, com, rog);
+}
+
 extern "C" int mdsea_b200_set_dt(mdsea_ctx *c, double dt) {
     if (!c) return MDSEA_ERR_BAD_ARG;
     if (!isfinite(dt)) return bad(c, "set_dt: dt must be finite");

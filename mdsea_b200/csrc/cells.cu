@@ -156,7 +156,9 @@ struct CellState {
     int     published_tag = 0;            // single GPU: the fused finish kernel already published this tag's trigger (h_flag[2 + (tag & 1)])
     // tile path (cells_tile.cuh): fp32 pair math, windows in shared memory, 16-bit window offsets as list entries
     bool    tile_ok = false;              // available: fp32 mode, >= 4 cells per dimension, not switched off (MDSEA_TILE=0)
-    bool    tile_active = false;          // the CURRENT list generation is in tile format
+    bool    tile_active = false;          // the CURRENT list generation has tile lists for the owned slots [0, tile_n)
+    long long tile_n = 0;                 // single GPU: all of them; world > 1: the whole blocks of INTERIOR slots (the boundary
+                                          // class -- faces of the domain, many short runs of cells per block -- keeps the per-particle lists)
     bool    tile_off = false;             // a block's window did not fit: per-particle kernels until the next set_state
     struct TileDesc *tl_desc = nullptr;   // [ceil(cap / 128)]
     uint4  *tl_list = nullptr;            // [cap / 32][tl_max_nbr / 8][32] vectors of 8 16-bit window offsets
@@ -684,22 +686,23 @@ struct PhaseTimer {  // debugging aid: wall-clock per rebuild phase (synchronise
 
 // per-particle 32-bit Verlet lists (k_nbr_build_warp / k_nbr_build): fp64 mode, < 4 cells per dimension, MDSEA_TILE=0, and
 // list generations whose tile windows did not fit.  The list itself is allocated on first use.
-static int legacy_list_build(mdsea_ctx *c) {
+static int legacy_list_build(mdsea_ctx *c, long long i_first) {
     CellState *s = c->cells;
+    if (i_first >= c->n && c->n > 0) return MDSEA_OK;
     if (!s->nbr) MD_CUDA(c, cudaMalloc(&s->nbr, sizeof(int) * (size_t)s->max_nbr * (size_t)s->n_pad));
     {
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
         const float lo = (float)(rl2s * (1.0 - 2e-5)), hi = (float)(rl2s * (1.0 + 2e-5));
-        const long long no = c->n > 0 ? c->n : 1;
+        const long long no = c->n > i_first ? c->n - i_first : 1;
         if (g_build_thread || s->nc < 4)
             k_nbr_build<<<md_div_up(no, NB_THREADS), NB_THREADS, 0, c->stream>>>(
-                c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
+                c->d_r, s->qfix, i_first, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->rl2, lo, hi,
                 s->max_nbr, s->nbr, s->nbr_cnt, c->d_sc);
         else {
 #define NBW_LAUNCH(EXP, G)                                                                                                          \
     k_nbr_build_warp<EXP, G><<<md_div_up(no, NBW_WARPS * 32), NBW_WARPS * 32, 0, c->stream>>>(                                     \
-        c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
+        c->d_r, s->qfix, i_first, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2, \
         rl2s, (float)(rl2s * 2e-5), lo, hi, s->max_nbr, std::min(NBW_RUN, s->nc - 3), s->nbr, s->nbr_cnt, c->d_sc)
             if (!(g_nbw_variant & 1)) NBW_LAUNCH(false, 4);   // MDSEA_NBW_VARIANT=0: direct distance test (A/B)
             else if (g_nbw_groups == 1) NBW_LAUNCH(true, 1);
@@ -786,14 +789,15 @@ static int rebuild(mdsea_ctx *c) {
     if (W > 1) MD_TRY(build_halo_lists(c));
     pt.lap("halo lists");
     s->tile_active = false;
-    if (s->tile_ok && !s->tile_off) {
+    s->tile_n = 0;
+    const long long tile_target = !(s->tile_ok && !s->tile_off) ? 0 : (W == 1 ? c->n : (s->n_int / TL_BLOCK) * TL_BLOCK);
+    if (tile_target > 0) {
         // tile lists + windows; the build reports (mapped memory, one host sync per rebuild) whether every block's window fit
         const double ih = fixed_inv_h(c);
         const double rl2s = s->rl2 * ih * ih;
-        const long long no = c->n > 0 ? c->n : 1;
         MD_CUDA(c, cudaMemsetAsync(s->tl_stats, 0, sizeof(int) * 4, c->stream));
-        k_tile_build<<<md_div_up(no, TL_BLOCK), TL_BLOCK, (size_t)(s->tl_max_nbr + 1) * 2 * TL_BLOCK, c->stream>>>(
-            c->d_r, s->qfix, c->n, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2,
+        k_tile_build<<<md_div_up(tile_target, TL_BLOCK), TL_BLOCK, (size_t)(s->tl_max_nbr + 1) * 2 * TL_BLOCK, c->stream>>>(
+            c->d_r, s->qfix, tile_target, s->cap, s->cell, s->cell_start, s->cell_end, s->nc, c->box.L, c->box.halfL, s->cell_len, ih, s->rl2,
             rl2s, (float)(rl2s * 2e-5), s->tl_max_nbr, std::min(NBW_RUN, s->nc - 3), s->tl_desc, s->tl_list, s->nbr_cnt, c->d_sc,
             s->tl_stats);
         k_peek<<<1, 32, 0, c->stream>>>(s->tl_stats, 1, 3, s->d_cnt_all_mapped + MD_MAXW * MD_MAXW + 4);
@@ -805,10 +809,11 @@ static int rebuild(mdsea_ctx *c) {
             s->tl_fallbacks += 1;
         } else {
             s->tile_active = true;
+            s->tile_n = tile_target;
             s->tl_win = h[1];
         }
     }
-    if (!s->tile_active) MD_TRY(legacy_list_build(c));
+    MD_TRY(legacy_list_build(c, s->tile_n));   // the owned slots the tile lists do not cover (all of them after a fallback)
     c->stats.tile_lists = s->tile_active ? 1 : 0;
     c->stats.tile_window_max = s->tile_active ? s->tl_win : 0;
     c->stats.tile_fallbacks = s->tl_fallbacks;
@@ -823,18 +828,31 @@ static int rebuild(mdsea_ctx *c) {
 }
 
 // force kernel over the owned slots [i0, i1); its per-block PE partials go to pe_part[pe_off ...]
+// number of PE partials (= blocks) of the force launches over the owned slots [i0, i1): tile blocks for the part below
+// tile_n, per-particle blocks for the rest
+static inline int force_parts(const CellState *s, long long i0, long long i1) {
+    if (i1 <= i0) return 0;
+    const long long t1 = s->tile_active ? std::min(i1, s->tile_n) : i0;
+    int g = 0;
+    if (t1 > i0) g += tile_grid(i0, t1);
+    const long long l0 = std::max(i0, s->tile_active ? s->tile_n : i0);
+    if (i1 > l0) g += force_grid(l0, i1);
+    return g;
+}
+
 static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded /* guard tag, 0 = unguarded */) {
     CellState *s = c->cells;
     if (i1 <= i0) return MDSEA_OK;
     const bool lj = c->pot.fast == POTF_LJ;
-    if (s->tile_active) {
+    if (s->tile_active && i0 < s->tile_n) {
+        const long long t1 = std::min(i1, s->tile_n);
         const double inv_h = fixed_inv_h(c);
         const PotF32 P = md_pot_f32(c->pot, inv_h);
         const float  rc2s = (float)(s->rc2 * inv_h * inv_h);
         const size_t smem = (size_t)((s->tl_win + 63) / 64 * 64) * 16;
 #define TILE_F32(POTK)                                                                                                              \
-    k_tile_force_f32<POTK><<<tile_grid(i0, i1), TL_BLOCK, smem, c->stream>>>((const uint4 *)s->pos4, c->d_r, s->tl_desc, s->tl_list, s->nbr_cnt, \
-                                                                         s->tl_max_nbr / 8, i0 / TL_BLOCK, i0, i1, s->cap, c->box.L, c->box.halfL, \
+    k_tile_force_f32<POTK><<<tile_grid(i0, t1), TL_BLOCK, smem, c->stream>>>((const uint4 *)s->pos4, c->d_r, s->tl_desc, s->tl_list, s->nbr_cnt, \
+                                                                         s->tl_max_nbr / 8, i0 / TL_BLOCK, i0, t1, s->cap, c->box.L, c->box.halfL, \
                                                                          s->rc2, rc2s, rc2s * 2e-6f, inv_h, P, c->d_acc, c->d_pe_part + pe_off,    \
                                                                          c->d_sc, guarded)
         if (lj) TILE_F32(POTF_LJ);
@@ -842,7 +860,9 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
 #undef TILE_F32
         MD_CUDA(c, cudaGetLastError());
         c->stats.kernel_launches += 1;
-        return MDSEA_OK;
+        if (i1 <= t1) return MDSEA_OK;
+        pe_off += tile_grid(i0, t1);
+        i0 = t1;
     }
     const int grid = force_grid(i0, i1);
     if (c->p.precision == MDSEA_FP64) {
@@ -892,7 +912,7 @@ static int cutoff_force(mdsea_ctx *c, int guarded) {
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
     md_prof_begin(c);
-    c->n_pe_part = s->tile_active ? tile_grid(0, c->n > 0 ? c->n : 1) : force_grid(0, c->n > 0 ? c->n : 1);
+    c->n_pe_part = force_parts(s, 0, c->n > 0 ? c->n : 1);
     MD_TRY(launch_force(c, 0, c->n, 0, guarded));
     md_prof_end(c, &c->stats.ms_force);
     c->stats.force_evals += 1;
@@ -984,8 +1004,8 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
         k_publish_flag<<<1, 1, 0, c->comm_stream>>>(c->d_sc, s->d_flag_mapped, tag);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
         const long long ni1 = s->n_int > 0 ? s->n_int : 1, nb1 = c->n > s->n_int ? c->n : s->n_int + 1;
-        const int gi = s->tile_active ? tile_grid(0, ni1) : force_grid(0, ni1);
-        c->n_pe_part = gi + (s->tile_active ? tile_grid(s->n_int, nb1) : force_grid(s->n_int, nb1));
+        const int gi = force_parts(s, 0, ni1);
+        c->n_pe_part = gi + force_parts(s, s->n_int, nb1);
         MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
         MD_TRY(launch_force(c, 0, s->n_int, 0, tag));                     // guarded by the LOCAL flag only (the global one
                                                                           // is not known yet): redone if any rank fired
@@ -1078,6 +1098,14 @@ int md_cutoff_copy_rows(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows 
 int md_cutoff_finish_rows(mdsea_ctx *c) { return MDSEA_OK; }
 long long md_cutoff_capacity(mdsea_ctx *c) { return c->cells ? c->cells->cap : 0; }
 
+// apply_bc (simulator.py:156-179) on the slots this rank holds; positions moved, so the next force evaluation rebuilds
+int md_cutoff_apply_bc(mdsea_ctx *c) {
+    CellState *s = c->cells;
+    for (int d = 0; d < 3; ++d) MD_TRY(md_apply_bc_range(c, c->d_r + (size_t)d * s->cap, c->d_v + (size_t)d * s->cap, (size_t)c->n));
+    s->need_rebuild = true;
+    return MDSEA_OK;
+}
+
 int md_cutoff_get_state(mdsea_ctx *c, double *r, double *v, double *a, int64_t *ids, int64_t *n_owned) {
     CellState *s = c->cells;
     const long long n = c->n, N = c->n_global;
@@ -1151,10 +1179,11 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
     for (long long g = 0; g < c->n_global; ++g) offsets[g + 1] = offsets[g] + count_by_id[g];
     *n_entries = offsets[c->n_global];
     if (!idx) return MDSEA_OK;
-    if (s->tile_active) {
+    const long long n_tile = s->tile_active ? s->tile_n : 0;
+    if (n_tile > 0) {
         // the lists the tile force kernel walks: 16-bit window offsets -> window entry -> slot (through the block's ranges) -> id
-        const size_t nblk = (size_t)((n + TL_BLOCK - 1) / TL_BLOCK), max8 = (size_t)(s->tl_max_nbr / 8);
-        const size_t tiles32 = (size_t)((n + 31) / 32);
+        const size_t nblk = (size_t)((n_tile + TL_BLOCK - 1) / TL_BLOCK), max8 = (size_t)(s->tl_max_nbr / 8);
+        const size_t tiles32 = (size_t)((n_tile + 31) / 32);
         std::vector<TileDesc> desc(nblk > 0 ? nblk : 1);
         std::vector<unsigned short> lst(tiles32 * max8 * 32 * 8 + 8);
         MD_CUDA(c, cudaMemcpy(desc.data(), s->tl_desc, sizeof(TileDesc) * nblk, cudaMemcpyDeviceToHost));
@@ -1167,7 +1196,7 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
                 const int lb = D.rng_lb[k], len = (k + 1 < D.n_rng ? D.rng_lb[k + 1] : D.n_win) - lb;
                 for (int e = 0; e < len; ++e) slot_of[(size_t)lb + e] = D.rng_slot[k] + e;
             }
-            for (long long k = (long long)b * TL_BLOCK; k < std::min<long long>(n, (long long)(b + 1) * TL_BLOCK); ++k) {
+            for (long long k = (long long)b * TL_BLOCK; k < std::min<long long>(n_tile, (long long)(b + 1) * TL_BLOCK); ++k) {
                 int32_t *row = idx + offsets[id[k]];
                 const size_t tile = (size_t)(k >> 5), lane = (size_t)(k & 31);
                 for (int m = 0; m < cnt[k]; ++m) {
@@ -1179,12 +1208,12 @@ extern "C" int mdsea_b200_get_neighbors(mdsea_ctx *c, int64_t *n_entries, int64_
                 std::sort(row, row + cnt[k]);
             }
         }
-        return MDSEA_OK;
+        if (n_tile >= n) return MDSEA_OK;
     }
     const size_t tiles = (size_t)((n + 31) / 32);
     std::vector<int> nbr(tiles * (size_t)s->max_nbr * 32);
     MD_CUDA(c, cudaMemcpy(nbr.data(), s->nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost));
-    for (long long k = 0; k < n; ++k) {
+    for (long long k = n_tile; k < n; ++k) {
         int32_t *row = idx + offsets[id[k]];
         const size_t base = md_nbr_row_base(k, s->max_nbr);
         for (int m = 0; m < cnt[k]; ++m) row[m] = id[nbr[base + md_nbr_off((unsigned)m)]];
@@ -1199,7 +1228,7 @@ extern "C" int mdsea_b200_get_tile_windows(mdsea_ctx *c, int64_t *n_blocks, int3
     MD_CUDA(c, cudaSetDevice(c->p.device));
     CellState *s = c->cells;
     if (s->need_rebuild) MD_TRY(rebuild(c));
-    const size_t nblk = s->tile_active ? (size_t)((c->n + TL_BLOCK - 1) / TL_BLOCK) : 0;
+    const size_t nblk = s->tile_active ? (size_t)((s->tile_n + TL_BLOCK - 1) / TL_BLOCK) : 0;
     *n_blocks = (int64_t)nblk;
     if (!nblk || !n_win || !n_rng) return MDSEA_OK;
     std::vector<TileDesc> desc(nblk);

@@ -98,11 +98,11 @@ __device__ __forceinline__ int nb_particle(long long i, const uint4 qi, int c, c
 }
 
 __global__ void __launch_bounds__(NB_THREADS)
-k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
+k_nbr_build(const double *__restrict__ r, const uint4 *__restrict__ q, long long i_first, long long n_own, long long cap,
             const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
             double L, double halfL, double rl2, float rl2s_lo, float rl2s_hi, int max_nbr, int *__restrict__ nbr,
             int *__restrict__ nbr_cnt, StepScalars *__restrict__ sc) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = i_first + (long long)blockIdx.x * blockDim.x + threadIdx.x;   // lists of the owned slots [i_first, n_own)
     if (i >= n_own) return;
     const uint4 qi = q[i];
     const int c = cell[i];
@@ -191,14 +191,14 @@ __device__ __forceinline__ void nbw_append_now(unsigned m, int base, unsigned lo
 
 template <bool EXPANDED, int NBW_G>
 __global__ void __launch_bounds__(NBW_WARPS * 32, 9)
-k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long n_own, long long cap,
+k_nbr_build_warp(const double *__restrict__ r, const uint4 *__restrict__ q, long long i_first /* multiple of 32 */, long long n_own, long long cap,
                  const int *__restrict__ cell, const int *__restrict__ cell_start, const int *__restrict__ cell_end, int nc,
                  double L, double halfL, double cell_len, double inv_h, double rl2, double rl2s_d, float bw, float rl2s_lo,
                  float rl2s_hi, int max_nbr, int run_max, int *__restrict__ nbr, int *__restrict__ nbr_cnt,
                  StepScalars *__restrict__ sc) {
     __shared__ float4 s_cand[NBW_WARPS][NBW_G][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long i0 = ((long long)blockIdx.x * NBW_WARPS + w) * 32;
+    const long long i0 = i_first + ((long long)blockIdx.x * NBW_WARPS + w) * 32;
     if (i0 >= n_own) return;   // whole warp out of range (only __syncwarp below)
     const long long i = i0 + lane;
     const bool valid = i < n_own;

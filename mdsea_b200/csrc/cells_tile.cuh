@@ -30,9 +30,10 @@
 #define TL_WARPS 4
 #define TL_MAXRUN 8         // runs per block
 #define TL_ROWC 16          // cells per (run, stencil row) incl. the two flanking cells: runs of <= 14 cells
-#define TL_MAXRNG 96        // contiguous slot ranges per window
+#define TL_MAXRNG 128       // contiguous slot ranges per window (<= TL_BLOCK: one thread copies one range descriptor)
 #define TL_WIN_MAX 4095     // window entries (16-bit byte offsets)
 #define TL_TAB (TL_MAXRUN * 9 * TL_ROWC)
+#define TL_MAXCHK 96        // chunks of <= 32 candidates per pass of the build
 
 struct TileDesc {           // window of one block: written by k_tile_build, read by the force kernel every step
     int n_rng;
@@ -111,13 +112,14 @@ k_tile_build(const double *__restrict__ r, const uint4 *__restrict__ q, long lon
              StepScalars *__restrict__ sc, int *__restrict__ tile_stats) {
     extern __shared__ unsigned short s_rows[];                 // [max_nbr + 1][TL_BLOCK]
     __shared__ float4 s_cand[TL_WARPS][32];
+    __shared__ int   s_chk[TL_WARPS][2 * TL_MAXCHK];
     __shared__ int   s_cell[TL_BLOCK];
     __shared__ int   s_aux[TL_BLOCK];
     __shared__ unsigned char s_brk[TL_BLOCK + 1];
     __shared__ int   s_w[TL_WARPS + 1];
     __shared__ int   run_cxa[TL_MAXRUN], run_cxb[TL_MAXRUN], run_cy[TL_MAXRUN], run_cz[TL_MAXRUN], run_ncx[TL_MAXRUN];
     __shared__ int   tab_cs[TL_TAB];
-    __shared__ int   tab_lb[TL_TAB];
+    __shared__ unsigned short tab_lb[TL_TAB];   // window indices (<= TL_WIN_MAX)
     __shared__ unsigned short tab_n[TL_TAB];
     __shared__ int   s_bad;
 
@@ -205,7 +207,7 @@ k_tile_build(const double *__restrict__ r, const uint4 *__restrict__ q, long lon
     for (int k = 0; k < per; ++k) {
         const int e = tid * per + k;
         if (e >= E) break;
-        tab_lb[e] = base;
+        tab_lb[e] = (unsigned short)min(base, 65535);
         base += tab_n[e];
     }
     __syncthreads();
@@ -249,6 +251,7 @@ k_tile_build(const double *__restrict__ r, const uint4 *__restrict__ q, long lon
     const long long il = valid ? i : n_own - 1;
     const uint4 qi = q[il];
     float4 *cand = s_cand[w];
+    int *chk = s_chk[w];
     unsigned short *const wrow = s_rows + tid;
     const unsigned wb0 = 2u * (unsigned)tid, wsink = wb0 + 2u * TL_BLOCK * (unsigned)max_nbr;
     unsigned wb = wb0;
@@ -269,23 +272,16 @@ k_tile_build(const double *__restrict__ r, const uint4 *__restrict__ q, long lon
         const float xi = (float)(int)(qi.x - ox), yi = (float)(int)(qi.y - oy), zi = (float)(int)(qi.z - oz);
         const float px2 = -2.0f * xi, py2 = -2.0f * yi, pz2 = -2.0f * zi;
         const float kp = (float)(fma((double)xi, (double)xi, fma((double)yi, (double)yi, (double)zi * (double)zi)) - rl2s_d + (double)bw);
-        // one chunk of <= 32 candidates at slots [b0, b0 + 32) /\ [.., re), window index lw of slot b0
-        auto do_range = [&](int rs, int re, int lb) {
+        // chunk list of the pass: (first slot, window index of it << 6 | candidates) per chunk of <= 32 candidates, recorded
+        // by the (warp-uniform) walk over the 9 stencil rows, then processed with the NEXT chunk's candidates already in flight
+        int nchk = 0;
+        auto add_range = [&](int rs, int re, int lb) {
             for (int b0 = rs; b0 < re; b0 += 32) {
-                const int jj = b0 + lane;
-                float4 cd = nbw_dummy<true>();
-                if (jj < re) cd = nbw_stage<true>(q[jj], ox, oy, oz);
-                __syncwarp();
-                cand[lane] = cd;
-                __syncwarp();
-                unsigned bb = 0x7f800000u;
-                int nbits;
-                unsigned m = tl_test_chunk(cand, min(32, re - b0), px2, py2, pz2, kp, bb, nbits);
-                if (mine) bandbits = min(bandbits, bb);
-                else m = 0u;
-                const long long self = i - b0;
-                if (self >= 0 && self < nbits) m &= ~(1u << (nbits - 1 - (int)self));
-                tl_append(m, nbits, lb + (b0 - rs), s_rows, wb, wsink);
+                if (nchk < TL_MAXCHK && lane == 0) {
+                    chk[2 * nchk] = b0;
+                    chk[2 * nchk + 1] = ((lb + (b0 - rs)) << 6) | min(32, re - b0);
+                }
+                ++nchk;
             }
         };
         for (int rho = 0; rho < 9; ++rho) {
@@ -298,7 +294,7 @@ k_tile_build(const double *__restrict__ r, const uint4 *__restrict__ q, long lon
                     const int sf = tab_cs[tb + t0], lf = tab_lb[tb + t0];
                     const int sspan = tab_cs[tb + tl] + nl - sf, lspan = tab_lb[tb + tl] + nl - lf;
                     if (nf > 0 && nl > 0 && sspan == lspan) {
-                        do_range(sf, sf + sspan, lf);
+                        add_range(sf, sf + sspan, lf);
                         continue;
                     }
                 }
@@ -315,10 +311,35 @@ k_tile_build(const double *__restrict__ r, const uint4 *__restrict__ q, long lon
                     if (n1 == 0) continue;
                     if (re > rs && s1 == re && l1 == lb + (re - rs)) { re += n1; continue; }   // contiguous in slots and in the window
                 }
-                do_range(rs, re, lb);
+                add_range(rs, re, lb);
                 rs = s1; re = s1 + n1; lb = l1;
             }
         }
+        if (nchk > TL_MAXCHK) {   // uniform; cannot happen at liquid densities (<= 9 rows x 7 chunks)
+            if (lane == 0) atomicExch(&tile_stats[0], 1);
+            nchk = TL_MAXCHK;
+        }
+        __syncwarp();
+        uint4 qn = make_uint4(0u, 0u, 0u, 0u);
+        if (nchk > 0 && lane < (chk[1] & 63)) qn = q[chk[0] + lane];
+        for (int ck = 0; ck < nchk; ++ck) {
+            const int b0 = chk[2 * ck], pk = chk[2 * ck + 1], nc_ = pk & 63, lw = pk >> 6;
+            float4 cd = nbw_dummy<true>();
+            if (lane < nc_) cd = nbw_stage<true>(qn, ox, oy, oz);
+            if (ck + 1 < nchk && lane < (chk[2 * ck + 3] & 63)) qn = q[chk[2 * ck + 2] + lane];   // next chunk's candidates
+            __syncwarp();
+            cand[lane] = cd;
+            __syncwarp();
+            unsigned bb = 0x7f800000u;
+            int nbits;
+            unsigned m = tl_test_chunk(cand, nc_, px2, py2, pz2, kp, bb, nbits);
+            if (mine) bandbits = min(bandbits, bb);
+            else m = 0u;
+            const long long self = i - b0;
+            if (self >= 0 && self < nbits) m &= ~(1u << (nbits - 1 - (int)self));
+            tl_append(m, nbits, lw, s_rows, wb, wsink);
+        }
+        __syncwarp();   // the chunk list is rewritten by the next pass
     }
     // ---- a candidate sat in the guard band: canonical float64 redo of that particle by the whole warp, over its own
     //      three cells of every stencil row (the same canonical set, in the same order)
@@ -452,13 +473,16 @@ k_tile_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, 
     unsigned cnt = 0;
     if (act) {
         const char  *__restrict__ wb = (const char *)s_win;
-        const float neg_bw = -bw;
+        const float rc2m = rc2s - bw;        // t' = r^2 - (rc^2 - bw): pair certainly inside <=> t' < 0 (sign bit); band <=> 0 <= t' <= 2 bw
+        const unsigned band_hi = __float_as_uint(2.0f * bw);
         const float c8 = P.c / P.sigma2_s;   // LJ: s = t8 * (c8 - 2 c8 t6)
         const float m2c8 = -2.0f * c8;
         float fx = 0.f, fy = 0.f, fz = 0.f, pe = 0.f;
+        const uint4 *__restrict__ lp = lrow;
         for (int k8 = 0; k8 < nn8; ++k8) {
             const uint4 e = e_next;
-            if (k8 + 1 < nn8) e_next = __ldcs(lrow + (size_t)(k8 + 1) * 32u);   // next group's vector: in flight during this group's arithmetic
+            lp += 32;
+            if (k8 + 1 < nn8) e_next = __ldcs(lp);   // next group's vector: in flight during this group's arithmetic
             unsigned off[8];
             off[0] = e.x & 0xffffu; off[1] = e.x >> 16;
             off[2] = e.y & 0xffffu; off[3] = e.y >> 16;
@@ -467,17 +491,18 @@ k_tile_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, 
             uint4 qj[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) qj[u] = *(const uint4 *)(wb + off[u]);
-            float tmin = 3.0e38f;
+            unsigned tb = 0x7f800000u;   // smallest non-negative t' of the group (unsigned compare: negative floats are larger)
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float dx = (float)(int)(qj[u].x - qi.x), dy = (float)(int)(qj[u].y - qi.y), dz = (float)(int)(qj[u].z - qi.z);
                 const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, __uint_as_float(qj[u].w))));
-                const float t = r2 - rc2s;
-                const bool  ok = t < neg_bw;
-                tmin = fminf(tmin, fabsf(t));
+                const unsigned tp = __float_as_uint(r2 - rc2m);
+                const int okm = (int)tp >> 31;          // all ones iff inside
+                tb = min(tb, tp);
                 float s, uu;
                 if (POTK == POTF_LJ) {
-                    const float inv = md_rcpf(ok ? r2 : __int_as_float(0x7f800000));
+                    // r^2 if inside, +inf otherwise (rcp -> 0: no force, no energy): one LOP3
+                    const float inv = md_rcpf(__uint_as_float((__float_as_uint(r2) & (unsigned)okm) | (~(unsigned)okm & 0x7f800000u)));
                     const float t2 = P.sigma2_s * inv;
                     const float t4 = t2 * t2;
                     const float t6 = t4 * t2;
@@ -485,20 +510,20 @@ k_tile_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, 
                     s = t8 * fmaf(m2c8, t6, c8);
                     uu = fmaf(t6, t6, -t6);
                 } else {
-                    md_pair<POTK>(r2, ok, P, s, uu);
+                    md_pair<POTK>(r2, okm != 0, P, s, uu);
                 }
                 fx = fmaf(dx, s, fx);
                 fy = fmaf(dy, s, fy);
                 fz = fmaf(dz, s, fz);
                 pe += uu;
-                cnt += ok ? 1u : 0u;
+                cnt -= (unsigned)okm;
             }
-            if (__builtin_expect(tmin <= bw, 0)) {   // rare: decide and evaluate the band pairs from the float64 positions
+            if (__builtin_expect(tb <= band_hi, 0)) {   // rare: decide and evaluate the band pairs from the float64 positions
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {   // unrolled: off[] / qj[] stay in registers
                     const float dxs = (float)(int)(qj[u].x - qi.x), dys = (float)(int)(qj[u].y - qi.y), dzs = (float)(int)(qj[u].z - qi.z);
                     const float r2s = fmaf(dzs, dzs, fmaf(dys, dys, fmaf(dxs, dxs, __uint_as_float(qj[u].w))));
-                    if (!(fabsf(r2s - rc2s) <= bw)) continue;
+                    if (__float_as_uint(r2s - rc2m) > band_hi) continue;
                     const int jj = tl_slot_of((int)(off[u] >> 4), s_slot, s_lb, nr);
                     const double ex = md_minimg_list(r64[jj] - r64[i], L, halfL);
                     const double ey = md_minimg_list(r64[cap + jj] - r64[cap + i], L, halfL);
@@ -517,7 +542,7 @@ k_tile_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, 
                     }
                 }
             }
-            if (k8 & 1) {   // fp32 partial sums of 16 entries are folded into the float64 accumulators
+            if ((k8 & 3) == 3) {   // fp32 partial sums of 32 entries are folded into the float64 accumulators
                 Fx += (double)fx; Fy += (double)fy; Fz += (double)fz; PE += (double)pe;
                 fx = fy = fz = pe = 0.f;
             }

@@ -88,6 +88,8 @@ int md_allpairs_setup(mdsea_ctx *c);
 int md_allpairs_force(mdsea_ctx *c);          // fills d_fpart / d_pe_part / d_cnt_part from d_r
 // integrate.cu
 int md_apply_bc(mdsea_ctx *c);
+int md_apply_bc_range(mdsea_ctx *c, double *r, double *v, size_t E);
+int md_com_rog(mdsea_ctx *c, const double *r, long long n, size_t stride, double *com, double *rog);
 int md_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, const double *fsrc, int nparts, size_t stride);
 struct FinalizeArgs;
 int md_kick_finish(mdsea_ctx *c, const double *fsrc, int nparts, size_t stride, int row, int record, double g_dt,
@@ -103,3 +105,4 @@ void md_cells_free(mdsea_ctx *c);
 int md_cutoff_force(mdsea_ctx *c);            // rebuilds the list when flagged, then forces
 int md_cutoff_copy_rows(mdsea_ctx *c, const mdsea_run_args *a, const mdsea_rows *rows);
 long long md_cutoff_capacity(mdsea_ctx *c);
+int md_cutoff_apply_bc(mdsea_ctx *c);

@@ -176,6 +176,80 @@ int md_apply_bc(mdsea_ctx *c) {
     return MDSEA_OK;
 }
 
+// the same boundary condition over E entries of arbitrary arrays (the cut-off path keeps one padded row per dimension)
+int md_apply_bc_range(mdsea_ctx *c, double *r, double *v, size_t E) {
+    if (E == 0) return MDSEA_OK;
+    k_apply_bc<<<md_div_up((long long)E, IG_THREADS), IG_THREADS, 0, c->stream>>>(r, v, E, c->box.pbc, c->box.L, c->p.radius,
+                                                                                   c->p.restitution);
+    c->stats.kernel_launches += 1;
+    MD_CUDA(c, cudaGetLastError());
+    return MDSEA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// centre of mass and radius of gyration (simulator.py:208-231): com = mean(r) per dimension, rog^2 = mean |r - com|^2,
+// with the rint image of the separation when periodic.  Two passes of block sums, reduced in a fixed order.
+// ---------------------------------------------------------------------------------------------
+#define ROG_BLOCKS 256
+__global__ void __launch_bounds__(256)
+k_com_part(const double *__restrict__ r, long long n, size_t stride, int ndim, double *__restrict__ part /* [ndim][ROG_BLOCKS] */) {
+    __shared__ double red[32];
+    for (int d = 0; d < ndim; ++d) {
+        double s = 0.0;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            s += r[(size_t)d * stride + i];
+        s = md_block_sum(s, red);
+        if (threadIdx.x == 0) part[d * ROG_BLOCKS + blockIdx.x] = s;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rog_part(const double *__restrict__ r, long long n, size_t stride, int ndim, const double *__restrict__ part, int pbc, double L,
+           double *__restrict__ out /* [ROG_BLOCKS] */, double *__restrict__ com_out /* [ndim] */) {
+    __shared__ double red[32];
+    __shared__ double com[3];
+    if (threadIdx.x < ndim) {
+        double s = 0.0;
+        for (int b = 0; b < ROG_BLOCKS; ++b) s += part[threadIdx.x * ROG_BLOCKS + b];
+        com[threadIdx.x] = s / (double)n;
+        if (blockIdx.x == 0) com_out[threadIdx.x] = com[threadIdx.x];
+    }
+    __syncthreads();
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double q = 0.0;
+        for (int d = 0; d < ndim; ++d) {
+            double x = r[(size_t)d * stride + i] - com[d];
+            if (pbc) x -= rint(x / L) * L;
+            q = fma(x, x, q);
+        }
+        s += q;
+    }
+    s = md_block_sum(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+int md_com_rog(mdsea_ctx *c, const double *r, long long n, size_t stride, double *com, double *rog) {
+    double *d_tmp = nullptr;
+    const size_t words = (size_t)(3 + 1) * ROG_BLOCKS + 3;
+    MD_CUDA(c, cudaMalloc(&d_tmp, sizeof(double) * words));
+    double *d_part = d_tmp, *d_out = d_tmp + 3 * ROG_BLOCKS, *d_com = d_out + ROG_BLOCKS;
+    k_com_part<<<ROG_BLOCKS, 256, 0, c->stream>>>(r, n, stride, c->ndim, d_part);
+    k_rog_part<<<ROG_BLOCKS, 256, 0, c->stream>>>(r, n, stride, c->ndim, d_part, c->box.pbc, c->box.L, d_out, d_com);
+    c->stats.kernel_launches += 2;
+    double h[ROG_BLOCKS + 3];
+    cudaError_t e = cudaMemcpyAsync(h, d_out, sizeof(double) * (ROG_BLOCKS + 3), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_tmp);
+    MD_CUDA(c, e);
+    double s = 0.0;
+    for (int b = 0; b < ROG_BLOCKS; ++b) s += h[b];
+    for (int d = 0; d < c->ndim; ++d) com[d] = h[ROG_BLOCKS + d];
+    *rog = sqrt(s / (double)n);
+    return MDSEA_OK;
+}
+
 int md_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, const double *fsrc, int nparts, size_t stride) {
     double *acc_out = (do_kick && fsrc != c->d_acc) ? c->d_acc : nullptr;
     md_prof_begin(c);

@@ -302,10 +302,89 @@ class _BaseSimulator:
 
     @property
     def com(self):
+        """Centre of mass (simulator.py:207-213), reduced on the device; None (with the reference's warning) when periodic."""
         if self.sm.PBC:
             log.warning("COM computation not available for PBC yet!")
             return
-        return np.mean(self.r_vec, axis=1)
+        if self._world > 1:
+            return np.mean(self.r_vec, axis=1)
+        return self._sync_to_device().com_rog()[0]
+
+    @property
+    def rog(self) -> float:
+        """Radius of gyration: root-mean-square distance to the centre of mass (simulator.py:215-231), on the device."""
+        if self.sm.PBC:
+            # the reference subtracts `self.com` (None for periodic boxes) from the positions: same TypeError here
+            raise TypeError("unsupported operand type(s) for -: 'float' and 'NoneType'")
+        if self._world > 1:
+            d = np.stack(self.r_vec, axis=-1) - self.com
+            return float(np.sqrt(np.mean(quicker.norm(d, axis=1) ** 2)))
+        return self._sync_to_device().com_rog()[1]
+
+    # -- boundary conditions, special events, fields as callable steps (simulator.py:156-205) -----------------
+    def _apply_bc_device(self) -> None:
+        ctx = self._sync_to_device()
+        ctx.apply_bc()
+        self._device_fresh = True
+
+    def apply_pbc(self) -> None:
+        """One-shot strict wrap (simulator.py:156-166).  On the device when the box is periodic."""
+        if self.sm.PBC:
+            return self._apply_bc_device()
+        r, L = self.r_vec, self.sm.LEN_BOX
+        r[np.where(r < 0)] += L
+        r[np.where(r > L)] -= L
+
+    def apply_hbc(self) -> None:
+        """Clamp to the walls and reflect with the restitution coefficient (simulator.py:168-179).  On the device when
+        the box has hard walls."""
+        if not self.sm.PBC:
+            return self._apply_bc_device()
+        r, v, L, a = self.r_vec, self.v_vec, self.sm.LEN_BOX, self.sm.RADIUS_PARTICLE
+        whr = np.where(r - a < 0)
+        r[whr] = a
+        v[whr] *= -self.restitution_coeff
+        whr = np.where(r + a > L)
+        r[whr] = L - a
+        v[whr] *= -self.restitution_coeff
+
+    def apply_bc(self) -> None:
+        """``apply_pbc if sm.PBC else apply_hbc`` (simulator.py:90)."""
+        self._apply_bc_device()
+
+    def apply_special(self) -> None:
+        """Isothermal rescale and scheduled quenches of the current step (simulator.py:185-190)."""
+        if self.isothermal:
+            self._quench(self.temp_init)
+        if self.step in self.sm.QUENCH_STEP:
+            self._quench(self.sm.QUENCH_T.pop(0))
+
+    def _quench(self, temperature: float) -> None:
+        self.update_temp()   # simulator.py:192-195
+        if self.temp != 0.0:
+            self.v_vec *= (temperature / self.temp) ** 0.5
+
+    def apply_field(self) -> None:
+        if self.gravity:     # simulator.py:201-205
+            self.v_vec[-1] -= Config.gravity_acceleration * self.dt
+
+    # -- the pair table (simulator.py:122-137): built on first use, O(N^2) like the reference's ------------
+    @property
+    def all_pairs(self) -> np.ndarray:
+        if getattr(self, "_all_pairs", None) is None:
+            i, j = np.triu_indices(self.sm.NUM_PARTICLES, k=1)   # itertools.combinations order
+            self._all_pairs = np.stack([i, j], axis=1).astype(np.int32)
+        return self._all_pairs
+
+    @property
+    def pairs(self) -> np.ndarray:
+        """Pairs selected by the last update_dists / update_pairs call (simulator.py:313-316)."""
+        return self.all_pairs[self.pairs_indexes]
+
+    def update_pairs(self, radius: Optional[float] = None, where: str = "inside"):
+        """Pairs within (or outside) a radius with their distances and unit vectors (simulator.py:318-323)."""
+        self.update_dists(radius=radius, where=where)
+        return zip(self.all_pairs[self.pairs_indexes], self.dists, self.drunits)
 
 
 @dataclass

@@ -197,3 +197,70 @@ def test_analyser_speed_statistics_on_device(in_tmp_cwd):  # noqa: F811
         assert abs(mean - ref.mean()) <= 1e-12 * ref.mean() and abs(std - ref.std()) <= 1e-11 * ref.std() and mx == ref.max()
         _, mean2, _, _ = _capi.analyse_speeds(v, want_speeds=False)
         assert mean2 == mean
+
+
+def test_boundary_and_pair_methods_of_the_base_simulator(in_tmp_cwd):  # noqa: F811
+    """apply_bc / apply_pbc / apply_hbc, _quench, apply_field, com, rog, pairs, update_pairs as callable methods
+    (mdsea/simulator.py:90,156-231,313-323), each against the NumPy statement of the reference lines."""
+    from mdsea_b200 import quicker
+    from mdsea_b200.config import Config, config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    with config_context(k_boltzmann=1.0):
+        # hard walls: clamp + reflect on the device, com / rog reduced on the device
+        sm = SysManager.new(simid="w", ndim=3, num_particles=27, steps=5, vol_fraction=0.1, radius_particle=0.5, pbc=False, temp=1)
+        np.random.seed(3)
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), restitution_coeff=1.0, gravity=True)
+        L, a = sm.LEN_BOX, sm.RADIUS_PARTICLE
+        r = sim.r_vec.copy()
+        v = sim.v_vec.copy()
+        r[0, :3] = [-0.2, L + 0.3, 0.1]
+        r[2, 5] = L - 0.1
+        sim.r_vec = r
+        er, ev = r.copy(), v.copy()
+        whr = np.where(er - a < 0); er[whr] = a; ev[whr] *= -1.0
+        whr = np.where(er + a > L); er[whr] = L - a; ev[whr] *= -1.0
+        sim.apply_bc()
+        np.testing.assert_array_equal(sim.r_vec, er)
+        np.testing.assert_array_equal(sim.v_vec, ev)
+        sim.apply_hbc()   # idempotent once inside
+        np.testing.assert_array_equal(sim.r_vec, er)
+        com = sim.com
+        np.testing.assert_allclose(com, er.mean(axis=1), rtol=1e-13)
+        d = np.stack(er, axis=-1) - er.mean(axis=1)
+        np.testing.assert_allclose(sim.rog, np.sqrt(np.mean(quicker.norm(d, axis=1) ** 2)), rtol=1e-13)
+        vz = sim.v_vec[-1].copy()
+        sim.apply_field()
+        np.testing.assert_allclose(sim.v_vec[-1], vz - Config.gravity_acceleration * sim.dt, rtol=0, atol=0)
+        # pairs within a radius: combinations order, the table built on first use
+        pr = list(sim.update_pairs(radius=2.0))
+        assert sim.all_pairs.shape == (27 * 26 // 2, 2) and tuple(sim.all_pairs[0]) == (0, 1) and tuple(sim.all_pairs[-1]) == (25, 26)
+        assert len(pr) == len(sim.pairs) == int(sim.pairs_indexes.sum()) > 0
+        (i, j), dist, unit = pr[0]
+        rr = sim.r_vec
+        assert dist == pytest.approx(np.linalg.norm(rr[:, j] - rr[:, i]), rel=1e-12) and dist < 2.0
+        # _quench: v *= sqrt(T / temp) with temp from the current mean kinetic energy
+        sim.update_mean_ke()
+        v0 = sim.v_vec.copy()
+        sim._quench(0.25)
+        t_now = (2 / 3) * 0.5 * sm.MASS * float((v0 * v0).sum(axis=0).mean())
+        np.testing.assert_allclose(sim.v_vec, v0 * (0.25 / t_now) ** 0.5, rtol=1e-14)
+
+        # periodic: strict one-shot wrap on the device; rog has no centre of mass to refer to (TypeError like the reference)
+        sm = SysManager.new(simid="p", ndim=2, num_particles=36, steps=5, vol_fraction=0.2, radius_particle=0.5)
+        np.random.seed(4)
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1))
+        L = sm.LEN_BOX
+        r = sim.r_vec.copy()
+        r[0, :4] = [-0.5, L + 0.25, 2.5 * L, -1.5 * L]
+        sim.r_vec = r
+        er = r.copy()
+        er[np.where(er < 0)] += L
+        er[np.where(er > L)] -= L
+        sim.apply_pbc()
+        np.testing.assert_array_equal(sim.r_vec, er)
+        assert sim.com is None
+        with pytest.raises(TypeError):
+            sim.rog

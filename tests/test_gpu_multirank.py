@@ -141,6 +141,29 @@ def test_decomposed_fp32_reuse_mode():
     o.close()
 
 
+@pytest.mark.parametrize("world,grid", [(2, (2, 1, 1)), (8, (2, 2, 2))])
+def test_decomposed_fp32_lists_bit_exact(world, grid):
+    """fp32 pair math with world > 1: tile lists for the whole blocks of interior slots, per-particle lists for the rest
+    (domain faces).  One step from a melted state: the lists in force are those of the initial positions.  32^3 particles
+    (13 cells per dimension) so that every rank has interior cells to tile."""
+    n, L, r, v, dt = _liquid(32, melt_steps=20)
+    out = _run_ranks(world, grid, n, L, dt, r, v, 1, precision=1, evals=1, batch=1, want_lists=True)
+    ref_off, ref_idx = oracle_c.neighbors(r, L, RC + SKIN)
+    seen = np.zeros(n, dtype=int)
+    for res in out:
+        assert res["stats"]["list_rebuilds"] == 1
+        assert res["stats"]["tile_lists"] == 1 and res["stats"]["tile_fallbacks"] == 0, res["stats"]
+        cell_of, order, nc = res["cells"]
+        off, idx = res["nbrs"]
+        owned = np.where(cell_of >= 0)[0]
+        seen[owned] += 1
+        cnt = np.diff(off)
+        np.testing.assert_array_equal(cnt[owned], np.diff(ref_off)[owned])
+        mine = np.repeat(cell_of >= 0, np.diff(ref_off))
+        np.testing.assert_array_equal(idx, ref_idx[mine])
+    assert np.all(seen == 1)
+
+
 def test_uneven_blocks_and_lattice_start():
     """nc not divisible by the process grid (blocks of different widths) and a perfect-lattice start."""
     n, L, r, v, dt = _liquid(14, melt_steps=0)   # L = 16.86 -> nc = 6 with 2 ranks in x... and 3 along z: widths 2,2,2
