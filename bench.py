@@ -28,6 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_UNIQUE_PAIR = {3: 45.0, 2: 34.0, 1: 23.0}
+# CUDA-core FMA peak from the data sheet: 148 SMs x 128 fp32 (64 fp64) lanes x 2 flop x 1.965 GHz boost
+DATASHEET_TFLOPS = {"fp32": 148 * 128 * 2 * 1.965e9 / 1e12, "fp64": 148 * 64 * 2 * 1.965e9 / 1e12}
 
 WORKLOADS = {
     # configs[1] of BASELINE.json: 3-D LJ fluid, 4096 particles, vf 0.3, all-pairs tiled kernel
@@ -157,6 +159,89 @@ def run_reference_arm(args, wl):
 
 
 # ---------------------------------------------------------------------------------------------------
+# parity of the benched configuration itself: the same state advanced k steps by the library and by the C oracle
+# (oracle/lj_oracle.c -- the checker, never the thing measured)
+# ---------------------------------------------------------------------------------------------------
+_H1, _H2 = np.uint64(0x9E3779B97F4A7C15), np.uint64(0xC2B2AE3D27D4EB4F)
+
+
+def row_hashes(off, idx, n):
+    """One 64-bit hash per particle of its (ascending) neighbour row: sum of per-entry hashes + a length term."""
+    cnt = np.diff(off).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        e = (idx.astype(np.uint64) + np.uint64(1)) * _H1
+        e ^= e >> np.uint64(29)
+        e *= _H2
+        cs = np.concatenate([[np.uint64(0)], np.cumsum(e, dtype=np.uint64)])
+        h = cs[off[1:]] - cs[off[:-1]] + cnt * _H2
+    return h
+
+
+def parity_allpairs(ctx, wl, L, dt, r_start, v_start, k, precision):
+    """All-pairs workloads: k steps from (r_start, v_start) against the NumPy float64 restatement of the reference."""
+    from oracle.oracle_np import MiePotential, OracleSolver
+
+    tol = 1e-10 if precision == "fp64" else 1e-5
+    rows = dict(r=None, v=None, pe=np.empty(k), ke=np.empty(k), temp=np.empty(k))
+    ctx.set_state(r_start, v_start)
+    ctx.run(k, kb=1.0, record=True, rows=rows)
+    ref = OracleSolver(r=np.array(r_start), v=np.array(v_start), boxlen=L, dt=dt, pot=MiePotential()).run(k)
+    pe_rel = float(np.max(np.abs(rows["pe"] - ref["pe"]) / np.abs(ref["pe"])))
+    ke_rel = float(np.max(np.abs(rows["ke"] - ref["ke"]) / np.abs(ref["ke"])))
+    return {"steps": k, "tolerance": tol, "pe_rel": pe_rel, "ke_rel": ke_rel, "oracle": "oracle/oracle_np.py (float64)",
+            "ok": bool(pe_rel <= tol and ke_rel <= tol)}
+
+
+def parity_check(ctx, wl, n, L, dt, r_start, v_start, k, precision, rank, world, dist, torch):
+    """Advance (r_start, v_start) k steps on the GPU path under test and on the C oracle; energies per step, the number of
+    list rebuilds and the neighbour lists in force at the end must agree (lists bit for bit)."""
+    import zlib
+
+    tol = 1e-10 if precision == "fp64" else 1e-5
+    rows = dict(r=None, v=None, pe=np.empty(k), ke=np.empty(k), temp=np.empty(k))
+    ctx.set_state(r_start, v_start)
+    s0 = ctx.stats()
+    ctx.run(k, kb=1.0, record=True, rows=rows)
+    s1 = ctx.stats()
+    off, idx = ctx.get_neighbors()
+    h = row_hashes(off, idx, n)
+    if world > 1:   # every rank holds the rows of the particles it owns
+        t = torch.from_numpy(h.view(np.int64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h = t.cpu().numpy().view(np.uint64)
+        ne = torch.tensor([idx.shape[0]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+        n_entries = int(ne.item())
+    else:
+        n_entries = int(idx.shape[0])
+    if rank != 0:
+        return None
+    from oracle import oracle_c
+
+    t0 = time.perf_counter()
+    o = oracle_c.CutoffSystem(r_start, v_start, L, wl["r_cutoff"], wl["skin"], dt)
+    ref = o.run(k)
+    oc = o.counters()
+    ref_off, ref_idx = o.neighbor_list()
+    o.close()
+    t_oracle = time.perf_counter() - t0
+    ref_h = row_hashes(ref_off, ref_idx, n)
+    pe_rel = float(np.max(np.abs(rows["pe"] - ref["pe"]) / np.abs(ref["pe"])))
+    ke_rel = float(np.max(np.abs(rows["ke"] - ref["ke"]) / np.abs(ref["ke"])))
+    lists_equal = bool(n_entries == ref_idx.shape[0] and np.array_equal(h, ref_h))
+    if world == 1:
+        lists_equal = lists_equal and bool(np.array_equal(off, ref_off) and np.array_equal(idx, ref_idx))
+    reb = int(s1["list_rebuilds"] - s0["list_rebuilds"])
+    out = {"steps": k, "tolerance": tol, "pe_rel": pe_rel, "ke_rel": ke_rel, "list_equal": lists_equal,
+           "list_entries": n_entries, "list_crc32_oracle": zlib.crc32(ref_idx.tobytes()),
+           "list_checksum_equal": lists_equal, "rebuilds": reb, "rebuilds_oracle": oc["rebuilds"],
+           "rebuilds_equal": reb == oc["rebuilds"], "oracle": "oracle/lj_oracle.c (float64, cell + Verlet list, same trigger)",
+           "oracle_seconds": t_oracle}
+    out["ok"] = bool(pe_rel <= tol and ke_rel <= tol and lists_equal and out["rebuilds_equal"])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def make_ctx(wl, n, L, dt, device, precision, ring, rank=0, world=1, proc_grid=(1, 1, 1), evals=1):
@@ -172,12 +257,15 @@ def run_ours(args, wl):
     import torch
     import torch.distributed as dist
 
-    from mdsea_b200 import _capi
+    from mdsea_b200 import _capi, parallel
 
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # host side of the row traffic: this rank's pinned buffers live on the NUMA node of its GPU
+    all_cpus = os.sched_getaffinity(0)
+    numa = None if os.environ.get("MDSEA_NO_NUMA_BIND") else parallel.bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     precision = args.precision or wl["precision"]
@@ -256,6 +344,18 @@ def run_ours(args, wl):
     fevals = s1["force_evals"] - s0["force_evals"]
     t_dev = sum(ms) * 1e-3
     energy_ok = bool(np.isfinite(rows["pe"]).all() and np.isfinite(rows["ke"]).all())
+
+    # the state the timed region ended in (a melted liquid after (warmup + steps) * md_steps timesteps): input of the e2e
+    # batches, of the roofline sample and of the parity check below.  Decomposed runs: every rank owns a part of it.
+    r_cur, v_cur, _, _ = ctx.get_state(want_acc=False)
+    if decomposed:
+        for a in (r_cur, v_cur):
+            t = torch.from_numpy(np.nan_to_num(a, nan=0.0)).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            a[:] = t.cpu().numpy()
+            del t
+    r_pin[:], v_pin[:] = r_cur, v_cur
+    del r_cur, v_cur
 
     # ---------------- end to end through the C ABI with host buffers ----------------
     # Every step: upload the batch's initial (r, v) from pinned memory, run md_steps, copy every dataset row of the
@@ -346,6 +446,17 @@ def run_ours(args, wl):
                     "traffic": ncu_traffic("r01_ncu_c3_kernels.txt", "k_cut_kick_finish<1>") if wl is WORKLOADS.get("c3") and not fp64 else None,
                     "bytes_per_launch": integ_bytes, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
 
+    os.sched_setaffinity(0, all_cpus)   # the CPU legs below (oracle, cpu_baseline) use every host core
+    # ---------------- parity of this very configuration against the CPU oracle ----------------
+    parity = None
+    if not args.no_parity:
+        if wl["r_cutoff"] > 0:
+            parity = parity_check(ctx, wl, n, L, dt, r_pin, v_pin, 10 if world == 1 else 6, precision, rank, world, dist, torch)
+        elif rank == 0:
+            parity = parity_allpairs(ctx, wl, L, dt, r_pin, v_pin, 3, precision)
+    transport = {0: "single GPU", 1: "p2p (CUDA IPC stores over NVLink + arrival counters; NCCL for control collectives)",
+                 2: "nccl (ncclSend/ncclRecv)", 3: "in-process"}[int(ctx.stats().get("halo_transport", 0))]
+
     # ---------------- aggregate over ranks ----------------
     t_dev_max, t_e2e_max, tot_pairs, tot_e2e_pairs = t_dev, t_e2e, pairs, e2e_pairs
     if world > 1:
@@ -386,6 +497,8 @@ def run_ours(args, wl):
             "e2e": {"value": tot_e2e_pairs / t_e2e_max, "unit": "pair-interactions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "timesteps_per_s": (1 if decomposed else world) * args.steps * md_steps / t_e2e_max,
                     "ms_per_step": 1e3 * t_e2e_max / args.steps,
+                    "d2h_gbs_per_rank": d2h / (t_e2e_max / args.steps) / 1e9, "host_numa_binding": numa,
+                    "input": "the current (melted) state is uploaded from pinned memory before every batch",
                     "pipeline": "2 batches in flight (run_async/wait): D2H of step s overlaps the compute of step s+1; "
                                 "wall clock over all K steps incl. the final drain; no L2 flush (working set >> L2)"},
             "gpu_launches": int(launches),
@@ -396,8 +509,12 @@ def run_ours(args, wl):
                          "flop_per_unique_pair": FLOP_PER_UNIQUE_PAIR[ndim], "unique_pairs_per_launch": f_pairs,
                          "ms_per_launch": f_ms,
                          "peak_source": "FMA micro-benchmark of the CUDA-core pipe measured in this run "
-                                        "(MEASURED_PEAKS.json has no CUDA-core FP peak)"},
+                                        "(MEASURED_PEAKS.json has no CUDA-core FP peak)",
+                         "peak_datasheet": DATASHEET_TFLOPS["fp64" if fp64 else "fp32"],
+                         "frac_of_datasheet": achieved_tf / DATASHEET_TFLOPS["fp64" if fp64 else "fp32"],
+                         "sample_state": "melted liquid: the state the timed region ended in"},
             "roofline_hbm": roof_hbm,
+            "parity": parity, "transport": transport,
             "cpu_baseline": cpu, "clocks": clocks, "energies_finite": energy_ok,
             "allpairs_configs1": extra,
             "host_wall_s_timed_region": t_wall,
@@ -406,6 +523,8 @@ def run_ours(args, wl):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: parity against the CPU oracle FAILED: " + json.dumps(parity))
 
 
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -486,6 +605,7 @@ def main():
     ap.add_argument("--md-steps", type=int, default=None, help="MD timesteps per bench step (one C-ABI run call)")
     ap.add_argument("--evals", type=int, default=1, choices=[1, 2], help="force evaluations per MD step (2 = reference-faithful)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the benched configuration")
     ap.add_argument("--no-extra", action="store_true", help="skip the additional all-pairs (configs[1]) measurement at N=1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -130,6 +130,10 @@ typedef struct {
     int64_t tile_lists;
     int64_t tile_window_max;     /* largest window of the current list generation, entries of 16 bytes        */
     int64_t tile_fallbacks;      /* list generations that fell back to the per-particle lists (window did not fit) */
+    /* data plane of the domain decomposition: 0 = single rank, 1 = peer memory (CUDA IPC stores over NVLink + arrival
+     * counters), 2 = ncclSend/ncclRecv (MDSEA_HALO=nccl, or a peer mapping failed on some rank: reported on stderr),
+     * 3 = in-process (host threads on one GPU, tests) */
+    int64_t halo_transport;
 } mdsea_stats;
 
 const char *mdsea_b200_version(void);

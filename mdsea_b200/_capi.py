@@ -49,7 +49,8 @@ class Stats(C.Structure):
                 ("pair_evals_executed", C.c_int64), ("kernel_launches", C.c_int64), ("list_rebuilds", C.c_int64),
                 ("n_local", C.c_int64), ("n_ghost", C.c_int64), ("nbr_entries", C.c_int64),
                 ("ms_force", C.c_double), ("ms_integrate", C.c_double), ("ms_rebuild", C.c_double), ("ms_comm", C.c_double),
-                ("tile_lists", C.c_int64), ("tile_window_max", C.c_int64), ("tile_fallbacks", C.c_int64)]
+                ("tile_lists", C.c_int64), ("tile_window_max", C.c_int64), ("tile_fallbacks", C.c_int64),
+                ("halo_transport", C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -590,7 +590,9 @@ static int build_halo_lists(mdsea_ctx *c) {
 // failure (peer access impossible, MDSEA_HALO=nccl) leaves the ncclSend/ncclRecv path in place, on all ranks alike.
 int md_cells_comm_ready(mdsea_ctx *c) {
     CellState *s = c->cells;
-    if (!s || c->p.world < 2 || md_comm_backend(c) != 1) return MDSEA_OK;
+    if (!s || c->p.world < 2) return MDSEA_OK;
+    c->stats.halo_transport = md_comm_backend(c) == 1 ? 2 : 3;
+    if (md_comm_backend(c) != 1) return MDSEA_OK;
     if (getenv("MDSEA_HALO") && !strcmp(getenv("MDSEA_HALO"), "nccl")) return MDSEA_OK;
     s->p2p_stride = 3 * s->cap + MD_MAXW;
     s->seg_cap = s->cap;   // worst case: everything a rank owns arrives from ONE source (first rebuild after set_state)
@@ -602,9 +604,15 @@ int md_cells_comm_ready(mdsea_ctx *c) {
     MD_CUDA(c, cudaMemset(s->p2p_buf, 0, s->inbox_off));
     MD_CUDA(c, cudaMalloc(&s->d_roff, sizeof(int) * (MD_MAXW + 2)));
     const int st = md_comm_share_buffer(c, s->p2p_buf, (void **)s->peer_buf);
-    if (st == MDSEA_ERR_UNSUPPORTED) return MDSEA_OK;   // keep NCCL send/recv
+    if (st == MDSEA_ERR_UNSUPPORTED) {   // keep NCCL send/recv -- never silently: the peer-memory path is the fast one
+        if (c->p.rank == 0)
+            fprintf(stderr, "mdsea_b200: a rank could not map a peer's buffer (CUDA IPC); the halo and rebuild traffic falls back to "
+                            "ncclSend/ncclRecv on all ranks\n");
+        return MDSEA_OK;
+    }
     if (st != MDSEA_OK) return st;
     s->p2p = true;
+    c->stats.halo_transport = 1;
     return MDSEA_OK;
 }
 

@@ -29,6 +29,45 @@ def dist_info() -> Tuple[int, int]:
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device: int, sysfs: str = "/sys/bus/pci/devices") -> Optional[dict]:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function).
+    Pinned host buffers allocated afterwards are first-touched -- and therefore placed -- on that node, so the D2H row
+    traffic of N ranks does not cross the socket interconnect or pile up on one node's memory controllers.  Returns
+    {"pci": ..., "numa_node": ..., "cpus": n} or None when the topology cannot be read (no change then)."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device)
+        pci = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = os.path.join(sysfs, pci)
+        with open(os.path.join(base, "local_cpulist")) as f:
+            cpus = _parse_cpulist(f.read())
+        node = -1
+        try:
+            with open(os.path.join(base, "numa_node")) as f:
+                node = int(f.read().strip())
+        except OSError:
+            pass
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return {"pci": pci, "numa_node": node, "cpus": len(allowed), "changed": False}
+        os.sched_setaffinity(0, cpus)
+        return {"pci": pci, "numa_node": node, "cpus": len(cpus), "changed": True}
+    except Exception:
+        return None
+
+
 def choose_proc_grid(world: int, ncells: Optional[int] = None) -> Tuple[int, int, int]:
     """Most cubic factorisation px*py*pz == world with px >= py >= pz (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2).
     `ncells` (cells per box edge) bounds every factor: a rank needs at least one cell per dimension."""
