@@ -44,7 +44,11 @@ WORKLOADS = {
                           "(BASELINE configs[3], weak scaling)"),
 }
 
-PROC_GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# x (the contiguous index of the cell grid) is never split: see mdsea_b200.parallel.choose_proc_grid
+PROC_GRIDS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
+if os.environ.get("MDSEA_PROC_GRID"):   # A/B: e.g. MDSEA_PROC_GRID=2,2,2
+    _g = tuple(int(x) for x in os.environ["MDSEA_PROC_GRID"].split(","))
+    PROC_GRIDS[_g[0] * _g[1] * _g[2]] = _g
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -611,6 +615,10 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     wl = WORKLOADS[args.workload]
+    # a hung collective must not hold the box: dump every thread's Python stack and exit after MDSEA_BENCH_WATCHDOG seconds
+    import faulthandler
+
+    faulthandler.dump_traceback_later(float(os.environ.get("MDSEA_BENCH_WATCHDOG", "1500")), exit=True)
     if args.impl == "reference":
         run_reference_arm(args, wl)
     else:

@@ -157,8 +157,8 @@ struct CellState {
     // tile path (cells_tile.cuh): fp32 pair math, windows in shared memory, 16-bit window offsets as list entries
     bool    tile_ok = false;              // available: fp32 mode, >= 4 cells per dimension, not switched off (MDSEA_TILE=0)
     bool    tile_active = false;          // the CURRENT list generation has tile lists for the owned slots [0, tile_n)
-    long long tile_n = 0;                 // single GPU: all of them; world > 1: the whole blocks of INTERIOR slots (the boundary
-                                          // class -- faces of the domain, many short runs of cells per block -- keeps the per-particle lists)
+    long long tile_n = 0;                 // all of them unless the process grid splits x: then the whole blocks of INTERIOR slots (the
+                                          // boundary class -- faces that cut the x-rows, many short runs per block -- keeps the per-particle lists)
     bool    tile_off = false;             // a block's window did not fit: per-particle kernels until the next set_state
     struct TileDesc *tl_desc = nullptr;   // [ceil(cap / 128)]
     uint4  *tl_list = nullptr;            // [cap / 32][tl_max_nbr / 8][32] vectors of 8 16-bit window offsets
@@ -798,7 +798,11 @@ static int rebuild(mdsea_ctx *c) {
     pt.lap("halo lists");
     s->tile_active = false;
     s->tile_n = 0;
-    const long long tile_target = !(s->tile_ok && !s->tile_off) ? 0 : (W == 1 ? c->n : (s->n_int / TL_BLOCK) * TL_BLOCK);
+    // world > 1: when x is not split (the default grids) every owned slot gets a tile list -- the domain faces are whole
+    // x-rows of cells; faces that cut the rows (p[0] > 1) leave many short runs per block, so there only the whole blocks of
+    // interior slots are tiled and the rest keeps the per-particle lists
+    const long long tile_target = !(s->tile_ok && !s->tile_off) ? 0
+                                  : ((W == 1 || s->D.p[0] == 1) ? c->n : (s->n_int / TL_BLOCK) * TL_BLOCK);
     if (tile_target > 0) {
         // tile lists + windows; the build reports (mapped memory, one host sync per rebuild) whether every block's window fit
         const double ih = fixed_inv_h(c);

@@ -438,8 +438,15 @@ k_tile_force_f32(const uint4 *__restrict__ pos, const double *__restrict__ r64, 
     __shared__ int      s_lb[TL_MAXRNG + 1];
     __shared__ double   red[32];
     __shared__ unsigned redu[32];
-    if (guard_tag && sc->rebuild_flag == guard_tag) return;  // speculative launch: the list is stale, the host will redo this step
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // speculative launch: if the skin trigger of the drift this launch follows has fired, the list is stale and the host
+    // will redo the step.  The decision must be BLOCK-UNIFORM: with world > 1 the flag can flip while the kernel runs (the
+    // halo unpack on the communication stream merges the neighbours' flags), and the threads of a block depend on each other
+    // here (window staging, range tables) -- a block that half-returned would gather through unwritten range descriptors.
+    __shared__ int s_skip;
+    if (tid == 0) s_skip = guard_tag && *(volatile const int *)&sc->rebuild_flag == guard_tag;
+    __syncthreads();
+    if (s_skip) return;
     const long long b = blk0 + blockIdx.x;
     const TileDesc *__restrict__ D = desc + b;
     const int nr = D->n_rng, nw = D->n_win;

@@ -69,8 +69,13 @@ def bind_to_gpu_numa(device: int, sysfs: str = "/sys/bus/pci/devices") -> Option
 
 
 def choose_proc_grid(world: int, ncells: Optional[int] = None) -> Tuple[int, int, int]:
-    """Most cubic factorisation px*py*pz == world with px >= py >= pz (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2).
-    `ncells` (cells per box edge) bounds every factor: a rank needs at least one cell per dimension."""
+    """Process grid (px, py, pz) with px*py*pz == world for the spatial decomposition of the cell grid.
+
+    x is the fastest-running cell index: particles of an x-row of cells are contiguous in memory and the list kernels
+    stream whole rows.  The grid therefore splits y and z and leaves x whole (1 -> 1x1x1, 2 -> 1x1x2, 4 -> 1x2x2,
+    8 -> 1x2x4: at 8 ranks the halo surface equals that of 2x2x2, with 5 instead of 7 distinct neighbour ranks and no faces
+    that cut the rows), choosing the most square py <= pz.  x is split only if y and z alone cannot hold `world`
+    (`ncells`, cells per box edge, bounds every factor: a rank needs at least one cell per dimension)."""
     best = None
     for px in range(1, world + 1):
         if world % px:
@@ -79,11 +84,11 @@ def choose_proc_grid(world: int, ncells: Optional[int] = None) -> Tuple[int, int
             if (world // px) % py:
                 continue
             pz = world // px // py
-            if not (px >= py >= pz):
+            if py > pz:
                 continue
-            if ncells is not None and px > ncells:
+            if ncells is not None and max(px, py, pz) > ncells:
                 continue
-            score = (px - pz, px)
+            score = (px, pz - py)
             if best is None or score < best[0]:
                 best = (score, (px, py, pz))
     if best is None:

@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from mdsea_b200 import _capi  # noqa: E402
+from mdsea_b200.parallel import choose_proc_grid  # noqa: E402
 from oracle import oracle_c  # noqa: E402
 from test_gpu_cutoff import RC, SKIN, _liquid  # noqa: E402
 
@@ -24,6 +25,9 @@ GRIDS = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
 def main():
+    import faulthandler
+
+    faulthandler.dump_traceback_later(240, exit=True)   # a hung collective must not hold the box
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -80,6 +84,41 @@ def main():
             print(f"NCCL domain decomposition check OK: world={world} evals={evals} quench={quench} rebuilds={st['list_rebuilds']} "
                   f"n_local={st['n_local']} n_ghost={st['n_ghost']}", flush=True)
         ctx.close()
+    # fp32 pair math on a system large enough for interior tile blocks (tile lists inside the domain, per-particle lists on
+    # its faces): energies to 1e-5, the neighbour lists in force at the end bit for bit, same rebuild schedule
+    n, L, r, v, dt = _liquid(32, melt_steps=20)
+    steps = 20
+    ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1, precision=1,
+                        epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=RC, skin=SKIN,
+                        force_evals_per_step=1, ring_rows=steps, device=local, rank=rank, world=world,
+                        proc_grid=choose_proc_grid(world, int(L // (RC + SKIN))))
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0)
+    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    rows = ctx.run(steps, kb=1.0)
+    off, idx = ctx.get_neighbors()
+    cnt = torch.from_numpy(np.diff(off)).cuda()
+    dist.all_reduce(cnt)
+    st = ctx.stats()
+    s = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+    ref = s.run(steps)
+    ref_off, ref_idx = s.neighbor_list()
+    cell_of, _, _ = ctx.get_cells()
+    mine = np.repeat(cell_of >= 0, np.diff(ref_off))
+    np.testing.assert_array_equal(idx, ref_idx[mine])          # this rank's rows, bit for bit
+    np.testing.assert_array_equal(cnt.cpu().numpy(), np.diff(ref_off))
+    np.testing.assert_allclose(rows["pe"], ref["pe"], rtol=1e-5)
+    np.testing.assert_allclose(rows["ke"], ref["ke"], rtol=1e-5)
+    assert st["list_rebuilds"] == s.counters()["rebuilds"]
+    tl = torch.tensor([st["tile_lists"]], device="cuda"); dist.all_reduce(tl)
+    if rank == 0:
+        print(f"NCCL domain decomposition check OK: world={world} fp32 tile lists on {int(tl.item())}/{world} ranks "
+              f"transport={st['halo_transport']} (1 = peer memory, 2 = ncclSend/ncclRecv) rebuilds={st['list_rebuilds']}", flush=True)
+    ctx.close()
     dist.destroy_process_group()
 
 

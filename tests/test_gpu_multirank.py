@@ -141,11 +141,12 @@ def test_decomposed_fp32_reuse_mode():
     o.close()
 
 
-@pytest.mark.parametrize("world,grid", [(2, (2, 1, 1)), (8, (2, 2, 2))])
+@pytest.mark.parametrize("world,grid", [(2, (2, 1, 1)), (8, (2, 2, 2)), (2, (1, 1, 2)), (4, (1, 2, 2)), (8, (1, 2, 4))])
 def test_decomposed_fp32_lists_bit_exact(world, grid):
-    """fp32 pair math with world > 1: tile lists for the whole blocks of interior slots, per-particle lists for the rest
-    (domain faces).  One step from a melted state: the lists in force are those of the initial positions.  32^3 particles
-    (13 cells per dimension) so that every rank has interior cells to tile."""
+    """fp32 pair math with world > 1.  Grids that leave x whole (the default): tile lists for every owned slot, windows
+    reaching into the ghost cells.  Grids that split x: tile lists for the whole blocks of interior slots, per-particle
+    lists for the rest (domain faces).  One step from a melted state: the lists in force are those of the initial
+    positions.  32^3 particles (13 cells per dimension) so that every rank has cells to tile."""
     n, L, r, v, dt = _liquid(32, melt_steps=20)
     out = _run_ranks(world, grid, n, L, dt, r, v, 1, precision=1, evals=1, batch=1, want_lists=True)
     ref_off, ref_idx = oracle_c.neighbors(r, L, RC + SKIN)

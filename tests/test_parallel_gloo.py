@@ -102,11 +102,13 @@ def test_choose_proc_grid():
     from mdsea_b200.parallel import choose_proc_grid
 
     assert choose_proc_grid(1) == (1, 1, 1)
-    assert choose_proc_grid(2) == (2, 1, 1)
-    assert choose_proc_grid(4) == (2, 2, 1)
-    assert choose_proc_grid(8) == (2, 2, 2)
-    assert choose_proc_grid(6) == (3, 2, 1)
-    assert choose_proc_grid(16) == (4, 2, 2)
-    assert choose_proc_grid(8, ncells=43) == (2, 2, 2)
+    # x (the contiguous cell index) stays whole; y and z share the ranks as evenly as possible
+    assert choose_proc_grid(2) == (1, 1, 2)
+    assert choose_proc_grid(4) == (1, 2, 2)
+    assert choose_proc_grid(8) == (1, 2, 4)
+    assert choose_proc_grid(6) == (1, 2, 3)
+    assert choose_proc_grid(16) == (1, 4, 4)
+    assert choose_proc_grid(8, ncells=43) == (1, 2, 4)
+    assert choose_proc_grid(8, ncells=3) == (2, 2, 2)   # y and z alone cannot hold 8 ranks of >= 1 cell
     with pytest.raises(ValueError):
         choose_proc_grid(7, ncells=3)
