@@ -474,6 +474,16 @@ def run_ours(args, wl):
     extra = None
     if world == 1 and not args.no_extra and args.workload != "c2":
         extra = allpairs_extra(local)
+    # strong scaling beside the weak-scaling headline: 8 M particles at every N (at N = 8 that IS the headline system),
+    # 64 M particles (BASELINE configs[4]) at N = 8
+    strong = {}
+    if wl is WORKLOADS["c3"] and precision == "fp32" and not args.no_strong:
+        ctx.close()
+        ctx = None
+        if world < 8:
+            strong["strong_8m"] = strong_scaling_extra(200, "strong_8m", rank, world, local, torch, dist)
+        if world == 8:
+            strong["strong_64m"] = strong_scaling_extra(400, "strong_64m", rank, world, local, torch, dist, dump_steps=1)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -521,14 +531,152 @@ def run_ours(args, wl):
             "parity": parity, "transport": transport,
             "cpu_baseline": cpu, "clocks": clocks, "energies_finite": energy_ok,
             "allpairs_configs1": extra,
+            **strong,
             "host_wall_s_timed_region": t_wall,
         }
+        if world == 8:
+            line["strong_8m"] = {"same_as": "the headline line: at 8 GPUs the weak-scaling system is the 8 M-particle system",
+                                 "pair_interactions_per_s": line["value"], "ms_per_md_step": line["ms_per_step"] / md_steps}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
     if rank == 0 and parity is not None and not parity["ok"]:
         raise SystemExit("bench.py: parity against the CPU oracle FAILED: " + json.dumps(parity))
+
+
+def strong_scaling_extra(per_row, label, rank, world, local, torch, dist, md=10, k_flush=4, dump_steps=0):
+    """One FIXED-SIZE system (per_row^3 particles, vf 0.3, rc 2.5, skin 0.3, fp32 pair math) decomposed over `world` GPUs:
+    BASELINE configs[3] "also report" (8 M particles on 1/2/4/8 GPUs) and configs[4] (64 M on 8).  The state is generated on
+    the device (csrc/gen.cu: the reference lattice bit for bit, Maxwell-Boltzmann speeds sampled from the reference's table,
+    isotropic directions) -- host generators would need minutes and 3 GB of host arrays per rank at 64 M.
+    Returns device-resident throughput (rows buffered in the device ring every step, energies all-reduced per batch), the
+    same with the rows of every step flushed to pinned host memory every k_flush steps, and optionally the time to scatter
+    `dump_steps` rows of every rank into one HDF5 file."""
+    import shutil
+
+    from mdsea_b200 import _capi, parallel
+    from mdsea_b200.gen import MONTECARLO_SPEEDRANGE, mb_cdf
+    from mdsea_b200.helpers import get_dt, nsphere_volume
+
+    wl = WORKLOADS["c3"]
+    n = per_row ** 3
+    L = (n * nsphere_volume(3, 0.5) / wl["vf"]) ** (1 / 3)
+    grid = PROC_GRIDS[world]
+    ctx = make_ctx(wl, n, L, 1e-3, local, "fp32", md, rank=rank, world=world, proc_grid=grid)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(_capi.Context.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    ctx.set_temperature(1.0)
+    step = float(MONTECARLO_SPEEDRANGE[1] - MONTECARLO_SPEEDRANGE[0])
+    mean_speed = ctx.generate_state(mb_cdf(1.0, 1.0, 1.0), step, seed=1234, isotropic=True)
+    ctx.set_dt(get_dt(0.5, mean_speed))
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    rows_dev = dict(r=None, v=None, pe=np.empty(md), ke=np.empty(md), temp=np.empty(md))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):   # 30 steps: the lattice has started to melt, several list rebuilds behind us
+        ctx.run(md, kb=1.0, record=True, rows=rows_dev)
+    sync()
+    s0 = ctx.stats()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        ctx.run(md, kb=1.0, record=True, rows=rows_dev)
+    e1.record(stream)
+    sync()
+    s1 = ctx.stats()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    pairs = float(s1["pair_evals_unique"] - s0["pair_evals_unique"])
+    energies_ok = bool(np.isfinite(rows_dev["pe"]).all() and np.isfinite(rows_dev["ke"]).all())
+    pe_last = float(rows_dev["pe"][-1])
+    # rows of every step flushed to the host every k_flush steps, two batches in flight
+    width = ctx.rank_capacity() if world > 1 else n
+    pin = lambda shape, dt_=torch.float64: torch.empty(shape, dtype=dt_, pin_memory=True).numpy()
+    sets = []
+    for _ in range(2):
+        rw = dict(r=pin((k_flush, 3, width)), v=pin((k_flush, 3, width)), pe=pin((k_flush,)), ke=pin((k_flush,)), temp=pin((k_flush,)))
+        if world > 1:
+            rw["ids"] = pin((k_flush, width), torch.int32)
+            rw["n_owned"] = pin((k_flush,), torch.int64)
+        sets.append(rw)
+    ctx.run(k_flush, kb=1.0, record=True, rows=sets[0])
+    sync()
+    p0 = ctx.stats()["pair_evals_unique"]
+    nb = 4
+    t0 = time.perf_counter()
+    in_flight = 0
+    for b in range(nb):
+        ctx.run(k_flush, kb=1.0, record=True, rows=sets[b % 2], asynchronous=True)
+        in_flight += 1
+        if in_flight == 2:
+            ctx.wait(); in_flight -= 1
+    while in_flight:
+        ctx.wait(); in_flight -= 1
+    torch.cuda.synchronize()
+    t_flush = time.perf_counter() - t0
+    sync()
+    st = ctx.stats()
+    flush_pairs = float(st["pair_evals_unique"] - p0)
+    n_loc, n_gh = st["n_local"] if world > 1 else n, st["n_ghost"]
+    row_bytes = k_flush * (48 + (4 if world > 1 else 0)) * n_loc
+    # HDF5 dump of the last flushed rows: every rank scatters the columns of the particles it owns into ONE file
+    dump = None
+    if dump_steps > 0:
+        from mdsea_b200.core import SysManager
+
+        need = 2 * dump_steps * 3 * n * 8
+        free = shutil.disk_usage(os.getcwd()).free
+        if free < 2 * need:
+            dump = {"skipped": f"{free / 1e9:.0f} GB free in the working directory, {need / 1e9:.0f} GB needed"}
+        else:
+            simid = f"bench_{label}"
+            if rank == 0:
+                sm = SysManager.new(simid=simid, ndim=3, num_particles=n, steps=dump_steps, vol_fraction=wl["vf"], radius_particle=0.5)
+            sync()
+            if rank != 0:
+                sm = SysManager.load(simid)
+            sm._open_datafile(shared=True)
+            td = time.perf_counter()
+            parallel.scatter_rows(sm, sets[(nb - 1) % 2], dump_steps, 0, rank)
+            sm.dfile.flush() if hasattr(sm.dfile, "flush") else None
+            sync()
+            t_dump = time.perf_counter() - td
+            ok = None
+            if rank == 0:
+                pe_file = sm.get_ds(sm.potenergy_dsname)
+                ok = bool(np.allclose(pe_file[:dump_steps], sets[(nb - 1) % 2]["pe"][:dump_steps]))
+            sm._close_datafile()
+            sync()
+            if rank == 0:
+                sm.delete()
+            dump = {"steps": dump_steps, "file_bytes": need, "seconds": t_dump, "gb_per_s": need / t_dump / 1e9,
+                    "backend": "hdf5min (shared memory maps; every rank writes the columns it owns)", "scalars_read_back_ok": ok}
+    ctx.close()
+    agg = torch.tensor([pairs, flush_pairs, float(n_loc), float(n_gh), float(row_bytes)], dtype=torch.float64, device="cuda")
+    mx = torch.tensor([t_dev, t_flush, float(n_gh) / max(n_loc, 1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    agg, mx = agg.tolist(), mx.tolist()
+    return {"workload": f"3D LJ liquid N={n} ({per_row}^3) vf=0.3 rc=2.5 skin=0.3, fixed total size over {world} GPU(s)",
+            "particles_total": n, "n_gpus": world, "grid": list(grid), "md_steps_timed": reps * md,
+            "pair_interactions_per_s": agg[0] / mx[0], "ms_per_md_step": 1e3 * mx[0] / (reps * md),
+            "timesteps_per_s": reps * md / mx[0], "ghost_fraction_max": mx[2], "list_rebuilds": int(s1["list_rebuilds"] - s0["list_rebuilds"]),
+            "energies": "pe / ke of every step all-reduced over the ranks once per batch", "energies_finite": energies_ok, "pe_last": pe_last,
+            "flushed": {"rows_flushed_every": k_flush, "bytes_per_flush_all_ranks": agg[4], "pair_interactions_per_s": agg[1] / mx[1],
+                        "ms_per_md_step": 1e3 * mx[1] / (nb * k_flush), "d2h_gbs_per_rank": (agg[4] / world) / (mx[1] / nb) / 1e9},
+            "hdf5_dump": dump, "state": "generated on the device (gen.cu), 30 warm-up steps", "tile_lists": int(st["tile_lists"]),
+            "transport": int(st.get("halo_transport", 0))}
 
 
 _UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -609,6 +757,7 @@ def main():
     ap.add_argument("--md-steps", type=int, default=None, help="MD timesteps per bench step (one C-ABI run call)")
     ap.add_argument("--evals", type=int, default=1, choices=[1, 2], help="force evaluations per MD step (2 = reference-faithful)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling ride-along systems (8 M / 64 M particles)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the benched configuration")
     ap.add_argument("--no-extra", action="store_true", help="skip the additional all-pairs (configs[1]) measurement at N=1")
     args = ap.parse_args()

@@ -93,8 +93,18 @@ class SysManager:
             os.mkdir(directory)
         log.debug("New directory tree created: %s", self.sim_path)
 
-    def _open_datafile(self, mode: str = "a"):
-        self.dfile = h5py.File(self.data_path, mode=mode)
+    def _open_datafile(self, mode: str = "a", shared: Optional[bool] = None):
+        """Open data.h5.  ``shared=True`` (multi-GPU runs: every rank writes the columns of the particles it owns into the
+        same file) always goes through the built-in ``hdf5min`` backend, whose datasets are shared memory maps: several
+        non-MPI processes holding the file open read-write is exactly what real h5py / libhdf5 file locking forbids."""
+        if shared is not None:
+            self._shared_file = bool(shared)
+        if getattr(self, "_shared_file", False):
+            from mdsea_b200 import hdf5min
+
+            self.dfile = hdf5min.File(self.data_path, mode=mode)
+        else:
+            self.dfile = h5py.File(self.data_path, mode=mode)
         return self.dfile
 
     def _close_datafile(self):

@@ -520,9 +520,20 @@ static int mr_assemble(mdsea_ctx *c) {
         soff[q + 1] = soff[q] + (q == me ? 0 : s->h_cnt_all[me * MD_MAXW + q]);
         roff[q + 1] = roff[q] + s->h_cnt_all[q * MD_MAXW + me];
     }
-    if (soff[W] > s->sendpool_cap || roff[W] > s->cap) {
-        md_set_error(c, "rebuild: migration/ghost buffer capacity exceeded on this rank");
-        return MDSEA_ERR_CAPACITY;
+    // The capacity decision is COLLECTIVE: every rank holds every rank's counts after the all-gather and all pools have
+    // the same size, so all ranks evaluate all ranks' totals and leave together -- a rank that returned alone would leave
+    // its peers blocked in ncclSend / ncclRecv.
+    for (int p = 0; p < W; ++p) {
+        long long sp_tot = 0, rp_tot = 0;
+        for (int q = 0; q < W; ++q) {
+            if (q != p) sp_tot += s->h_cnt_all[p * MD_MAXW + q];
+            rp_tot += s->h_cnt_all[q * MD_MAXW + p];
+        }
+        if (sp_tot > s->sendpool_cap || rp_tot > s->cap) {
+            md_set_error(c, p == me ? "rebuild: migration/ghost buffer capacity exceeded on this rank"
+                                    : "rebuild: migration/ghost buffer capacity exceeded on another rank (all ranks stop)");
+            return MDSEA_ERR_CAPACITY;
+        }
     }
     // fill pass: messages for peer q -> its segment of the send pool; what this rank keeps -> straight into its own
     // segment of the receive pool (the union is unpacked from there in one go; the sort canonicalises the order)

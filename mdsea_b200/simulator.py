@@ -42,8 +42,9 @@ _ALGORITHMS = {"verlet": 0, "simple": 1}
 _PRECISIONS = {"fp64": 0, "fp32": 1}
 
 
-def _pinned_empty(shape):
-    """Page-locked float64 host buffer (torch is used for allocation only); plain numpy if CUDA is absent."""
+def _pinned_empty(shape, keep: list):
+    """Page-locked float64 host buffer (torch is used for allocation only); plain numpy if CUDA is absent.  The owning
+    tensor goes into `keep` (a list on the solver instance): the pages are unpinned when the solver drops it."""
     try:
         import torch
 
@@ -51,14 +52,11 @@ def _pinned_empty(shape):
             t = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
             a = t.numpy()
             a.setflags(write=True)
-            _pinned_empty._keep.append(t)
+            keep.append(t)
             return a
     except Exception:  # pragma: no cover
         pass
     return np.empty(shape, dtype=np.float64)
-
-
-_pinned_empty._keep = []
 
 
 @dataclass
@@ -91,8 +89,9 @@ class _BaseSimulator:
             # initial state: same generators, same RNG call order as simulator.py:54-59
             self._r = PosGen(ndim=sm.NDIM, boxlen=sm.LEN_BOX, nparticles=sm.NUM_PARTICLES).simplecubic()
             self._v = VelGen(ndim=sm.NDIM, nparticles=sm.NUM_PARTICLES).mb(sm.MASS, sm.TEMP, Config.k_boltzmann)
-        self._acc = np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
-        self.ndnp_zeroes = np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
+        # device_init runs are the large ones (configs[4]: 64 M particles on 8 ranks): no O(N) host mirrors until asked for
+        self._acc = None if self.device_init else np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
+        self.ndnp_zeroes = None if self.device_init else np.zeros((sm.NDIM, sm.NUM_PARTICLES), dtype=DTYPE)
         self._dists = self._drunits = self.pairs_indexes = None
         self.mean_ke = None
         self.mean_pe = None
@@ -108,6 +107,7 @@ class _BaseSimulator:
         if self.precision not in _PRECISIONS:
             raise ValueError(f"precision '{self.precision}' not in {tuple(_PRECISIONS)}")
         self._ctx = None
+        self._pinned = []            # page-locked row buffers of this solver (released by close())
         self._device_fresh = False   # device holds a newer state than the host copies
         self._host_exposed = True    # host arrays may have been edited -> upload before the next device op
         if self.device_init:
@@ -173,8 +173,11 @@ class _BaseSimulator:
         if self._world > 1:
             self._ctx.comm_init(parallel.broadcast_unique_id(_capi.Context.nccl_unique_id))
             parallel.barrier()
-            if self._rank != 0 and sm.dfile is None:  # rank 0 created the simfile tree; the others only open it
-                sm._open_datafile()
+            # rank 0 created the simfile tree; every rank (rank 0 included) now holds the file through the shared
+            # memory-mapped backend: concurrent read-write opens are not something libhdf5's file locking allows
+            if sm.dfile is not None and getattr(sm.dfile, "id", None) is not None and sm.dfile.id.valid:
+                sm._close_datafile()
+            sm._open_datafile(shared=True)
         self._ctx.set_temperature(self.temp, reset_ke=self.mean_ke is None)
         width = n if self._world == 1 else self._ctx.rank_capacity()
         self._rows_width = width
@@ -182,10 +185,29 @@ class _BaseSimulator:
         self._rows_alt = None   # second host buffer set, created when run_simulation pipelines more than one batch
         return self._ctx
 
+    def close(self) -> None:
+        """Release the device context and the page-locked row buffers (the state stays readable on the host)."""
+        if self._ctx is not None:
+            self._sync_to_host()
+            self._ctx.close()
+            self._ctx = None
+            self._host_exposed = True
+        self._rows = self._rows_alt = None
+        self._pinned.clear()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None) is not None:
+                self._ctx.close()
+            getattr(self, "_pinned", []).clear()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
     def _new_rows(self) -> dict:
         k, nd, width = self._k, self.sm.NDIM, self._rows_width
-        rows = dict(r=_pinned_empty((k, nd, width)), v=_pinned_empty((k, nd, width)),
-                    pe=_pinned_empty((k,)), ke=_pinned_empty((k,)), temp=_pinned_empty((k,)))
+        keep = self._pinned
+        rows = dict(r=_pinned_empty((k, nd, width), keep), v=_pinned_empty((k, nd, width), keep),
+                    pe=_pinned_empty((k,), keep), ke=_pinned_empty((k,), keep), temp=_pinned_empty((k,), keep))
         if self._world > 1:
             rows["ids"] = np.full((k, width), -1, dtype=np.int32)
             rows["n_owned"] = np.zeros(k, dtype=np.int64)
@@ -234,6 +256,8 @@ class _BaseSimulator:
     @property
     def acc(self) -> np.ndarray:
         self._sync_to_host()
+        if self._acc is None:
+            self._acc = np.zeros((self.sm.NDIM, self.sm.NUM_PARTICLES), dtype=DTYPE)
         return self._acc
 
     @acc.setter
@@ -457,7 +481,7 @@ class ContinuousPotentialSolver(_BaseSimulator):
             self._complete_batch(n, rows)
             if self._world > 1:
                 if not sm.dfile.id.valid:
-                    sm._open_datafile()
+                    sm._open_datafile(shared=True)
                 parallel.scatter_rows(sm, rows, n, first, self._rank)
             else:
                 sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], first)

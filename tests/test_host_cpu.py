@@ -268,3 +268,24 @@ def test_bench_reads_dram_traffic_from_the_tracked_ncu_summaries(tmp_path, monke
     assert bench.ncu_traffic("r01_ncu_c3_kernels.txt", "k_nbr_force_f32") > 1e8
     assert bench.ncu_traffic("r01_ncu_c3_force_f64.txt", "k_nbr_force_f64") > 1e8
     assert bench.ncu_traffic("r01_ncu_c2_allpairs_f64.txt", "k_allpairs") is not None
+
+
+def test_shared_datafile_backend_is_the_memory_mapped_one(in_tmp_cwd):
+    """Multi-GPU runs open data.h5 from every rank: that always goes through hdf5min (shared memory maps), whether or not
+    real h5py is installed -- libhdf5's file locking forbids several non-MPI read-write opens."""
+    from mdsea_b200 import hdf5min
+    from mdsea_b200.core import SysManager
+
+    sm = SysManager.new(simid="sh", ndim=3, num_particles=8, steps=3, vol_fraction=0.2, radius_particle=0.5)
+    a = sm._open_datafile(shared=True)
+    assert isinstance(a, hdf5min.File)
+    b = SysManager.load("sh")
+    b._open_datafile(shared=True)
+    a[sm.rcoord_dsname].raw[1][:, [0, 3]] = 7.0     # two "ranks" writing disjoint columns of the same row
+    b.dfile[sm.rcoord_dsname].raw[1][:, [1, 2]] = 9.0
+    a.close(); b.dfile.close()
+    row = SysManager.load("sh").get_ds(sm.rcoord_dsname)[1]
+    assert (row[:, [0, 3]] == 7.0).all() and (row[:, [1, 2]] == 9.0).all()
+    # a reopen after a close keeps the shared backend
+    sm._open_datafile()
+    assert isinstance(sm.dfile, hdf5min.File)
