@@ -445,6 +445,177 @@ k_allpairs_f32(const uint32_t *__restrict__ q, const double *__restrict__ r64, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 kernel, Newton's third law (up to AP3_MAXT tiles): the fp32 twin of k_allpairs_n3_f64.  One CTA per UNORDERED
+// pair of 128-particle tiles, every pair evaluated once; the reaction goes to the j particle through the warp's private
+// copy of the tile's force array (lanes of a warp visit distinct j in every batch: no atomics, fixed order).  Positions
+// are converted to 32-bit fixed point inside the kernel (no separate conversion launch) and staged as one 16-byte record
+// per particle; the warp-private reaction arrays are float4 as well, so a pair costs one LDS.128 for the position and
+// one LDS.128 + STS.128 for the reaction.  Pairs at the half-box tie or within 2e-6 of the cutoff are redone from the
+// float64 positions exactly like in k_allpairs_f32.  fp32 sums cover one tile (128 pairs per particle) and are written
+// out as float64 partials: fpart[partner tile][dim][particle], summed in fixed order by the integrator.
+// ---------------------------------------------------------------------------------------------
+// AP3_JS: every tile pair is shared by AP3_JS CTAs (blockIdx.z), each taking 128 / AP3_JS of the j tile: 528 tile pairs of
+// 4 warps would leave a B200 at 14 resident warps per SM; partner slots are (J, z), so the integrator sums AP3_JS * T partials.
+#define AP3_JS 2
+#define AP3_JN (AP_TI / AP3_JS)   // j particles per CTA
+#define AP3_U (AP3_JN / 32)       // independent pairs per batch
+template <int NDIM, int POTK, bool CUT, bool PBC>
+__global__ void __launch_bounds__(AP_TI)
+k_allpairs_n3_f32(const double *__restrict__ r64, int n, BoxDev box, PotF32 P, float rc2s, double rc2, double inv_h,
+                  double *__restrict__ fpart, double *__restrict__ pe_part, unsigned long long *__restrict__ cnt_part,
+                  StepScalars *__restrict__ sc) {
+    __shared__ uint4    sj[AP3_JN];
+    __shared__ float4   sfj[AP_TI / 32][AP3_JN];
+    __shared__ double   red[32];
+    __shared__ unsigned redu[32];
+    const int J = blockIdx.x, I = blockIdx.y, h = blockIdx.z;
+    const int bidx = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (I > J) {   // lower triangle: nothing to do, but the partial-sum slots are read by the finalize kernel
+        if (threadIdx.x == 0) { pe_part[bidx] = 0.0; cnt_part[bidx] = 0ull; }
+        return;
+    }
+    const int  t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int  i = I * AP_TI + t;
+    const int  j0 = J * AP_TI + h * AP3_JN;            // first j of this CTA
+    const bool active = i < n, diag = I == J;
+    const int  ic = active ? i : n - 1, nj = min(AP3_JN, n - j0);   // may be <= 0 for the ragged last tile
+    const int  tj = t - h * AP3_JN;                    // this thread's own index inside the j range (diagonal tiles: pairs jl > tj)
+    uint32_t qi[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) qi[d] = (uint32_t)(unsigned long long)__double2ll_rn(r64[(size_t)d * n + ic] * inv_h);
+    if (t < AP3_JN) {
+        const int jc = min(j0 + t, n - 1);
+        uint32_t qj[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) qj[d] = (uint32_t)(unsigned long long)__double2ll_rn(r64[(size_t)d * n + jc] * inv_h);
+        sj[t] = make_uint4(qj[0], qj[1], qj[2], 0u);
+#pragma unroll
+        for (int ww = 0; ww < AP_TI / 32; ++ww) sfj[ww][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    float    f[3] = {0.f, 0.f, 0.f}, pe = 0.f;
+    unsigned cnt = 0;
+    const float cut_lo = rc2s * (1.0f - 2e-6f), cut_hi = rc2s * (1.0f + 2e-6f);
+    float4 *__restrict__ myf = sfj[w];
+    // two batches per iteration (b and b + 16): their pair arithmetic is independent (2 * AP3_U pairs in flight); only the
+    // reaction updates of the two batches are ordered by __syncwarp (lane l's slot of batch b + 16 is lane l+16's slot of batch b)
+    for (int b = 0; b < 16; ++b) {
+        float    dd[2 * AP3_U][3], s4[2 * AP3_U];
+        int      jls[2 * AP3_U];
+        unsigned slow_mask = 0u;
+#pragma unroll
+        for (int u = 0; u < 2 * AP3_U; ++u) {
+            const int   g = (lane + b + (u >= AP3_U ? 16 : 0)) & 31;
+            const int   jl = (u % AP3_U) * 32 + g;
+            jls[u] = jl;
+            const uint4 q = sj[jl];
+            const uint32_t qq[3] = {q.x, q.y, q.z};
+            float    r2 = 0.0f;
+            uint32_t band = 0xffffffffu;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                const uint32_t du = qq[d] - qi[d];
+                if (PBC) band = min(band, du - 0x7ffff000u);   // |di| within 2^12 units of the half-box tie <=> du - 0x7ffff000 <= 0x2000
+                const float x = (float)(int)du;
+                dd[u][d] = x;
+                r2 = fmaf(x, x, r2);
+            }
+            bool ok = active && jl < nj && (!diag || jl > tj);
+            bool slow = PBC && band <= 0x2000u;
+            if (CUT) slow = slow || (r2 > cut_lo && r2 < cut_hi);
+            if (slow) {
+                slow_mask |= ok ? (1u << u) : 0u;
+                ok = false;
+            }
+            if (CUT) ok = ok && (r2 < rc2s);
+            float s, uu;
+            md_pair<POTK>(r2, ok, P, s, uu);
+            s4[u] = s;
+            pe += uu;
+            cnt += ok ? 2u : 0u;
+        }
+        if (slow_mask) {   // rare: image and in/out-of-cutoff decision from the float64 positions
+#pragma unroll
+            for (int u = 0; u < 2 * AP3_U; ++u) {   // static indices keep dd / s4 in registers
+                if (!((slow_mask >> u) & 1u)) continue;
+                double r2d = 0.0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    const double x = ap_exact_sep<PBC>(r64, (size_t)d * n + (j0 + jls[u]), (size_t)d * n + ic, box.L, box.invL);
+                    r2d = fma(x, x, r2d);
+                    dd[u][d] = (float)(x * inv_h);
+                }
+                const bool ok = !CUT || r2d < rc2;
+                float s, uu;
+                md_pair<POTK>((float)(r2d * inv_h * inv_h), ok, P, s, uu);
+                s4[u] = s;
+                pe += uu;
+                cnt += ok ? 2u : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * AP3_U; ++u) {
+            if (u == AP3_U) __syncwarp();
+            float4 a = myf[jls[u]];
+            const float fx = dd[u][0] * s4[u];
+            f[0] += fx; a.x -= fx;           // a_i += dr * s, a_j -= dr * s   (dr = r_j - r_i)
+            if (NDIM > 1) { const float fy = dd[u][1] * s4[u]; f[1] += fy; a.y -= fy; }
+            if (NDIM > 2) { const float fz = dd[u][2] * s4[u]; f[2] += fz; a.z -= fz; }
+            myf[jls[u]] = a;                 // this warp's copy; within a batch its lanes hit distinct j
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const int slot = J * AP3_JS + h;         // partner slot of the i particles; the j particles use slot I * AP3_JS + h' (h' = their own half)
+    if (active && !diag) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) fpart[((size_t)slot * NDIM + d) * n + i] = (double)f[d];
+    }
+    double fj[3] = {0.0, 0.0, 0.0};
+    if (t < AP3_JN) {
+#pragma unroll
+        for (int ww = 0; ww < AP_TI / 32; ++ww) {
+            const float4 a = sfj[ww][t];
+            fj[0] += (double)a.x; fj[1] += (double)a.y; fj[2] += (double)a.z;
+        }
+    }
+    if (diag) {
+        // diagonal tile pair: slot (I, h) of particle i holds its action over this CTA's j half; the reactions of that half go
+        // to the other slot family of the SAME tile, (I, h) as seen from the j side -- fold both into one write per particle:
+        // particle i gets f (all threads) and, if it lies in this CTA's j half, the reaction sum as well
+        __shared__ double sfold[3][AP3_JN];
+        if (t < AP3_JN) {
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) sfold[d][t] = fj[d];
+        }
+        __syncthreads();
+        if (active) {
+            const bool mine = tj >= 0 && tj < AP3_JN;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) fpart[((size_t)slot * NDIM + d) * n + i] = (double)f[d] + (mine ? sfold[d][tj] : 0.0);
+        }
+    } else if (t < AP3_JN) {
+        // slot (I, h) of the j tile's particles: the reaction for this CTA's half, zero for the other halves (every
+        // (slot, particle) entry is written by exactly one CTA per evaluation: the integrator sums all slots)
+#pragma unroll
+        for (int hh = 0; hh < AP3_JS; ++hh) {
+            const int jp = J * AP_TI + hh * AP3_JN + t;
+            if (jp < n) {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) fpart[((size_t)(I * AP3_JS + h) * NDIM + d) * n + jp] = hh == h ? fj[d] : 0.0;
+            }
+        }
+    }
+    const double   bpe = md_block_sum((double)pe, red);
+    const unsigned bc = md_block_sum(cnt, redu);
+    if (threadIdx.x == 0) {
+        pe_part[bidx] = 2.0 * bpe;   // every unordered pair once: counted for both directions like the split-j kernel
+        cnt_part[bidx] = bc;
+        atomicAdd(&sc->pairs_pending, (unsigned long long)bc);
+    }
+}
+
 // positions -> 32-bit fixed point (flat over ndim*n elements)
 __global__ void k_to_fixed(const double *__restrict__ r, uint32_t *__restrict__ q, size_t E, double scale) {
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,9 +642,9 @@ int md_allpairs_setup(mdsea_ctx *c) {
     c->ap_nsplit = nsplit;
     c->ap_jchunk = md_div_up(md_div_up(n, nsplit), AP_TI) * AP_TI;  // whole tiles: the diagonal tile is block-uniform
     c->ap_nsplit = md_div_up(n, c->ap_jchunk);
-    // fp64, up to AP3_MAXT tiles: the Newton's-third-law kernel (one CTA per unordered tile pair, T partner slots)
-    c->ap_n3 = c->p.precision == MDSEA_FP64 && c->ap_blocks_x <= AP3_MAXT && !(getenv("MDSEA_AP_N3") && !strcmp(getenv("MDSEA_AP_N3"), "0"));
-    if (c->ap_n3) c->ap_nsplit = c->ap_blocks_x;
+    // up to AP3_MAXT tiles: the Newton's-third-law kernels (one CTA per unordered tile pair, T partner slots), both precisions
+    c->ap_n3 = c->ap_blocks_x <= AP3_MAXT && !(getenv("MDSEA_AP_N3") && !strcmp(getenv("MDSEA_AP_N3"), "0"));
+    if (c->ap_n3) c->ap_nsplit = c->ap_blocks_x * (c->p.precision == MDSEA_FP32 ? AP3_JS : 1);   // partner slots
     c->n_pe_part = c->ap_blocks_x * c->ap_nsplit;
     MD_CUDA(c, cudaMalloc(&c->d_fpart, sizeof(double) * c->E * c->ap_nsplit));
     MD_CUDA(c, cudaMalloc(&c->d_pe_part, sizeof(double) * c->n_pe_part));
@@ -493,6 +664,11 @@ template <int NDIM, int POTK, bool CUT, bool PBC>
 static void launch_n3_f64(mdsea_ctx *c, dim3 grid, const PotF64 &P, double rc2) {
     k_allpairs_n3_f64<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(c->d_r, (int)c->n, c->box, P, rc2, c->d_fpart, c->d_pe_part,
                                                                         c->d_cnt_part, c->d_sc);
+}
+template <int NDIM, int POTK, bool CUT, bool PBC>
+static void launch_n3_f32(mdsea_ctx *c, dim3 grid, const PotF32 &P, float rc2s, double rc2, double inv_h) {
+    k_allpairs_n3_f32<NDIM, POTK, CUT, PBC><<<grid, AP_TI, 0, c->stream>>>(c->d_r, (int)c->n, c->box, P, rc2s, rc2, inv_h, c->d_fpart,
+                                                                        c->d_pe_part, c->d_cnt_part, c->d_sc);
 }
 template <int NDIM, int POTK, bool CUT, bool PBC>
 static void launch_f32(mdsea_ctx *c, dim3 grid, const PotF32 &P, float rc2s, double rc2, double inv_h) {
@@ -547,11 +723,16 @@ int md_allpairs_force(mdsea_ctx *c) {
     } else {
         const double units = c->box.pbc ? 4294967296.0 : 2147483648.0;
         const double h = c->box.L / units, inv_h = units / c->box.L;
-        k_to_fixed<<<md_div_up((long long)c->E, 256), 256, 0, c->stream>>>(c->d_r, (uint32_t *)c->d_rhi, c->E, inv_h);
         const PotF32 P = md_pot_f32(pd, inv_h);
         (void)h;
-        AP_DISPATCH(launch_f32, c, grid, P, (float)(rc2 * inv_h * inv_h), rc2, inv_h);
-        c->stats.kernel_launches += 2;
+        if (c->ap_n3) {
+            AP_DISPATCH(launch_n3_f32, c, dim3(c->ap_blocks_x, c->ap_blocks_x, AP3_JS), P, (float)(rc2 * inv_h * inv_h), rc2, inv_h);
+            c->stats.kernel_launches += 1;
+        } else {
+            k_to_fixed<<<md_div_up((long long)c->E, 256), 256, 0, c->stream>>>(c->d_r, (uint32_t *)c->d_rhi, c->E, inv_h);
+            AP_DISPATCH(launch_f32, c, grid, P, (float)(rc2 * inv_h * inv_h), rc2, inv_h);
+            c->stats.kernel_launches += 2;
+        }
     }
     md_prof_end(c, &c->stats.ms_force);
     MD_CUDA(c, cudaGetLastError());

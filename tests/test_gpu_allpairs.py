@@ -191,3 +191,43 @@ def test_errors_and_edge_cases():
     with pytest.raises(_capi.MdseaError):  # more steps than ring rows
         ctx.run(5, kb=1.0)
     ctx.close()
+
+
+@pytest.mark.parametrize("precision,etol,ftol", [(0, FP64_E, FP64_F), (1, FP32_E, FP32_F)])
+def test_split_j_kernels_behind_the_switch(monkeypatch, precision, etol, ftol):
+    """Up to 64 tiles both precisions take the Newton's-third-law kernels (one CTA per unordered tile pair); the split-j
+    kernels (directed pairs, any N) stay behind MDSEA_AP_N3=0 and above 8192 particles.  Same golden rows, same bounds."""
+    monkeypatch.setenv("MDSEA_AP_N3", "0")
+    g = load_golden("lj_3d_n4096")
+    s = golden_settings(g)
+    ctx = context_from_settings(s, precision=precision, evals=2)
+    ctx.set_temperature(s["temp"])
+    ctx.set_state(g["r0"], g["v0"])
+    steps = min(s["steps"], 20)
+    rows = run_context(ctx, s, steps)
+    np.testing.assert_allclose(rows["pe"], g["pot_energy"][:steps], rtol=etol, atol=1e-7 if precision else 1e-12)
+    np.testing.assert_allclose(rows["ke"], g["kin_energy"][:steps], rtol=etol, atol=1e-7 if precision else 1e-12)
+    assert ctx.stats()["pair_evals_executed"] > 0
+    ctx.close()
+    monkeypatch.delenv("MDSEA_AP_N3")
+    # N > 8192 (more than 64 tiles): the split-j kernels without the switch, first force evaluation against the C oracle
+    from oracle import oracle_c
+    from test_gpu_cutoff import _liquid
+
+    n, L, r, v, dt = _liquid(21, melt_steps=5)   # 9261 particles
+    o = oracle_c.CutoffSystem(r, v, L, 0.49 * L, 0.0, dt)   # rc just below L/2 = every minimum-image pair the cell path can hold
+    ref_acc, ref_pe = o.forces()
+    o.close()
+    from mdsea_b200 import _capi
+
+    ctx = _capi.Context(ndim=3, num_particles=n, boxlen=L, mass=1.0, radius=0.5, dt=dt, pbc=1, algorithm=0, pot_kind=1,
+                        precision=precision, epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, r_cutoff=0.49 * L,
+                        force_evals_per_step=2, ring_rows=1, device=0)
+    ctx.set_state(r, v)
+    acc, pe = ctx.update_acc()
+    assert abs(pe - ref_pe) <= etol * abs(ref_pe)
+    if precision == 0:
+        assert force_rel_err(acc, ref_acc) <= ftol
+    else:
+        assert force_rel_err(acc, ref_acc) <= 1e-4
+    ctx.close()
