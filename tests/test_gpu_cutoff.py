@@ -169,7 +169,9 @@ def test_forces_and_pe_vs_oracle(precision):
     else:
         onp = OracleSolver(r=r, v=v, boxlen=L, dt=dt, pot=MiePotential(), r_cutoff=RC)
         assert force_rel_err_pairscale(acc, ref_acc, onp.pair_force_scale()) <= 1e-5
-        assert force_rel_err(acc, ref_acc) <= 1e-4
+        # a melted liquid: the PLAIN per-particle metric |dF_i| / max(|F_i|, median|F|) meets north_star's 1e-5 as written
+        # (measured 4e-6 here, 8e-6 at 32^3); the pair-scale metric is only needed near a lattice, where |F_i| << sum_j |f_ij|
+        assert force_rel_err(acc, ref_acc) <= 1e-5
         assert abs(pe - ref_pe) <= 1e-5 * abs(ref_pe)
     ctx.close()
     o.close()
@@ -364,4 +366,92 @@ def test_neighbor_capacity_overflow_is_reported():
     with pytest.raises(_capi.MdseaError) as ei:
         ctx.run(1, kb=1.0)
     assert ei.value.status == -6
+    ctx.close()
+
+
+@pytest.mark.parametrize("precision,etol,rtol", [(1, 1e-5, 1e-3), (0, 1e-10, None)])
+def test_benched_size_one_million_particles_20_steps_vs_oracle(precision, etol, rtol):
+    """BASELINE configs[2] at its full size (100^3 particles, the system bench.py times): 20 steps from the gen.py start
+    against the C oracle -- energies of every step, the rebuild schedule, the neighbour lists in force at the end bit for
+    bit, and the final positions (fp64: 1e-9 L; fp32: 1e-3 sigma)."""
+    from bench import WORKLOADS, initial_state
+
+    wl = WORKLOADS["c3"]
+    n, L, r0, v0, dt = initial_state(3, wl["per_row"], wl["vf"])
+    assert n == 1_000_000
+    steps = 20
+    ref_off0, ref_idx0 = oracle_c.neighbors(r0, L, wl["r_cutoff"] + wl["skin"])
+    o = oracle_c.CutoffSystem(r0, v0, L, wl["r_cutoff"], wl["skin"], dt)
+    ref = o.run(steps)
+    oc = o.counters()
+    ref_off, ref_idx = o.neighbor_list()
+    ref_r, _, _ = o.state()
+    o.close()
+    ctx = _ctx(n, L, dt, precision=precision, evals=1, ring=steps, rc=wl["r_cutoff"], skin=wl["skin"])
+    ctx.set_temperature(1.0)
+    ctx.set_state(r0, v0)
+    off, idx = ctx.get_neighbors()   # same positions on both sides: bit for bit
+    np.testing.assert_array_equal(off, ref_off0)
+    np.testing.assert_array_equal(idx, ref_idx0)
+    rows = ctx.run(steps, kb=1.0, record=True, rows=dict(r=None, v=None, pe=np.empty(steps), ke=np.empty(steps), temp=np.empty(steps)))
+    np.testing.assert_allclose(rows["pe"], ref["pe"], rtol=etol)
+    np.testing.assert_allclose(rows["ke"], ref["ke"], rtol=etol)
+    st = ctx.stats()
+    assert st["list_rebuilds"] == oc["rebuilds"] and oc["rebuilds"] >= 2
+    assert st["tile_lists"] == (1 if precision == 1 else 0)
+    off, idx = ctx.get_neighbors()
+    if precision == 0:
+        np.testing.assert_array_equal(off, ref_off)
+        np.testing.assert_array_equal(idx, ref_idx)
+    else:
+        # fp32 pair math: the positions differ by ~1e-7 sigma after 20 steps, a pair that close to the list radius may
+        # fall on the other side -- a handful of the 5e7 entries
+        assert np.count_nonzero(np.diff(off) != np.diff(ref_off)) <= 50
+    r, _, _, _ = ctx.get_state(want_acc=False)
+    d = r - ref_r
+    d -= np.rint(d / L) * L
+    assert np.abs(d).max() <= (1e-9 * L if precision == 0 else rtol)
+    ctx.close()
+
+
+_DRIFT_CACHE = {}
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_long_run_energy_drift_within_the_oracles(precision):
+    """north_star: "energy drift over long runs must stay within the reference's own drift".  32^3 liquid, 5000 steps on the
+    cut-off path (plain truncation at rc: total energy is conserved up to cutoff-crossing jumps, on both sides alike):
+    the excursion of E = pe + ke from its start value and the least-squares drift per step must not exceed those of the C
+    oracle (float64, same algorithm) on the same run by more than the stated factors.  Trajectories decorrelate after
+    ~1e3 steps (chaos), so the comparison is statistical, not pointwise."""
+    steps, batch = 5000, 250
+    if "ref" not in _DRIFT_CACHE:   # one oracle run (about a minute on 16 host cores) serves both precisions
+        n, L, r, v, dt = _liquid(32, melt_steps=100)
+        o = oracle_c.CutoffSystem(r, v, L, RC, SKIN, dt)
+        ref = o.run(steps)
+        o.close()
+        _DRIFT_CACHE["ref"] = (n, L, r, v, dt, ref["pe"] + ref["ke"])
+    n, L, r, v, dt, e_ref = _DRIFT_CACHE["ref"]
+    ctx = _ctx(n, L, dt, precision=precision, evals=1, ring=batch)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r, v)
+    pe, ke = [], []
+    buf = dict(r=None, v=None, pe=np.empty(batch), ke=np.empty(batch), temp=np.empty(batch))
+    for _ in range(steps // batch):
+        ctx.run(batch, kb=1.0, record=True, rows=buf)
+        pe.append(buf["pe"].copy()); ke.append(buf["ke"].copy())
+    e = np.concatenate(pe) + np.concatenate(ke)
+    assert np.isfinite(e).all()
+    # the first 100 steps are still the same trajectory: energies agree pointwise there
+    np.testing.assert_allclose(e[:100], e_ref[:100], rtol=1e-9 if precision == 0 else 1e-5)
+    t = np.arange(steps)
+    slope = abs(np.polyfit(t, e, 1)[0])
+    slope_ref = abs(np.polyfit(t, e_ref, 1)[0])
+    exc = np.abs(e - e[0]).max()
+    exc_ref = np.abs(e_ref - e_ref[0]).max()
+    scale = abs(e_ref.mean())
+    # excursion and drift bounded by the oracle's (x1.5 / x2 for the statistical scatter of a different chaotic branch),
+    # with an absolute floor of 2e-6 |E| for runs where the oracle happens to drift almost nothing
+    assert exc <= 1.5 * exc_ref + 2e-6 * scale, (exc, exc_ref)
+    assert slope * steps <= 2.0 * slope_ref * steps + 2e-6 * scale, (slope, slope_ref)
     ctx.close()
