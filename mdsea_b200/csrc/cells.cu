@@ -144,6 +144,7 @@ struct CellState {
     int    *h_flag = nullptr;             // pinned + mapped: the skin trigger is published with a store over PCIe
     int    *d_flag_mapped = nullptr;      // device alias of h_flag
     cudaEvent_t ev_flag = nullptr;
+    cudaEvent_t ev_bnd = nullptr;         // comm stream -> main stream: the boundary particles' force kernel has run
     int     id_bits = 0, cell_bits = 0;
     int     finish_blocks = 1480;         // grid of the finish kernel: two full waves of its resident blocks per SM (5 -> 10 per SM)
     int     finish_blocks_fused = 888;    // same for the variant that also starts the next step (3 resident -> 6 per SM)
@@ -354,6 +355,7 @@ int md_cells_setup(mdsea_ctx *c) {
     MD_CUDA(c, cudaHostGetDevicePointer((void **)&s->d_flag_mapped, s->h_flag, 0));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_drift, cudaEventDisableTiming));
     MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_flag, cudaEventDisableTiming));
+    MD_CUDA(c, cudaEventCreateWithFlags(&s->ev_bnd, cudaEventDisableTiming));
     MD_CUDA(c, cudaHostAlloc(&s->h_cnt_all, sizeof(int) * (MD_MAXW * MD_MAXW + 8), cudaHostAllocMapped));
     MD_CUDA(c, cudaHostGetDevicePointer((void **)&s->d_cnt_all_mapped, s->h_cnt_all, 0));
     const size_t row_stride = W == 1 ? (size_t)N : (size_t)s->cap;
@@ -406,6 +408,7 @@ void md_cells_free(mdsea_ctx *c) {
     cudaFree(s->tl_desc); cudaFree(s->tl_list); cudaFree(s->tl_stats);
     if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->ev_flag) cudaEventDestroy(s->ev_flag);
+    if (s->ev_bnd) cudaEventDestroy(s->ev_bnd);
     if (s->ev_drift) cudaEventDestroy(s->ev_drift);
     if (s->h_cnt_all) cudaFreeHost(s->h_cnt_all);
     delete s;
@@ -685,6 +688,7 @@ static int halo_exchange(mdsea_ctx *c, cudaStream_t st) {
 
 #include <chrono>
 static bool g_trace_rebuild = getenv("MDSEA_TRACE_REBUILD") != nullptr;
+static bool g_bnd_overlap = !(getenv("MDSEA_BND_OVERLAP") && !strcmp(getenv("MDSEA_BND_OVERLAP"), "0"));   // A/B switch
 static int  g_nbw_groups = getenv("MDSEA_NBW_GROUPS") ? atoi(getenv("MDSEA_NBW_GROUPS")) : 2;   // r01: 4: 848 us, 2: 832 us, 1: 851 us per rebuild
 static int  g_nbw_variant = getenv("MDSEA_NBW_VARIANT") ? atoi(getenv("MDSEA_NBW_VARIANT")) : 1;   // bit 0: expanded distance test
 static bool g_force_cs = !(getenv("MDSEA_FORCE_CS") && !strcmp(getenv("MDSEA_FORCE_CS"), "0"));   // A/B switch: streaming list loads
@@ -863,8 +867,10 @@ static inline int force_parts(const CellState *s, long long i0, long long i1) {
     return g;
 }
 
-static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded /* guard tag, 0 = unguarded */) {
+static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, int guarded /* guard tag, 0 = unguarded */,
+                        cudaStream_t st = nullptr /* default: the compute stream */) {
     CellState *s = c->cells;
+    if (!st) st = c->stream;
     if (i1 <= i0) return MDSEA_OK;
     const bool lj = c->pot.fast == POTF_LJ;
     if (s->tile_active && i0 < s->tile_n) {
@@ -874,7 +880,7 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
         const float  rc2s = (float)(s->rc2 * inv_h * inv_h);
         const size_t smem = (size_t)((s->tl_win + 63) / 64 * 64) * 16;
 #define TILE_F32(POTK)                                                                                                              \
-    k_tile_force_f32<POTK><<<tile_grid(i0, t1), TL_BLOCK, smem, c->stream>>>((const uint4 *)s->pos4, c->d_r, s->tl_desc, s->tl_list, s->nbr_cnt, \
+    k_tile_force_f32<POTK><<<tile_grid(i0, t1), TL_BLOCK, smem, st>>>((const uint4 *)s->pos4, c->d_r, s->tl_desc, s->tl_list, s->nbr_cnt, \
                                                                          s->tl_max_nbr / 8, i0 / TL_BLOCK, i0, t1, s->cap, c->box.L, c->box.halfL, \
                                                                          s->rc2, rc2s, rc2s * 2e-6f, inv_h, P, c->d_acc, c->d_pe_part + pe_off,    \
                                                                          c->d_sc, guarded)
@@ -896,7 +902,7 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
         else NBR_F64_(POTK, false);                                                                                                \
     } while (0)
 #define NBR_F64_(POTK, CS)                                                                                                         \
-    k_nbr_force_f64<POTK, CS><<<grid, NB_THREADS, 0, c->stream>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr, \
+    k_nbr_force_f64<POTK, CS><<<grid, NB_THREADS, 0, st>>>((const double4 *)s->pos4, i0, i1, s->cap, s->nbr, s->nbr_cnt, s->max_nbr, \
                                                               c->box.L, c->box.halfL, s->rc2, P, c->d_acc, c->d_pe_part + pe_off,   \
                                                               c->d_sc, guarded)
         if (lj) NBR_F64(POTF_LJ);
@@ -912,7 +918,7 @@ static int launch_force(mdsea_ctx *c, long long i0, long long i1, int pe_off, in
         else NBR_F32_(TEX, POTK, false);                                                                                           \
     } while (0)
 #define NBR_F32_(TEX, POTK, CS)                                                                                                    \
-    k_nbr_force_f32<TEX, POTK, CS><<<grid, NB_THREADS, 0, c->stream>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr, \
+    k_nbr_force_f32<TEX, POTK, CS><<<grid, NB_THREADS, 0, st>>>((const uint4 *)s->pos4, s->tex_pos, c->d_r, i0, i1, s->cap, s->nbr, \
                                                                    s->nbr_cnt, s->max_nbr, c->box.L, c->box.halfL, s->rc2,         \
                                                                    (float)(s->rc2 * inv_h * inv_h), inv_h, P, c->d_acc,            \
                                                                    c->d_pe_part + pe_off, c->d_sc, guarded)
@@ -1021,19 +1027,28 @@ static int force_after_drift(mdsea_ctx *c, const mdsea_run_args *a, int k, doubl
         MD_TRY(cutoff_force(c, tag));
     } else {
         // comm stream: ghost refresh (+ flags) while the main stream computes the INTERIOR forces, which need no ghosts
+        // The boundary particles' force kernel follows the ghost refresh ON THE COMM STREAM, so it runs beside the interior
+        // kernel instead of after it (a small launch whose ramp-up and tail would otherwise sit on the critical path); the
+        // compute stream joins before the finish kernel.
+        const long long ni1 = s->n_int > 0 ? s->n_int : 1, nb1 = c->n > s->n_int ? c->n : s->n_int + 1;
+        const int gi = force_parts(s, 0, ni1);
+        c->n_pe_part = gi + force_parts(s, s->n_int, nb1);
+        MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
         MD_CUDA(c, cudaEventRecord(s->ev_drift, c->stream));
         MD_CUDA(c, cudaStreamWaitEvent(c->comm_stream, s->ev_drift, 0));
         MD_TRY(halo_exchange(c, c->comm_stream));
         k_publish_flag<<<1, 1, 0, c->comm_stream>>>(c->d_sc, s->d_flag_mapped, tag);
         MD_CUDA(c, cudaEventRecord(s->ev_flag, c->comm_stream));
-        const long long ni1 = s->n_int > 0 ? s->n_int : 1, nb1 = c->n > s->n_int ? c->n : s->n_int + 1;
-        const int gi = force_parts(s, 0, ni1);
-        c->n_pe_part = gi + force_parts(s, s->n_int, nb1);
-        MD_CUDA(c, cudaMemsetAsync(c->d_pe_part, 0, sizeof(double) * c->n_pe_part, c->stream));
         MD_TRY(launch_force(c, 0, s->n_int, 0, tag));                     // guarded by the LOCAL flag only (the global one
                                                                           // is not known yet): redone if any rank fired
-        MD_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_flag, 0));
-        MD_TRY(launch_force(c, s->n_int, c->n, gi, tag));                 // boundary particles: ghosts are fresh now
+        if (g_bnd_overlap) {
+            MD_TRY(launch_force(c, s->n_int, c->n, gi, tag, c->comm_stream));   // boundary particles: ghosts are fresh there
+            MD_CUDA(c, cudaEventRecord(s->ev_bnd, c->comm_stream));
+            MD_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_bnd, 0));
+        } else {
+            MD_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_flag, 0));
+            MD_TRY(launch_force(c, s->n_int, c->n, gi, tag));                   // boundary particles: ghosts are fresh now
+        }
         c->stats.force_evals += 1;
     }
     MD_TRY(cut_finish_and_finalize(c, a, k, g_dt, tag, next_tag));
