@@ -10,7 +10,7 @@ Parity pinning: the upstream reference ships no golden vectors for this path
 is pinned against OUTPUTS OF THE UNMODIFIED REFERENCE executed in the build
 container (oracle/gen_golden.py -> tests/golden/*.npz, via oracle/refshim.py) and,
 when /root/reference is present, against the live reference in
-tests/test_oracle_pinning.py.
+tests/test_oracle_golden.py.
 
 Every function cites the reference lines (relative to /root/reference/) it follows.
 The restatement keeps the reference's evaluation structure -- explicit i<j pair

@@ -15,6 +15,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
+@pytest.fixture(autouse=True)
+def _no_sticky_cuda_error(request):
+    """GPU tests: a test must not leave a CUDA error behind (cudaGetLastError is per thread and sticky: the next test's
+    first launch check would report it as its own)."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    import ctypes
+
+    try:
+        rt = ctypes.CDLL("libcudart.so.12")
+    except OSError:
+        return
+    err = rt.cudaGetLastError()
+    assert err == 0, f"{request.node.name} left CUDA error {err} behind"
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
     return {k: z[k] for k in z.files}
