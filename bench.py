@@ -448,18 +448,18 @@ def run_ours(args, wl):
     # DRAM bytes per launch of the force kernel from the tracked ncu --set full capture of this workload (same N)
     force_traffic, force_traffic_src = None, None
     if world == 1 and wl is WORKLOADS.get("c3"):
-        src = "r01_ncu_c3_force_f64.txt" if fp64 else "r01_ncu_c3_kernels.txt"
-        force_traffic = ncu_traffic(src, "k_nbr_force_f64" if fp64 else "k_nbr_force_f32")
+        src = "r01_ncu_c3_force_f64.txt" if fp64 else "r02/r02_ncu_c3_kernels.txt"
+        force_traffic = ncu_traffic(src, "k_nbr_force_f64" if fp64 else "k_tile_force_f32")
         force_traffic_src = "profiles/" + src if force_traffic else None
     elif world == 1 and wl is WORKLOADS.get("c2"):
-        src = "r01_ncu_c2_allpairs_f64.txt" if fp64 else "r01_ncu_c2_allpairs_f32.txt"
+        src = "r02/r02_ncu_c2_allpairs_f64.txt" if fp64 else "r02/r02_ncu_c2_allpairs_f32.txt"
         force_traffic = ncu_traffic(src, "k_allpairs")
         force_traffic_src = "profiles/" + src if force_traffic else None
     roof_hbm = None
     if i_ms > 0:
         roof_hbm = {"bound": "hbm", "kernel": integ_name, "achieved": integ_bytes / (i_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": integ_bytes / (i_ms * 1e-3) / 1e9 / hbm_peak,
-                    "traffic": ncu_traffic("r01_ncu_c3_kernels.txt", "k_cut_kick_finish<1>") if wl is WORKLOADS.get("c3") and not fp64 else None,
+                    "traffic": ncu_traffic("r02/r02_ncu_c3_kernels.txt", "k_cut_kick_finish<1>") if wl is WORKLOADS.get("c3") and not fp64 else None,
                     "bytes_per_launch": integ_bytes, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
 
     os.sched_setaffinity(0, all_cpus)   # the CPU legs below (oracle, cpu_baseline) use every host core
@@ -528,7 +528,8 @@ def run_ours(args, wl):
                     "pipeline": "2 batches in flight (run_async/wait): D2H of step s overlaps the compute of step s+1; "
                                 "wall clock over all K steps incl. the final drain; no L2 flush (working set >> L2)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64" if fp64 else "fp32", "kernel": "all-pairs force" if wl["r_cutoff"] <= 0 else "neighbour-list force",
+            "roofline": {"bound": "fp64" if fp64 else "fp32", "kernel": "all-pairs force (Newton's-third-law tile-pair kernel)" if wl["r_cutoff"] <= 0 else
+                         ("neighbour-list force (k_nbr_force_f64)" if fp64 else "neighbour-list force (k_tile_force_f32: windows in shared memory)"),
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": force_traffic,
                          "traffic_source": force_traffic_src,
