@@ -462,6 +462,26 @@ def run_ours(args, wl):
                     "traffic": ncu_traffic("r02/r02_ncu_c3_kernels.txt", "k_cut_kick_finish<1>") if wl is WORKLOADS.get("c3") and not fp64 else None,
                     "bytes_per_launch": integ_bytes, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
 
+    # what the box's PCIe / host memory path gives when all ranks copy at once: one 256 MB device -> pinned-host copy per rank,
+    # started together -- the ceiling of e2e.d2h_gbs_per_rank (8 GPUs of one node do not get 8 x the single-GPU rate)
+    raw_d2h = None
+    try:
+        src_t = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        dst_t = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+        dst_t.copy_(src_t, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dst_t.copy_(src_t, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_raw = time.perf_counter() - t0
+        rt = torch.tensor([dt_raw], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        raw_d2h = 4 * (256 << 20) / float(rt.item()) / 1e9
+        del src_t, dst_t
+    except Exception:
+        pass
     os.sched_setaffinity(0, all_cpus)   # the CPU legs below (oracle, cpu_baseline) use every host core
     # ---------------- parity of this very configuration against the CPU oracle ----------------
     parity = None
@@ -523,7 +543,8 @@ def run_ours(args, wl):
             "e2e": {"value": tot_e2e_pairs / t_e2e_max, "unit": "pair-interactions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "timesteps_per_s": (1 if decomposed else world) * args.steps * md_steps / t_e2e_max,
                     "ms_per_step": 1e3 * t_e2e_max / args.steps,
-                    "d2h_gbs_per_rank": d2h / (t_e2e_max / args.steps) / 1e9, "host_numa_binding": numa,
+                    "d2h_gbs_per_rank": d2h / (t_e2e_max / args.steps) / 1e9, "raw_d2h_gbs_per_rank_all_ranks_copying": raw_d2h,
+                    "host_numa_binding": numa,
                     "input": "the current (melted) state is uploaded from pinned memory before every batch",
                     "pipeline": "2 batches in flight (run_async/wait): D2H of step s overlaps the compute of step s+1; "
                                 "wall clock over all K steps incl. the final drain; no L2 flush (working set >> L2)"},
