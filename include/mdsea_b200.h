@@ -71,7 +71,10 @@ typedef struct {
     double  mie_m, mie_n, mie_a;
     double  r_cutoff;          /* <= 0: all pairs, no cutoff (the reference's only working mode).
                                   > 0 : EXTENSION -- plain truncation, pair counted iff dist < r_cutoff
-                                  (strict, as simulator.py:283), cell list + Verlet list, 3-D pbc only */
+                                  (strict, as simulator.py:283), cell list + Verlet list: 3-D boxes with >= 3
+                                  cells of side r_cutoff + skin per edge.  pbc = 0 (hard walls, single rank): the
+                                  box is embedded in a periodic cell grid of period boxlen + 2 (r_cutoff + skin),
+                                  which is the grid mdsea_b200_get_cells reports; other boxes: all-pairs kernels */
     double  skin;              /* Verlet skin; list radius = r_cutoff + skin                    */
     int32_t force_evals_per_step; /* 2: evaluate a(r) twice per verlet step like simulator.py:540,544;
                                      1: reuse a(t+dt) as the next step's a(t) (pbc only; identical

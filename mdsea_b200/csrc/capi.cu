@@ -88,14 +88,31 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
 
     c->cutoff_path = false;
     if (p->r_cutoff > 0 && pd.fast != POTF_IDEAL) {
-        // the cell/neighbour-list path needs a 3-D periodic box with at least 3 cells per side
+        // the cell/neighbour-list path needs a 3-D box with at least 3 cells per side
         const double rl = p->r_cutoff + (p->skin > 0 ? p->skin : 0.0);
-        const int nc = (int)floor(p->boxlen / rl);
-        c->cutoff_path = (p->ndim == 3 && p->pbc && nc >= 3);
+        if (p->pbc) {
+            const int nc = (int)floor(p->boxlen / rl);
+            c->cutoff_path = (p->ndim == 3 && nc >= 3);
+        } else if (p->ndim == 3 && p->world == 1 && (int)floor(p->boxlen / rl) >= 1 && !getenv("MDSEA_NO_WALL_CELLS")) {
+            // Hard walls (simulator.py:168-179): the box is EMBEDDED in a periodic cell grid of period L + 2 (rc + skin).  The
+            // particles live in [radius, L - radius] (a drift can carry one past a wall by v dt << rc until the next clamp),
+            // so two particles and their images across the period are always further apart than the list radius: the
+            // periodic machinery -- binning, stencils, minimum image, 32-bit fixed-point wrap -- computes exactly the
+            // non-periodic system, and nothing in the list kernels has to know about walls.  Only the boundary condition of
+            // the drift kernel (clamp + reflect instead of the wrap) uses the real box.  The cells that
+            // mdsea_b200_get_cells reports are those of the padded grid.
+            b.L = p->boxlen + 2.0 * rl;
+            b.invL = 1.0 / b.L;
+            b.halfL = 0.5 * b.L;
+            b.Lh = (float)b.L;
+            b.Ll = (float)(b.L - (double)b.Lh);
+            b.invLf = (float)(1.0 / b.L);
+            c->cutoff_path = true;
+        }
     }
     if (p->world > 1 && !c->cutoff_path) {
         delete c;
-        return bad(nullptr, "create: world > 1 needs the cutoff path (3-D, pbc, >= 3 cells per side); all-pairs runs are replicas only");
+        return bad(nullptr, "create: world > 1 needs the cutoff path (3-D, periodic, >= 3 cells per side); all-pairs runs are replicas only");
     }
     if (p->num_particles > 2000000 && !c->cutoff_path) {
         delete c;

@@ -250,8 +250,9 @@ int md_cells_setup(mdsea_ctx *c) {
     s->rl2 = s->rlist * s->rlist;
     s->rc2 = p.r_cutoff * p.r_cutoff;
     s->trig2 = (0.5 * skin) * (0.5 * skin);
-    s->nc = (int)floor(p.boxlen / s->rlist);
-    s->cell_len = p.boxlen / s->nc;
+    // c->box.L is the PERIOD of the cell grid: the box edge when periodic, the padded period L + 2 rlist for hard walls (capi.cu)
+    s->nc = (int)floor(c->box.L / s->rlist);
+    s->cell_len = c->box.L / s->nc;
     s->ncell = s->nc * s->nc * s->nc;
     const int W = p.world;
     // decomposition
@@ -954,9 +955,11 @@ static int cut_kick_drift(mdsea_ctx *c, bool do_bc, bool do_kick, bool do_drift)
     CellState *s = c->cells;
     md_prof_begin(c);
     if (do_drift) s->drift_tag = s->drift_tag == 0x7fffffff ? 1 : s->drift_tag + 1;
-    k_cut_kick_drift<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->rb, c->n, s->cap, do_bc, do_kick, do_drift,
-                                                        c->box.L, c->box.halfL, c->p.dt, s->trig2, c->p.precision == MDSEA_FP32,
-                                                        fixed_inv_h(c), s->pos4, c->d_sc, s->drift_tag);
+    WallBC wall;
+    wall.L = c->p.boxlen; wall.radius = c->p.radius; wall.restitution = c->p.restitution;
+    k_cut_kick_drift<<<g256(c->n), 256, 0, c->stream>>>(c->d_r, c->d_v, c->d_acc, s->rb, c->n, s->cap, do_bc ? (c->box.pbc ? 1 : 2) : 0,
+                                                        do_kick, do_drift, c->box.L, c->box.halfL, c->p.dt, s->trig2,
+                                                        c->p.precision == MDSEA_FP32, fixed_inv_h(c), s->pos4, c->d_sc, s->drift_tag, wall);
     md_prof_end(c, &c->stats.ms_integrate);
     MD_CUDA(c, cudaGetLastError());
     c->stats.kernel_launches += 1;

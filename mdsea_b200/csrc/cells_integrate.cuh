@@ -5,11 +5,14 @@
 // K5 (cut-off flavour): particle-wise integrators.  Same per-component arithmetic as integrate.cu, plus
 // the skin-displacement trigger, the packed position copy and the id-scatter of the dataset rows.
 // ---------------------------------------------------------------------------------------------------
+struct WallBC { double L, radius, restitution; };   // the REAL box of a hard-wall run (L below is the period of the cell grid)
+
+// do_bc: 0 none, 1 periodic one-shot strict wrap (simulator.py:156-166), 2 hard walls: clamp + reflect (simulator.py:168-179)
 __global__ void __launch_bounds__(256)
 k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *__restrict__ acc,
                  const double *__restrict__ rb, long long n, long long cap, int do_bc, int do_kick, int do_drift, double L,
                  double halfL, double dt, double trig2, int fp32, double inv_h, void *__restrict__ pos4,
-                 StepScalars *__restrict__ sc, int tag) {
+                 StepScalars *__restrict__ sc, int tag, WallBC wall) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     // all loads first (the stores below go through the same base pointers; see k_cut_kick_finish)
@@ -25,14 +28,17 @@ k_cut_kick_drift(double *__restrict__ r, double *__restrict__ v, const double *_
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         double xx = rr[d], u = vv[d];
-        if (do_bc) {  // one-shot strict wrap, simulator.py:165-166
+        if (do_bc == 1) {  // one-shot strict wrap, simulator.py:165-166
             if (xx < 0.0) xx += L;
             if (xx > L) xx -= L;
+        } else if (do_bc == 2) {  // same two tests, in the same order, as apply_hbc (k_apply_bc, integrate.cu)
+            if (xx - wall.radius < 0.0) { xx = wall.radius; u *= -wall.restitution; }
+            if (xx + wall.radius > wall.L) { xx = wall.L - wall.radius; u *= -wall.restitution; }
         }
         if (do_kick) u += __dmul_rn(__dmul_rn(0.5, aa[d]), dt);
         if (do_drift) xx += __dmul_rn(u, dt);
         r[d * cap + i] = xx;
-        if (do_kick) v[d * cap + i] = u;
+        if (do_kick || do_bc == 2) v[d * cap + i] = u;
         x[d] = xx;
         const double dd = md_minimg_exact(__dsub_rn(xx, bb[d]), L, halfL);
         d2 = __dadd_rn(d2, __dmul_rn(dd, dd));

@@ -179,8 +179,9 @@ int md_apply_bc(mdsea_ctx *c) {
 // the same boundary condition over E entries of arbitrary arrays (the cut-off path keeps one padded row per dimension)
 int md_apply_bc_range(mdsea_ctx *c, double *r, double *v, size_t E) {
     if (E == 0) return MDSEA_OK;
-    k_apply_bc<<<md_div_up((long long)E, IG_THREADS), IG_THREADS, 0, c->stream>>>(r, v, E, c->box.pbc, c->box.L, c->p.radius,
-                                                                                   c->p.restitution);
+    // hard walls on the cut-off path: c->box.L is the period of the padded cell grid, the walls are those of the real box
+    k_apply_bc<<<md_div_up((long long)E, IG_THREADS), IG_THREADS, 0, c->stream>>>(r, v, E, c->box.pbc, c->box.pbc ? c->box.L : c->p.boxlen,
+                                                                                   c->p.radius, c->p.restitution);
     c->stats.kernel_launches += 1;
     MD_CUDA(c, cudaGetLastError());
     return MDSEA_OK;

@@ -11,8 +11,8 @@ to the HDF5 datasets every ``flush_every`` steps.  There is no NumPy fallback fo
 New keyword fields (defaults keep the reference's behaviour):
     precision             "fp64" (default) | "fp32"  -- arithmetic of the pair kernel; state is always float64
     r_cutoff              None => all pairs (the reference's only working mode); a number => plain truncation
-                          at dist < r_cutoff through the cell-list / Verlet-list kernels (3-D periodic boxes
-                          with >= 3 cells per side; otherwise the all-pairs kernel applies the cutoff)
+                          at dist < r_cutoff through the cell-list / Verlet-list kernels (3-D boxes: periodic with
+                          >= 3 cells per side, or hard walls on one GPU; otherwise the all-pairs kernel applies the cutoff)
     skin                  Verlet skin of the neighbour list (default 0.3 sigma)
     flush_every           rows buffered on the device between HDF5 flushes (default: sized from memory)
     force_evals_per_step  1 (default, periodic boxes): a(t+dt) is reused as the next step's a(t);

@@ -9,6 +9,7 @@ import pytest
 
 from conftest import force_rel_err, force_rel_err_pairscale
 from oracle import oracle_c
+from test_host_cpu import in_tmp_cwd  # noqa: F401  (fixture)
 from oracle.oracle_np import MiePotential, OracleSolver, box_length, default_dt, lattice_positions, mb_velocities
 
 pytestmark = pytest.mark.gpu
@@ -455,3 +456,110 @@ def test_long_run_energy_drift_within_the_oracles(precision):
     assert exc <= 1.5 * exc_ref + 2e-6 * scale, (exc, exc_ref)
     assert slope * steps <= 2.0 * slope_ref * steps + 2e-6 * scale, (slope, slope_ref)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# hard walls (pbc=False) on the cut-off path: the box embedded in a periodic cell grid of period L + 2 (rc + skin)
+# ---------------------------------------------------------------------------------------------------
+def _walled_gas(per_row, vf=0.12, seed=5):
+    """gen.py lattice + velocities in a hard-wall box: dilute enough to move, dense enough to collide with the walls."""
+    n = per_row ** 3
+    L = box_length(3, n, 0.5, vf)
+    np.random.seed(seed)
+    r0 = lattice_positions(3, n, L)
+    v0 = mb_velocities(3, n, 1.0, 1.0, 1.0) + np.random.default_rng(seed).normal(scale=0.9, size=(3, n))
+    return n, L, r0, v0, default_dt(0.5, v0)
+
+
+def _wall_ctx(n, L, dt, precision, ring, **kw):
+    from mdsea_b200 import _capi
+
+    pot = dict(epsilon=1.0, sigma=1.0, mie_m=12.0, mie_n=6.0, mie_a=0.0, mass=1.0)
+    pot.update({k: kw.pop(k) for k in list(kw) if k in pot})
+    return _capi.Context(ndim=3, num_particles=n, boxlen=L, radius=0.5, dt=dt, pbc=0, algorithm=kw.pop("algorithm", 0), pot_kind=1,
+                         precision=precision, r_cutoff=RC, skin=SKIN, force_evals_per_step=2, ring_rows=ring, device=0,
+                         restitution=kw.pop("restitution", 1.0), **pot, **kw)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_hard_walls_take_the_cutoff_path_cells_and_lists_bit_exact(precision):
+    n, L, r0, v0, dt = _walled_gas(12)
+    rng = np.random.default_rng(11)
+    r = np.clip(r0 + rng.normal(scale=0.25, size=r0.shape), 0.5, L - 0.5)   # off the lattice, inside the walls
+    r[0, :3] = [-0.01, L + 0.02, 0.5]                                      # a drift may carry a particle past a wall
+    ctx = _wall_ctx(n, L, dt, precision, 4, max_neighbors=128)
+    ctx.set_state(r, v0)
+    Lp = L + 2.0 * (RC + SKIN)            # period of the padded cell grid (include/mdsea_b200.h, r_cutoff)
+    cell_of, order, nc = ctx.get_cells()
+    ref_cell, ref_order, ref_nc = oracle_c.cells(r, Lp, RC + SKIN)
+    assert nc == (ref_nc,) * 3
+    np.testing.assert_array_equal(cell_of, ref_cell)
+    np.testing.assert_array_equal(order, ref_order)
+    off, idx = ctx.get_neighbors()
+    ref_off, ref_idx = oracle_c.neighbors(r, Lp, RC + SKIN)
+    np.testing.assert_array_equal(off, ref_off)
+    np.testing.assert_array_equal(idx, ref_idx)
+    # no pair across the period: the list is the NON-periodic list of the walled box
+    i = np.repeat(np.arange(n), np.diff(off))
+    d = r[:, idx] - r[:, i]
+    assert (np.sqrt((d * d).sum(axis=0)) < RC + SKIN).all()
+    assert ctx.stats()["tile_lists"] == (1 if precision == 1 else 0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["plain", "gravity", "simple", "mie"])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_hard_wall_runs_match_the_numpy_oracle_with_cutoff(mode, precision):
+    """apply_hbc (clamp + reflect, simulator.py:168-179) + verlet / simple steps + gravity on the cell path against the NumPy
+    restatement of the reference with the same plain cutoff: energies of every step, final positions and velocities."""
+    n, L, r0, v0, dt = _walled_gas(10, vf=0.15)
+    steps, batch = 60, 20
+    grav = mode == "gravity"
+    algo = "simple" if mode == "simple" else "verlet"
+    potkw = dict(mie_m=9.0, mie_n=6.0, mie_a=0.3) if mode == "mie" else {}
+    pot = MiePotential(m=9.0, n=6.0, a=0.3) if mode == "mie" else MiePotential()
+    ref = OracleSolver(r=r0, v=v0, boxlen=L, dt=dt, pot=pot, pbc=False, radius=0.5, temp=1.0, kb=1.0, gravity=grav, g_acc=9.80665,
+                       algorithm=algo, r_cutoff=RC).run(steps)
+    ctx = _wall_ctx(n, L, dt, precision, batch, algorithm=1 if algo == "simple" else 0, **potkw)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r0, v0)
+    pe, ke, rr, vv = [], [], [], []
+    for _ in range(steps // batch):
+        rows = ctx.run(batch, kb=1.0, g=9.80665 if grav else 0.0)
+        pe.append(rows["pe"].copy()); ke.append(rows["ke"].copy()); rr.append(rows["r"].copy()); vv.append(rows["v"].copy())
+    pe, ke, rr, vv = np.concatenate(pe), np.concatenate(ke), np.concatenate(rr), np.concatenate(vv)
+    etol, xtol = (1e-10, 1e-9 * L) if precision == 0 else (1e-5, 1e-3)
+    np.testing.assert_allclose(pe, ref["pe"], rtol=etol, atol=etol * 1e-3)
+    np.testing.assert_allclose(ke, ref["ke"], rtol=etol)
+    assert np.abs(rr - np.array(ref["r"])).max() <= xtol
+    assert np.abs(vv - np.array(ref["v"])).max() <= (1e-9 if precision == 0 else 1e-2)
+    st = ctx.stats()
+    assert st["list_rebuilds"] >= 2                       # the cut-off path ran (the all-pairs path never rebuilds)
+    ref_r = np.array(ref["r"])   # rows hold the positions AFTER the drift: a particle past r = radius / L - radius is clamped and reflected next step
+    assert int(((ref_r < 0.5) | (ref_r > L - 0.5)).sum()) > 0, "no particle reached a wall in this run"
+    ctx.close()
+
+
+def test_hard_wall_cutoff_through_the_solver_api(in_tmp_cwd, monkeypatch):  # noqa: F811
+    """ContinuousPotentialSolver(sm(pbc=False), r_cutoff=...) -- examples/initsetup.py's scenario (bounded Mie, hard walls) at a
+    size where the cell path applies -- against the same solver without a cutoff path (all-pairs kernel with the same cutoff)."""
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+
+    out = {}
+    with config_context(k_boltzmann=1.0):
+        for tag, env in (("cells", None), ("allpairs", "1")):
+            if env:
+                monkeypatch.setenv("MDSEA_NO_WALL_CELLS", env)
+            sm = SysManager.new(simid=tag, ndim=3, num_particles=1000, steps=30, vol_fraction=0.1, radius_particle=0.5, pbc=False, temp=1)
+            np.random.seed(8)
+            sim = ContinuousPotentialSolver(sm, pot=Potential.boundedmie(a=0.2, epsilon=1, sigma=1, m=12, n=6), r_cutoff=2.5)
+            sim.run_simulation()
+            out[tag] = (sm.get_ds("pot_energy"), sm.get_ds("kin_energy"), sm.get_ds("r_coords")[-1], sim.stats()["list_rebuilds"])
+            sim.close()
+    assert out["cells"][3] >= 1 and out["allpairs"][3] == 0
+    np.testing.assert_allclose(out["cells"][0], out["allpairs"][0], rtol=1e-10)
+    np.testing.assert_allclose(out["cells"][1], out["allpairs"][1], rtol=1e-10)
+    assert np.abs(out["cells"][2] - out["allpairs"][2]).max() <= 1e-9 * sm.LEN_BOX
