@@ -72,7 +72,7 @@ typedef struct {
     double  r_cutoff;          /* <= 0: all pairs, no cutoff (the reference's only working mode).
                                   > 0 : EXTENSION -- plain truncation, pair counted iff dist < r_cutoff
                                   (strict, as simulator.py:283), cell list + Verlet list: 3-D boxes with >= 3
-                                  cells of side r_cutoff + skin per edge.  pbc = 0 (hard walls, single rank): the
+                                  cells of side r_cutoff + skin per edge.  pbc = 0 (hard walls): the
                                   box is embedded in a periodic cell grid of period boxlen + 2 (r_cutoff + skin),
                                   which is the grid mdsea_b200_get_cells reports; other boxes: all-pairs kernels */
     double  skin;              /* Verlet skin; list radius = r_cutoff + skin                    */

@@ -93,14 +93,15 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
         if (p->pbc) {
             const int nc = (int)floor(p->boxlen / rl);
             c->cutoff_path = (p->ndim == 3 && nc >= 3);
-        } else if (p->ndim == 3 && p->world == 1 && (int)floor(p->boxlen / rl) >= 1 && !getenv("MDSEA_NO_WALL_CELLS")) {
+        } else if (p->ndim == 3 && (int)floor(p->boxlen / rl) >= 1 && !getenv("MDSEA_NO_WALL_CELLS")) {
             // Hard walls (simulator.py:168-179): the box is EMBEDDED in a periodic cell grid of period L + 2 (rc + skin).  The
             // particles live in [radius, L - radius] (a drift can carry one past a wall by v dt << rc until the next clamp),
             // so two particles and their images across the period are always further apart than the list radius: the
             // periodic machinery -- binning, stencils, minimum image, 32-bit fixed-point wrap -- computes exactly the
             // non-periodic system, and nothing in the list kernels has to know about walls.  Only the boundary condition of
             // the drift kernel (clamp + reflect instead of the wrap) uses the real box.  The cells that
-            // mdsea_b200_get_cells reports are those of the padded grid.
+            // mdsea_b200_get_cells reports are those of the padded grid; with world > 1 the ranks share the PADDED grid
+            // (its outer cell layers are empty, so the outer ranks of a split dimension own fewer particles).
             b.L = p->boxlen + 2.0 * rl;
             b.invL = 1.0 / b.L;
             b.halfL = 0.5 * b.L;
@@ -112,7 +113,7 @@ extern "C" int mdsea_b200_create(const mdsea_params *p, mdsea_ctx **out) {
     }
     if (p->world > 1 && !c->cutoff_path) {
         delete c;
-        return bad(nullptr, "create: world > 1 needs the cutoff path (3-D, periodic, >= 3 cells per side); all-pairs runs are replicas only");
+        return bad(nullptr, "create: world > 1 needs the cutoff path (3-D; periodic with >= 3 cells per side, or hard walls); all-pairs runs are replicas only");
     }
     if (p->num_particles > 2000000 && !c->cutoff_path) {
         delete c;
