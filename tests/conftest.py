@@ -29,6 +29,8 @@ def _no_sticky_cuda_error(request):
     except OSError:
         return
     err = rt.cudaGetLastError()
+    if err in (35, 100):   # cudaErrorInsufficientDriver / cudaErrorNoDevice: a GPU test selected on a box without a GPU
+        return
     assert err == 0, f"{request.node.name} left CUDA error {err} behind"
 
 
