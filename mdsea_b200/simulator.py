@@ -229,6 +229,10 @@ class _BaseSimulator:
             self._device_fresh = False
 
     # -- state attributes (host views of the device state) -----------------------------------------
+    # Reading r_vec / v_vec downloads the state if the device holds a newer one and -- because the reference mutates these
+    # arrays in place (simulator.py:165-166, 194-195, 205) -- marks it as possibly edited: the next device call uploads it
+    # again.  With world > 1 the download is COLLECTIVE (every rank holds only the particles it owns and the pieces are
+    # all-reduced): read these attributes on all ranks or on none.
     @property
     def r_vec(self) -> np.ndarray:
         self._sync_to_host()

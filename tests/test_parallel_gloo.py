@@ -112,3 +112,17 @@ def test_choose_proc_grid():
     assert choose_proc_grid(8, ncells=3) == (2, 2, 2)   # y and z alone cannot hold 8 ranks of >= 1 cell
     with pytest.raises(ValueError):
         choose_proc_grid(7, ncells=3)
+
+
+def test_numa_binding_helpers_without_a_gpu(tmp_path):
+    """bench.py binds every rank to the CPUs next to its GPU before it allocates pinned row buffers: the sysfs parsing and the
+    'cannot tell' path (no device, no sysfs entry) must not raise or change the affinity."""
+    import os
+
+    from mdsea_b200.parallel import _parse_cpulist, bind_to_gpu_numa
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0, sysfs=str(tmp_path)) is None    # no CUDA device here / no such PCI function
+    assert os.sched_getaffinity(0) == before
