@@ -141,9 +141,14 @@ def run_reference_arm(args, wl):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    name = wl["name"]
     if wl["r_cutoff"] > 0:
         from oracle import oracle_c
 
+        if args.gpus > 1 and args.gpus in wl.get("per_row_by_world", {}):
+            # the SAME system our arm decomposes over args.gpus GPUs (weak scaling: ~1e6 particles per GPU), on the host cores
+            wl = dict(wl, per_row=wl["per_row_by_world"][args.gpus])
+            name = wl["name_multi"]
         res = oracle_c.bench_cutoff(wl, steps=args.steps, warmup=args.warmup)
     else:
         res = cpu_allpairs_numpy(wl, args.steps, args.warmup)
@@ -153,7 +158,8 @@ def run_reference_arm(args, wl):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "timesteps_per_s": res["md_steps"] / res["seconds"],
-        "config": {"workload": wl["name"], "md_steps_per_step": res["md_steps"] // max(args.steps, 1), "k_boltzmann": 1.0},
+        "config": {"workload": name, "particles_total": res["n"], "md_steps_per_step": res["md_steps"] // max(args.steps, 1),
+                   "k_boltzmann": 1.0},
         "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": res["cores"], "kind": "port",
                          "sample": res["sample"]},
         "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
