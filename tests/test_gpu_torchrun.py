@@ -27,6 +27,8 @@ def test_real_transports_under_torchrun(transport):
     n = _device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
+    if os.environ.get("MDSEA_TEST_TORCHRUN", "1") == "0":
+        pytest.skip("switched off (MDSEA_TEST_TORCHRUN=0)")
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
     env = dict(os.environ)
     env.pop("MDSEA_HALO", None)
