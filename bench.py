@@ -258,7 +258,10 @@ def parity_check(ctx, wl, n, L, dt, r_start, v_start, k, precision, rank, world,
            "lists_after_k_steps": {"entries": ne_end, "entries_oracle": int(ref_idx.shape[0]), "rows_that_differ": rows_diff_end,
                                    "ok": bool(end_ok)},
            "rebuilds": reb, "rebuilds_oracle": oc["rebuilds"], "rebuilds_equal": reb == oc["rebuilds"],
-           "oracle": "oracle/lj_oracle.c (float64, cell + Verlet list, same trigger)", "oracle_seconds": t_oracle}
+           "oracle": "oracle/lj_oracle.c (float64, cell + Verlet list, same trigger): the cut-off variant is THIS repository's "
+                     "extension (the reference has no working cutoff), self-pinned -- to the reference-generated golden rows through "
+                     "the all-pairs limit and to the NumPy restatement with a cutoff",
+           "oracle_seconds": t_oracle}
     out["ok"] = bool(pe_rel <= tol and ke_rel <= tol and lists_equal and end_ok and out["rebuilds_equal"])
     return out
 
@@ -544,6 +547,8 @@ def run_ours(args, wl):
                        "particles_per_gpu": n // world if decomposed else n, "md_steps_per_step": md_steps,
                        "force_evals_per_md_step": fevals / (args.steps * md_steps), "precision": precision,
                        "k_boltzmann": 1.0, "l2": "flushed between timed steps (256 MiB write)",
+                       "tolerances": "fp64 1e-10; fp32 pair math: energies 1e-5, per-particle forces 1e-5 of max(|F_i|, median|F|) on "
+                                     "liquid states (the plain metric), of max(.., sum_j |f_ij|) near a lattice (tests/conftest.py)",
                        "parallelism": "replicas only (all-pairs does not shard)" if wl["r_cutoff"] <= 0 else
                        f"dd{world} grid {PROC_GRIDS.get(world)}", "list_rebuilds_in_timed_region": int(s1["list_rebuilds"] - s0["list_rebuilds"])},
             "e2e": {"value": tot_e2e_pairs / t_e2e_max, "unit": "pair-interactions/s", "h2d_bytes_per_step": h2d,
