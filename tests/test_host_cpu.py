@@ -289,3 +289,35 @@ def test_shared_datafile_backend_is_the_memory_mapped_one(in_tmp_cwd):
     # a reopen after a close keeps the shared backend
     sm._open_datafile()
     assert isinstance(sm.dfile, hdf5min.File)
+
+
+def test_bench_row_hashes_detect_any_change_of_a_neighbour_row():
+    """bench.py compares neighbour lists of decomposed runs through one 64-bit hash per particle row (all-reduced over the ranks):
+    equal lists hash equal, a changed / missing / extra entry or a moved row boundary changes the hash of the rows it touches."""
+    import bench
+
+    rng = np.random.default_rng(0)
+    n = 500
+    cnt = rng.integers(0, 9, size=n)
+    cnt[[0, 17, n - 1]] = 0                                   # empty rows, also at the ends
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    idx = np.concatenate([np.sort(rng.choice(n, size=c, replace=False)) for c in cnt] + [np.empty(0, dtype=np.int64)]).astype(np.int32)
+    h = bench.row_hashes(off, idx, n)
+    assert h.shape == (n,) and h.dtype == np.uint64
+    np.testing.assert_array_equal(h, bench.row_hashes(off.copy(), idx.copy(), n))
+    assert (h[cnt == 0] == 0).all()
+    k = int(np.flatnonzero(cnt > 1)[3])
+    idx2 = idx.copy()
+    idx2[off[k]] = (idx2[off[k]] + 1) % n if (idx2[off[k]] + 1) % n not in idx[off[k]:off[k + 1]] else (idx2[off[k]] + 250) % n
+    h2 = bench.row_hashes(off, idx2, n)
+    assert h2[k] != h[k] and (np.delete(h2, k) == np.delete(h, k)).all()
+    # the sum over "ranks" of per-rank hashes (each rank holds only the rows it owns) equals the global hashes
+    own = rng.integers(0, 2, size=n).astype(bool)
+    parts = []
+    for mask in (own, ~own):
+        c = np.where(mask, cnt, 0)
+        o = np.concatenate([[0], np.cumsum(c)]).astype(np.int64)
+        i = np.concatenate([idx[off[p]:off[p + 1]] for p in np.flatnonzero(mask)] + [np.empty(0, dtype=np.int32)]).astype(np.int32)
+        parts.append(bench.row_hashes(o, i, n))
+    with np.errstate(over="ignore"):
+        np.testing.assert_array_equal(parts[0] + parts[1], h)
