@@ -12,7 +12,8 @@ New keyword fields (defaults keep the reference's behaviour):
     precision             "fp64" (default) | "fp32"  -- arithmetic of the pair kernel; state is always float64
     r_cutoff              None => all pairs (the reference's only working mode); a number => plain truncation
                           at dist < r_cutoff through the cell-list / Verlet-list kernels (3-D boxes: periodic with
-                          >= 3 cells per side, or hard walls on one GPU; otherwise the all-pairs kernel applies the cutoff)
+                          >= 3 cells per side, or hard walls; 2-D boxes on one GPU, run as the 3-D system (x, L/2, y);
+                          otherwise the all-pairs kernel applies the cutoff)
     skin                  Verlet skin of the neighbour list (default 0.3 sigma)
     flush_every           rows buffered on the device between HDF5 flushes (default: sized from memory)
     force_evals_per_step  1 (default, periodic boxes): a(t+dt) is reused as the next step's a(t);
@@ -23,6 +24,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -107,6 +109,8 @@ class _BaseSimulator:
         if self.precision not in _PRECISIONS:
             raise ValueError(f"precision '{self.precision}' not in {tuple(_PRECISIONS)}")
         self._ctx = None
+        self._embed = None           # 2-D system run as the 3-D system (x, L/2, y) on the cut-off path (_ensure_ctx)
+        self._nd_dev = sm.NDIM
         self._pinned = []            # page-locked row buffers of this solver (released by close())
         self._device_fresh = False   # device holds a newer state than the host copies
         self._host_exposed = True    # host arrays may have been edited -> upload before the next device op
@@ -156,19 +160,37 @@ class _BaseSimulator:
         # multi-GPU: one process per GPU (torchrun); only the cut-off path decomposes, all-pairs runs stay replicas
         rank, world = parallel.dist_info()
         self._rank, self._world = (rank, world) if (world > 1 and self.r_cutoff) else (0, 1)
+        # 2-D boxes on the cut-off path: the cell / list kernels are 3-D, so a 2-D system with a cutoff runs as the 3-D system
+        # (x, L/2, y): the padding coordinate is the same for every particle, every pair has dy' = 0 exactly, no force ever acts
+        # along it and it never changes -- r^2, forces, energies and (with the 2/3 of simulator.py:238) temperatures are those of
+        # the 2-D system; gravity acts on the LAST dimension in both (simulator.py:205).  Only the occupied layer of the cubic cell
+        # grid holds particles.  Single-rank runs; boxes whose cubic grid would not fit stay on the all-pairs kernels.
+        self._embed = None
+        if nd == 2 and self.r_cutoff and self._world == 1 and not os.environ.get("MDSEA_NO_2D_EMBED"):
+            rl = float(self.r_cutoff) + (float(self.skin) if self.skin is not None else 0.3 * sigma)
+            period = float(sm.LEN_BOX) if sm.PBC else float(sm.LEN_BOX) + 2.0 * rl
+            nc = int(period // rl)
+            if (nc >= 3 if sm.PBC else int(sm.LEN_BOX // rl) >= 1) and nc ** 3 <= 200_000_000:
+                self._embed = [0, 2]   # device dimensions that hold x and y
+        nd_dev = 3 if self._embed else nd
+        self._nd_dev = nd_dev
+        max_nbr = int(self.max_neighbors)
+        if self._embed and max_nbr == 0:   # the library sizes the lists from N / L^3, which is not this layer's density
+            rl = float(self.r_cutoff) + (float(self.skin) if self.skin is not None else 0.3 * sigma)
+            max_nbr = int(1.6 * math.pi * rl * rl * n / float(sm.LEN_BOX) ** 2) + 32
         grid = (1, 1, 1)
         if self._world > 1:
             rlist = float(self.r_cutoff) + (float(self.skin) if self.skin is not None else 0.3 * sigma)
             grid = parallel.choose_proc_grid(self._world, int(sm.LEN_BOX // rlist))
         self._ctx = _capi.Context(
             rank=self._rank, world=self._world, proc_grid=grid,
-            ndim=nd, num_particles=n, boxlen=float(sm.LEN_BOX), mass=float(sm.MASS), radius=float(sm.RADIUS_PARTICLE),
+            ndim=nd_dev, num_particles=n, boxlen=float(sm.LEN_BOX), mass=float(sm.MASS), radius=float(sm.RADIUS_PARTICLE),
             dt=float(self.dt), pbc=1 if sm.PBC else 0, algorithm=self._algorithm_code(),
             restitution=float(self.restitution_coeff), pot_kind=pp["kind"], precision=_PRECISIONS[self.precision],
             epsilon=pp["epsilon"], sigma=sigma, mie_m=pp["m"], mie_n=pp["n"], mie_a=pp["a"],
             r_cutoff=float(self.r_cutoff) if self.r_cutoff else 0.0,
             skin=float(self.skin) if self.skin is not None else 0.3 * sigma,
-            force_evals_per_step=int(fe), ring_rows=k, device=int(self.device), max_neighbors=int(self.max_neighbors),
+            force_evals_per_step=int(fe), ring_rows=k, device=int(self.device), max_neighbors=max_nbr,
         )
         if self._world > 1:
             self._ctx.comm_init(parallel.broadcast_unique_id(_capi.Context.nccl_unique_id))
@@ -204,7 +226,7 @@ class _BaseSimulator:
             pass
 
     def _new_rows(self) -> dict:
-        k, nd, width = self._k, self.sm.NDIM, self._rows_width
+        k, nd, width = self._k, self._nd_dev, self._rows_width
         keep = self._pinned
         rows = dict(r=_pinned_empty((k, nd, width), keep), v=_pinned_empty((k, nd, width), keep),
                     pe=_pinned_empty((k,), keep), ke=_pinned_empty((k,), keep), temp=_pinned_empty((k,), keep))
@@ -216,7 +238,14 @@ class _BaseSimulator:
     def _sync_to_device(self):
         ctx = self._ensure_ctx()
         if self._host_exposed:
-            ctx.set_state(self._r, self._v)
+            if self._embed:
+                n = self.sm.NUM_PARTICLES
+                r3 = np.full((3, n), 0.5 * float(self.sm.LEN_BOX), dtype=DTYPE)
+                v3 = np.zeros((3, n), dtype=DTYPE)
+                r3[self._embed], v3[self._embed] = self._r, self._v
+                ctx.set_state(r3, v3)
+            else:
+                ctx.set_state(self._r, self._v)
             self._host_exposed = False
             self._device_fresh = False
         return ctx
@@ -224,6 +253,8 @@ class _BaseSimulator:
     def _sync_to_host(self):
         if self._device_fresh and self._ctx is not None:
             self._r, self._v, self._acc, _ = self._ctx.get_state()
+            if self._embed:
+                self._r, self._v, self._acc = (np.ascontiguousarray(a[self._embed]) for a in (self._r, self._v, self._acc))
             if self._world > 1:  # every rank holds its owned entries only
                 self._r, self._v, self._acc = (parallel.assemble_owned(a) for a in (self._r, self._v, self._acc))
             self._device_fresh = False
@@ -290,6 +321,8 @@ class _BaseSimulator:
             raise ValueError(f"'{where}' is not a valid value for 'where'. Try 'inside' or 'outside' instead.")
         ctx = self._sync_to_device()
         d, u = ctx.update_dists()
+        if self._embed:
+            u = np.ascontiguousarray(u[:, self._embed])
         if radius is None:
             self.pairs_indexes = np.repeat(True, d.shape[0])
         else:
@@ -305,6 +338,8 @@ class _BaseSimulator:
                                       "use the solver's r_cutoff field instead")
         ctx = self._sync_to_device()
         self._acc, self._last_pe = ctx.update_acc()
+        if self._embed:
+            self._acc = np.ascontiguousarray(self._acc[self._embed])
         return self._acc
 
     def update_mean_pe(self):
@@ -336,7 +371,8 @@ class _BaseSimulator:
             return
         if self._world > 1:
             return np.mean(self.r_vec, axis=1)
-        return self._sync_to_device().com_rog()[0]
+        com = self._sync_to_device().com_rog()[0]
+        return com[self._embed] if self._embed else com
 
     @property
     def rog(self) -> float:
@@ -488,8 +524,12 @@ class ContinuousPotentialSolver(_BaseSimulator):
                     sm._open_datafile(shared=True)
                 parallel.scatter_rows(sm, rows, n, first, self._rank)
             else:
-                sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], first)
-                sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], first)
+                if self._embed:   # (x, pad, y) rows of the 3-D device system -> the 2-D rows of the datasets
+                    sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n][:, self._embed], first)
+                    sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n][:, self._embed], first)
+                else:
+                    sm.update_ds_block(sm.rcoord_dsname, rows["r"][:n], first)
+                    sm.update_ds_block(sm.vcoord_dsname, rows["v"][:n], first)
                 sm.update_ds_block(sm.potenergy_dsname, rows["pe"][:n], first)
                 sm.update_ds_block(sm.kinenergy_dsname, rows["ke"][:n], first)
                 sm.update_ds_block(sm.temp_dsname, rows["temp"][:n], first)

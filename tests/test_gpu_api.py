@@ -264,3 +264,37 @@ def test_boundary_and_pair_methods_of_the_base_simulator(in_tmp_cwd):  # noqa: F
         assert sim.com is None
         with pytest.raises(TypeError):
             sim.rog
+
+
+@pytest.mark.parametrize("pbc,gravity", [(True, False), (False, True)])
+def test_two_dimensional_boxes_take_the_cutoff_path(in_tmp_cwd, pbc, gravity):  # noqa: F811
+    """A 2-D system with a cutoff (the README family at sizes the all-pairs kernels cannot hold) runs as the 3-D system (x, L/2, y) on
+    the cell / list kernels: every row against the NumPy restatement of the reference (2-D, same plain cutoff)."""
+    from mdsea_b200.config import config_context
+    from mdsea_b200.core import SysManager
+    from mdsea_b200.potentials import Potential
+    from mdsea_b200.simulator import ContinuousPotentialSolver
+    from oracle.oracle_np import MiePotential, OracleSolver
+
+    steps = 40
+    with config_context(k_boltzmann=1.0):
+        sm = SysManager.new(simid="d2", ndim=2, num_particles=900, steps=steps, vol_fraction=0.25, radius_particle=0.5, pbc=pbc, temp=1)
+        np.random.seed(12)
+        sim = ContinuousPotentialSolver(sm, pot=Potential.lennardjones(1, 1), r_cutoff=2.5, gravity=gravity, flush_every=16)
+        r0, v0 = sim.r_vec.copy(), sim.v_vec.copy()
+        ref = OracleSolver(r=r0, v=v0, boxlen=sm.LEN_BOX, dt=sim.dt, pot=MiePotential(), pbc=pbc, radius=0.5, temp=1.0, kb=1.0,
+                           gravity=gravity, g_acc=9.80665, r_cutoff=2.5).run(steps)
+        sim.run_simulation()
+        st = sim.stats()
+        assert st["list_rebuilds"] >= 1 and sim._embed == [0, 2]          # the cell path ran, as a 3-D system
+        rr, vv = sm.get_ds("r_coords"), sm.get_ds("v_coords")
+        assert rr.shape == (steps, 2, 900)
+        np.testing.assert_allclose(sm.get_ds("pot_energy"), ref["pe"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(sm.get_ds("kin_energy"), ref["ke"], rtol=1e-10)
+        np.testing.assert_allclose(sm.get_ds("temp"), ref["temp"], rtol=1e-10)
+        assert np.abs(rr - np.array(ref["r"])).max() <= 1e-9 * sm.LEN_BOX
+        assert np.abs(vv - np.array(ref["v"])).max() <= 1e-9
+        # the host views are 2-D as well
+        assert sim.r_vec.shape == (2, 900) and sim.acc.shape == (2, 900)
+        np.testing.assert_allclose(sim.r_vec, rr[-1], rtol=0, atol=0)
+        sim.close()
