@@ -53,6 +53,10 @@ typedef struct {
     /* counters */
     int64_t rebuilds, pairs_unique, force_evals, list_checksum;
     double  pe_sum; /* sum over unique in-cutoff pairs of V at the last force evaluation */
+    /* hard walls (simulator.py:168-179): wall_L > 0 means that L above is only the PERIOD of the cell grid / minimum image
+     * (the product embeds a walled box [0, wall_L] in a periodic grid of period wall_L + 2 (rc + skin), include/mdsea_b200.h)
+     * and that the boundary condition of a step is clamp + reflect at [radius, wall_L - radius] instead of the wrap */
+    double  wall_L, radius, restitution;
 } lj_sys;
 
 static inline double minimg(double d, double L) { return d - rint(d / L) * L; }
@@ -336,9 +340,16 @@ void oracle_sys_forces(lj_sys *s, double *acc_out, double *mean_pe) {
 void oracle_sys_step(lj_sys *s, double *pe_out, double *ke_out) {
     const int64_t n = s->n, E = 3 * n;
     const double  L = s->L, dt = s->dt;
-    for (int64_t e = 0; e < E; ++e) { /* apply_pbc */
-        if (s->r[e] < 0) s->r[e] += L;
-        if (s->r[e] > L) s->r[e] -= L;
+    if (s->wall_L > 0) {
+        for (int64_t e = 0; e < E; ++e) { /* apply_hbc, simulator.py:168-179: two tests in this order */
+            if (s->r[e] - s->radius < 0) { s->r[e] = s->radius; s->v[e] *= -s->restitution; }
+            if (s->r[e] + s->radius > s->wall_L) { s->r[e] = s->wall_L - s->radius; s->v[e] *= -s->restitution; }
+        }
+    } else {
+        for (int64_t e = 0; e < E; ++e) { /* apply_pbc */
+            if (s->r[e] < 0) s->r[e] += L;
+            if (s->r[e] > L) s->r[e] -= L;
+        }
     }
     forces(s, 0);
     for (int64_t e = 0; e < E; ++e) {
@@ -353,6 +364,11 @@ void oracle_sys_step(lj_sys *s, double *pe_out, double *ke_out) {
     }
     if (pe_out) *pe_out = s->pe_sum / (double)n;
     if (ke_out) *ke_out = 0.5 * s->mass * ke / (double)n;
+}
+
+/* switch a system created with L = wall_L + 2 (rc + skin) to hard walls */
+void oracle_sys_set_walls(lj_sys *s, double wall_L, double radius, double restitution) {
+    s->wall_L = wall_L; s->radius = radius; s->restitution = restitution;
 }
 
 void oracle_sys_get(const lj_sys *s, double *r, double *v, double *a) {

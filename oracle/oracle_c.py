@@ -39,6 +39,8 @@ def load():
     lib.oracle_sys_list.restype = i64
     lib.oracle_sys_list.argtypes = [vp, vp, vp]
     lib.oracle_set_threads.argtypes = [C.c_int]
+    lib.oracle_sys_set_walls.argtypes = [vp, dbl, dbl, dbl]
+    lib.oracle_sys_set_walls.restype = None
     _lib = lib
     return lib
 
@@ -75,13 +77,18 @@ def neighbors(r, L, rlist, brute=False):
 class CutoffSystem:
     """Verlet-list LJ system stepped by the C oracle (two force evaluations per step, like the reference)."""
 
-    def __init__(self, r0, v0, L, rc, skin, dt, eps=1.0, sigma=1.0, mass=1.0):
+    def __init__(self, r0, v0, L, rc, skin, dt, eps=1.0, sigma=1.0, mass=1.0, walls=None):
+        """walls = (radius, restitution): hard walls at [radius, L - radius] (simulator.py:168-179).  Cells, lists and the
+        minimum image then use the PERIOD L + 2 (rc + skin) of the padded grid the product embeds the box in (self.period)."""
         self.lib = load()
         r0 = np.ascontiguousarray(r0, dtype=np.float64)
         v0 = np.ascontiguousarray(v0, dtype=np.float64)
         assert r0.shape[0] == 3
         self.n = r0.shape[1]
-        self.h = self.lib.oracle_sys_create(self.n, L, rc, skin, eps, sigma, mass, dt, _p(r0), _p(v0))
+        self.period = L if walls is None else L + 2.0 * (rc + skin)
+        self.h = self.lib.oracle_sys_create(self.n, self.period, rc, skin, eps, sigma, mass, dt, _p(r0), _p(v0))
+        if walls is not None:
+            self.lib.oracle_sys_set_walls(self.h, L, float(walls[0]), float(walls[1]))
 
     def close(self):
         if self.h:

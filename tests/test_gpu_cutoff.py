@@ -563,3 +563,39 @@ def test_hard_wall_cutoff_through_the_solver_api(in_tmp_cwd, monkeypatch):  # no
     np.testing.assert_allclose(out["cells"][0], out["allpairs"][0], rtol=1e-10)
     np.testing.assert_allclose(out["cells"][1], out["allpairs"][1], rtol=1e-10)
     assert np.abs(out["cells"][2] - out["allpairs"][2]).max() <= 1e-9 * sm.LEN_BOX
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_hard_wall_run_against_the_c_oracle_lists_and_rebuild_schedule(precision):
+    """Hard walls at a size the NumPy oracle cannot hold (20^3 particles): the C oracle with walls (padded-period construction,
+    pinned to oracle_np in tests/test_oracle_c.py) -- energies of every step, the SAME rebuild schedule, the neighbour lists in
+    force at the end bit for bit (fp64) and the unique-pair count."""
+    n, L, r0, v0, dt = _walled_gas(20, vf=0.25, seed=9)
+    steps, batch = 40, 20
+    o = oracle_c.CutoffSystem(r0, v0, L, RC, SKIN, dt, walls=(0.5, 1.0))
+    ref = o.run(steps, record=True)
+    oc = o.counters()
+    ref_off, ref_idx = o.neighbor_list()
+    o.close()
+    ctx = _wall_ctx(n, L, dt, precision, batch)
+    ctx.set_temperature(1.0)
+    ctx.set_state(r0, v0)
+    pe, ke, rr = [], [], []
+    for _ in range(steps // batch):
+        rows = ctx.run(batch, kb=1.0)
+        pe.append(rows["pe"].copy()); ke.append(rows["ke"].copy()); rr.append(rows["r"].copy())
+    pe, ke, rr = np.concatenate(pe), np.concatenate(ke), np.concatenate(rr)
+    etol = 1e-10 if precision == 0 else 1e-5
+    np.testing.assert_allclose(pe, ref["pe"], rtol=etol, atol=etol * 1e-3)
+    np.testing.assert_allclose(ke, ref["ke"], rtol=etol)
+    st = ctx.stats()
+    assert st["list_rebuilds"] == oc["rebuilds"] and oc["rebuilds"] >= 3
+    if precision == 0:
+        assert np.abs(rr - ref["r"]).max() <= 1e-9 * L
+        assert st["pair_evals_unique"] == oc["pairs_unique"]
+        off, idx = ctx.get_neighbors()
+        np.testing.assert_array_equal(off, ref_off)
+        np.testing.assert_array_equal(idx, ref_idx)
+    else:
+        assert np.abs(rr - ref["r"]).max() <= 1e-3
+    ctx.close()

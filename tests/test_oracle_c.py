@@ -83,3 +83,37 @@ def test_skin_trigger_and_rebuild_counter():
     c = s.counters()
     assert 2 <= c["rebuilds"] <= 30 and c["force_evals"] == 120
     s.close()
+
+
+def test_c_oracle_with_hard_walls_matches_the_numpy_restatement():
+    """lj_oracle.c with walls = the padded-period construction of the product (cells / lists / minimum image at period
+    L + 2 (rc + skin), clamp + reflect instead of the wrap): pinned to oracle_np (pbc=False, same plain cutoff), which is pinned
+    to the reference-generated hard-wall rows (gravity_hbc_3d, initsetup_boundedmie_hbc)."""
+    import numpy as np
+
+    from oracle import oracle_c
+    from oracle.oracle_np import MiePotential, OracleSolver, box_length, default_dt, lattice_positions, mb_velocities
+
+    n = 6 ** 3
+    L = box_length(3, n, 0.5, 0.15)
+    np.random.seed(5)
+    r0 = lattice_positions(3, n, L)
+    v0 = mb_velocities(3, n, 1.0, 1.0, 1.0) + np.random.default_rng(5).normal(scale=0.9, size=(3, n))
+    dt = default_dt(0.5, v0)
+    steps = 60
+    ref = OracleSolver(r=r0, v=v0, boxlen=L, dt=dt, pot=MiePotential(), pbc=False, radius=0.5, temp=1.0, kb=1.0, r_cutoff=2.5).run(steps)
+    o = oracle_c.CutoffSystem(r0, v0, L, 2.5, 0.3, dt, walls=(0.5, 1.0))
+    assert o.period == L + 2.0 * 2.8
+    out = o.run(steps, record=True)
+    np.testing.assert_allclose(out["pe"], ref["pe"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["ke"], ref["ke"], rtol=1e-10)
+    assert np.abs(out["r"] - np.array(ref["r"])).max() <= 1e-9 * L
+    ref_r = np.array(ref["r"])
+    assert int(((ref_r < 0.5) | (ref_r > L - 0.5)).sum()) > 0, "no particle reached a wall in this run"
+    # the list in force is the non-periodic one: no pair across the period
+    off, idx = o.neighbor_list()
+    r, _, _ = o.state()
+    i = np.repeat(np.arange(n), np.diff(off))
+    d = r[:, idx] - r[:, i]
+    assert (np.sqrt((d * d).sum(axis=0)) < 2.8 + 0.3).all()   # built within rc + skin, moved by < skin / 2 each since
+    o.close()
